@@ -1,0 +1,99 @@
+"""ctypes binding of libcalfkit_b200.so (C-ABI: include/calfkit_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or cannot be loaded the engine
+raises EngineError — the product never routes through a CPU implementation."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from calfkit.exceptions import EngineError
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+LIB_PATH = os.path.join(_PKG_ROOT, "libcalfkit_b200.so")
+
+# ---- constants mirrored from csrc/ck_common.h (checked against the header in tests/test_abi.py) ----
+CK_OK, CK_NOT_CANONICAL, CK_JSON_INVALID, CK_SCHEMA_INVALID, CK_UNSUPPORTED, CK_EMPTY = range(6)
+STATUS_NAMES = ["ok", "not_canonical", "json_invalid", "schema_invalid", "unsupported", "empty"]
+(CK_ACT_NONE, CK_ACT_RETURN, CK_ACT_SILENT, CK_ACT_RAISES, CK_ACT_CALL, CK_ACT_TAILCALL, CK_ACT_FANOUT,
+ CK_ACT_HOST_TOOL) = range(8)
+ACTION_NAMES = ["none", "return", "silent", "raises", "call", "tailcall", "fanout", "host_tool"]
+
+COLS = ["STATUS", "ACTION", "ERR", "CORR_OFF", "CORR_LEN", "NFRAMES", "FRAMES_OFF", "FRAMES_LEN", "TOP_OFF", "TOP_LEN",
+        "TGT_OFF", "TGT_LEN", "CB_OFF", "CB_LEN", "NARGS", "ARG0_OFF", "ARG0_LEN", "ARG1_OFF", "ARG1_LEN", "ARGKINDS",
+        "FOV_OFF", "FOV_LEN", "TC_OFF", "TC_LEN", "TR_OFF", "TR_LEN", "UNC_OFF", "UNC_LEN", "HIST_OFF", "HIST_LEN",
+        "FOP_OFF", "FOP_LEN", "TI_OFF", "TI_LEN", "SMETA_OFF", "SMETA_LEN", "SOV_OFF", "SOV_LEN", "PD_OFF", "PD_LEN",
+        "WFMETA_OFF", "WFMETA_LEN", "CALL_VAL_OFF", "CALL_VAL_LEN", "TNAME_OFF", "TNAME_LEN", "ARGS_OFF", "ARGS_LEN",
+        "RES_OFF", "RES_LEN", "NOUT"]
+COL = {name: i for i, name in enumerate(COLS)}
+NUM_COLS = len(COLS)
+
+KERNELS = ["walk", "plan", "scan", "emit", "route", "fanout"]
+NUM_KERNELS = len(KERNELS)
+
+PUB_DTYPE = np.dtype([("payload", "<u4"), ("topic_id", "<i4"), ("topic_off", "<u4"), ("topic_len", "<u4"),
+                      ("record", "<u4"), ("has_key", "<u4"), ("partition", "<i4"), ("pad", "<u4")])
+
+EXPORTS = ["ck_create", "ck_destroy", "ck_last_error", "ck_version", "ck_register_topics", "ck_set_tool_node", "ck_submit",
+           "ck_submit_device", "ck_tool_args", "ck_tool_plan", "ck_tool_plan_device", "ck_set_agent_node", "ck_fanout_plan",
+           "ck_sync", "ck_out_size", "ck_fetch_columns", "ck_fetch_output", "ck_fetch_topic_hist", "ck_stream",
+           "ck_device_buffers", "ck_profile", "ck_profile_read"]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} not found: build it with `python calfkit-sdk_b200/build.py` "
+                          "(there is no CPU fallback)")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:
+        raise EngineError(f"cannot load {LIB_PATH}: {e}") from e
+    vp, u8p, u32p, i32p, i64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    sig = {
+        "ck_create": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(vp)]),
+        "ck_destroy": (None, [vp]),
+        "ck_last_error": (C.c_char_p, [vp]),
+        "ck_version": (C.c_int, []),
+        "ck_register_topics": (C.c_int, [vp, u8p, u32p, C.c_uint32, i32p, C.c_uint32]),
+        "ck_set_tool_node": (C.c_int, [vp, C.c_int32, C.c_uint32, u32p, u8p, u32p]),
+        "ck_submit": (C.c_int, [vp, u8p, i64p, C.c_uint32]),
+        "ck_submit_device": (C.c_int, [vp, u8p, i64p, C.c_uint32]),
+        "ck_tool_args": (C.c_int, [vp]),
+        "ck_tool_plan": (C.c_int, [vp, u8p, i64p]),
+        "ck_tool_plan_device": (C.c_int, [vp, u8p, i64p]),
+        "ck_set_agent_node": (C.c_int, [vp, C.c_int32, u8p, C.c_uint32, u8p, C.c_uint32, u8p, u32p, u8p, u32p, C.c_uint32]),
+        "ck_fanout_plan": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32]),
+        "ck_sync": (C.c_int, [vp]),
+        "ck_out_size": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+        "ck_fetch_columns": (C.c_int, [vp, u32p]),
+        "ck_fetch_output": (C.c_int, [vp, u8p, C.c_uint64, i64p, vp]),
+        "ck_fetch_topic_hist": (C.c_int, [vp, u32p, C.c_uint32]),
+        "ck_stream": (vp, [vp]),
+        "ck_device_buffers": (C.c_int, [vp] + [C.POINTER(vp)] * 5),
+        "ck_profile": (C.c_int, [vp, C.c_int]),
+        "ck_profile_read": (C.c_int, [vp, vp, vp, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)      # AttributeError here = the library does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(a) -> int | None:
+    """address of a numpy array / torch tensor / None"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))

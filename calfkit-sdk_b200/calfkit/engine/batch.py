@@ -1,0 +1,248 @@
+"""BatchEngine: the host side of one CUDA stream's worth of the hot path.
+
+One engine = one `ck_handle` (device buffers + stream).  It replaces, batch-wise, the reference's
+per-record sandwich  bytes-in -> Envelope -> handler -> _publish_action -> bytes-out
+(reference calfkit/nodes/base.py:149-164, calfkit/worker/worker.py:45-53) for the node kinds the
+reference ships (@agent_tool nodes, Agent fan-out).  All decoding, routing and encoding happens in
+the CUDA kernels behind the C-ABI; this class only moves buffers and interprets result tables.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import string
+from dataclasses import dataclass
+from typing import Iterator, Sequence
+
+import numpy as np
+
+from calfkit.engine import _lib
+from calfkit.engine._lib import COL, NUM_COLS, PUB_DTYPE, ptr
+from calfkit.exceptions import EngineError
+
+
+@dataclass
+class ToolTemplate:
+    """A tool whose return value is a pure string template of its string arguments, e.g. the
+    quickstart's get_weather: f"It's sunny in {location}" (reference
+    examples/quickstart/weather_tool.py:9-12).  Such tools are evaluated on the device: the JSON
+    return value is assembled from pre-escaped literal pieces and the raw (already canonically
+    escaped) argument strings, so no host round trip is needed.  Anything else stays a host tool."""
+    kinds: list[int]          # 0 literal, 1 argument
+    pieces: list[bytes]       # literal bytes (JSON-escaped) or the argument's key name
+
+    @classmethod
+    def from_format(cls, fmt: str) -> "ToolTemplate":
+        kinds, pieces = [], []
+        parsed = list(string.Formatter().parse(fmt))
+        lit_acc = '"'
+        for literal, field, spec, conv in parsed:
+            lit_acc += json.dumps(literal, ensure_ascii=False)[1:-1]
+            if field is not None:
+                if spec or conv or not field.isidentifier():
+                    raise ValueError(f"unsupported template field {field!r}")
+                kinds.append(0); pieces.append(lit_acc.encode()); lit_acc = ""
+                kinds.append(1); pieces.append(json.dumps(field, ensure_ascii=False)[1:-1].encode())
+        lit_acc += '"'
+        kinds.append(0); pieces.append(lit_acc.encode())
+        return cls(kinds, pieces)
+
+
+@dataclass
+class Publish:
+    topic: str
+    key: bytes | None
+    payload: bytes
+    record: int
+    partition: int
+
+
+class BatchOutput:
+    """Result of one plan+emit: unique payloads + the publish table that references them."""
+
+    def __init__(self, engine: "BatchEngine", out: np.ndarray, out_off: np.ndarray, pubs: np.ndarray,
+                 in_data: np.ndarray | None, in_off: np.ndarray | None, cols: np.ndarray | None):
+        self.engine, self.out, self.out_off, self.pubs = engine, out, out_off, pubs
+        self.in_data, self.in_off, self.cols = in_data, in_off, cols
+
+    def payload(self, i: int) -> bytes:
+        return self.out[self.out_off[i]:self.out_off[i + 1]].tobytes()
+
+    def live(self) -> np.ndarray:
+        return self.pubs[self.pubs["payload"] != 0xFFFFFFFF]
+
+    def topic_of(self, p) -> str:
+        if p["topic_id"] >= 0:
+            return self.engine.topic_names[int(p["topic_id"])]
+        base = int(self.in_off[p["record"]]) + int(p["topic_off"])
+        raw = self.in_data[base:base + int(p["topic_len"])].tobytes()
+        return json.loads(b'"' + raw + b'"')
+
+    def key_of(self, p) -> bytes | None:
+        if not p["has_key"]:
+            return None
+        r = int(p["record"])
+        base = int(self.in_off[r]) + int(self.cols[COL["CORR_OFF"], r])
+        raw = self.in_data[base:base + int(self.cols[COL["CORR_LEN"], r])].tobytes()
+        return json.loads(b'"' + raw + b'"').encode()
+
+    def publishes(self) -> Iterator[Publish]:
+        for p in self.live():
+            yield Publish(self.topic_of(p), self.key_of(p), self.payload(int(p["payload"])), int(p["record"]),
+                          int(p["partition"]))
+
+
+class BatchEngine:
+    def __init__(self, device: int = 0, max_records: int = 1 << 16, max_in_bytes: int = 128 << 20,
+                 max_out_bytes: int | None = None, max_aux_bytes: int | None = None):
+        self.lib = _lib.load()
+        self.max_records, self.max_in = max_records, max_in_bytes
+        self.max_out = max_out_bytes if max_out_bytes is not None else max_in_bytes + 512 * max_records
+        self.max_aux = max_aux_bytes if max_aux_bytes is not None else max(1 << 20, max_in_bytes // 4)
+        h = C.c_void_p()
+        if self.lib.ck_create(device, self.max_in, self.max_out, max_records, self.max_aux, C.byref(h)):
+            raise EngineError(self.lib.ck_last_error(None).decode())
+        self.h = h
+        self.topic_names: dict[int, str] = {}
+        self.topic_ids: dict[str, int] = {}
+        self.num_partitions = 0
+        self.n = 0
+        self._in_data = self._in_off = None
+
+    # ------------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.ck_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise EngineError(self.lib.ck_last_error(self.h).decode())
+
+    # ------------------------------------------------------------------------------------------
+    def register_topics(self, names: Sequence[str], num_partitions: int = 0) -> dict[str, int]:
+        """topic string -> id table on the device (ids are positions in `names`, de-duplicated)."""
+        uniq = list(dict.fromkeys(names))
+        blob = b"".join(n.encode() for n in uniq)
+        offs = np.zeros(len(uniq) + 1, dtype=np.uint32)
+        np.cumsum([len(n.encode()) for n in uniq], out=offs[1:])
+        ids = np.arange(len(uniq), dtype=np.int32)
+        b = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.ck_register_topics(self.h, ptr(b), ptr(offs), len(uniq), ptr(ids), num_partitions))
+        self.topic_names = dict(enumerate(uniq))
+        self.topic_ids = {n: i for i, n in enumerate(uniq)}
+        self.num_partitions = num_partitions
+        return self.topic_ids
+
+    def set_tool_node(self, publish_topic: str | None, template: ToolTemplate | None = None) -> None:
+        pid = -1
+        if publish_topic is not None:
+            if publish_topic not in self.topic_ids:
+                raise EngineError(f"publish topic {publish_topic!r} is not registered")
+            pid = self.topic_ids[publish_topic]
+        if template is None:
+            self._check(self.lib.ck_set_tool_node(self.h, pid, 0, None, None, None))
+            return
+        kinds = np.asarray(template.kinds, dtype=np.uint32)
+        blob = np.frombuffer(b"".join(template.pieces) or b"\0", dtype=np.uint8)
+        offs = np.zeros(len(template.pieces) + 1, dtype=np.uint32)
+        np.cumsum([len(p) for p in template.pieces], out=offs[1:])
+        self._check(self.lib.ck_set_tool_node(self.h, pid, len(kinds), ptr(kinds), ptr(blob), ptr(offs)))
+
+    # ------------------------------------------------------------------------------------------
+    def submit(self, data: np.ndarray, offsets: np.ndarray) -> None:
+        """H2D + decode of a host batch (uint8 bytes, int64 offsets[n+1]); asynchronous."""
+        assert data.dtype == np.uint8 and offsets.dtype == np.int64
+        self.n = len(offsets) - 1
+        self._in_data, self._in_off = data, offsets
+        self._check(self.lib.ck_submit(self.h, ptr(data), ptr(offsets), self.n))
+
+    def submit_device(self, dev_data, dev_off, n: int, host_data: np.ndarray | None = None,
+                      host_off: np.ndarray | None = None) -> None:
+        """decode a batch already resident in HBM (torch tensors or raw device addresses)."""
+        self.n = n
+        self._in_data, self._in_off = host_data, host_off
+        a = dev_data if isinstance(dev_data, int) else ptr(dev_data)
+        b = dev_off if isinstance(dev_off, int) else ptr(dev_off)
+        self._check(self.lib.ck_submit_device(self.h, a, b, n))
+
+    def tool_args(self) -> tuple[np.ndarray, np.ndarray]:
+        """(blob, offsets[n+1]): the `args` JSON of every record that reaches the tool (host tools)."""
+        self._check(self.lib.ck_tool_args(self.h))
+        out, off, _ = self._fetch(want_pubs=False)
+        return out, off
+
+    def tool_plan(self, aux: np.ndarray | None = None, aux_off: np.ndarray | None = None) -> None:
+        self._check(self.lib.ck_tool_plan(self.h, ptr(aux), ptr(aux_off)))
+
+    def tool_plan_device(self, dev_aux, dev_aux_off) -> None:
+        self._check(self.lib.ck_tool_plan_device(self.h, ptr(dev_aux), ptr(dev_aux_off)))
+
+    def sync(self) -> None:
+        self._check(self.lib.ck_sync(self.h))
+
+    def columns(self) -> np.ndarray:
+        cols = np.empty((NUM_COLS, self.n), dtype=np.uint32)
+        if self.n:
+            self._check(self.lib.ck_fetch_columns(self.h, ptr(cols)))
+        return cols
+
+    def out_size(self) -> tuple[int, int, int]:
+        nb, npay, npub = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.ck_out_size(self.h, C.byref(nb), C.byref(npay), C.byref(npub)))
+        return nb.value, npay.value, npub.value
+
+    def _fetch(self, want_pubs: bool = True, out_buf: np.ndarray | None = None):
+        nb, npay, npub = self.out_size()
+        out = out_buf if out_buf is not None else np.empty(max(nb, 1), dtype=np.uint8)
+        off = np.zeros(npay + 1, dtype=np.int64)
+        pubs = np.zeros(npub if want_pubs else 0, dtype=PUB_DTYPE)
+        self._check(self.lib.ck_fetch_output(self.h, ptr(out), out.nbytes, ptr(off) if npay else None,
+                                             ptr(pubs) if (want_pubs and npub) else None))
+        return out[:nb], off, pubs
+
+    def fetch(self, out_buf: np.ndarray | None = None, with_columns: bool = True) -> BatchOutput:
+        out, off, pubs = self._fetch(out_buf=out_buf)
+        cols = self.columns() if with_columns else None
+        return BatchOutput(self, out, off, pubs, self._in_data, self._in_off, cols)
+
+    # ------------------------------------------------------------------------------------------
+    def stream_ptr(self) -> int:
+        return int(self.lib.ck_stream(self.h))
+
+    def device_buffers(self) -> dict[str, int]:
+        ps = [C.c_void_p() for _ in range(5)]
+        self._check(self.lib.ck_device_buffers(self.h, *[C.byref(p) for p in ps]))
+        return dict(zip(["in", "in_off", "out", "out_off", "cols"], [p.value for p in ps]))
+
+    def profile(self, enable: bool) -> None:
+        self._check(self.lib.ck_profile(self.h, int(enable)))
+
+    def profile_read(self, reset: bool = True) -> dict[str, tuple[float, int]]:
+        ms = np.zeros(_lib.NUM_KERNELS, dtype=np.float32)
+        cnt = np.zeros(_lib.NUM_KERNELS, dtype=np.uint32)
+        self._check(self.lib.ck_profile_read(self.h, ptr(ms), ptr(cnt), int(reset)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.KERNELS)}
+
+    # ------------------------------------------------------------------------------------------
+    def run_tool_batch(self, data: np.ndarray, offsets: np.ndarray, host_tool=None) -> BatchOutput:
+        """Convenience: one full tool-node step over a host batch.  `host_tool(args_json: bytes) ->
+        result_json: bytes` is used when the node has no device template."""
+        self.submit(data, offsets)
+        if host_tool is None:
+            self.tool_plan()
+        else:
+            blob, off = self.tool_args()
+            results = [host_tool(blob[off[i]:off[i + 1]].tobytes()) if off[i + 1] > off[i] else b""
+                       for i in range(self.n)]
+            aux_off = np.zeros(self.n + 1, dtype=np.int64)
+            np.cumsum([len(r) for r in results], out=aux_off[1:])
+            aux = np.frombuffer(b"".join(results) or b"\0", dtype=np.uint8)
+            self.tool_plan(aux, aux_off)
+        return self.fetch()

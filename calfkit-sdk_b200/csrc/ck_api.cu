@@ -1,0 +1,364 @@
+// C-ABI of libcalfkit_b200.so: handle, device buffers, stream, kernel launches.
+// See include/calfkit_b200.h for the contract and the reference call sites each entry replaces.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/calfkit_b200.h"
+#include "ck_kernels.cuh"
+
+static_assert(sizeof(ck_publish) == sizeof(ck_pub), "ck_publish must mirror ck_pub");
+
+#define CK_PAD 256   // tail padding of every byte buffer (readers may touch a few bytes past a span)
+
+static thread_local std::string g_create_error;
+
+struct ck_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t max_in = 0, max_out = 0, max_aux = 0;
+    uint32_t max_records = 0, max_payloads = 0, max_pubs = 0;
+    // device buffers
+    u8* d_in = nullptr; long long* d_in_off = nullptr;
+    u8* d_out = nullptr; long long* d_out_off = nullptr;
+    u8* d_aux = nullptr; long long* d_aux_off = nullptr;
+    u32* d_cols = nullptr; ck_out_desc* d_descs = nullptr; u32* d_pay_len = nullptr; ck_pub* d_pubs = nullptr;
+    unsigned long long* d_tile_sum = nullptr; unsigned long long* d_grand = nullptr;
+    u8* d_lit = nullptr; ck_tool_cfg* d_tool_cfg = nullptr;
+    u32* d_topic_hist = nullptr;
+    // topic table
+    ck_topic_table tab{}; u32 *d_tab_hash = nullptr, *d_tab_off = nullptr, *d_tab_len = nullptr; int32_t* d_tab_id = nullptr; u8* d_tab_names = nullptr;
+    uint32_t num_partitions = 0, hist_cap = 0;
+    // current batch
+    const u8* cur_in = nullptr; const long long* cur_in_off = nullptr;
+    uint32_t n = 0, n_payloads = 0, n_pubs = 0;
+    bool tool_set = false; ck_tool_cfg h_tool_cfg{};
+    unsigned long long* h_grand = nullptr;   // pinned
+    // profiling
+    bool profile = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float k_ms[CK_NUM_KERNELS] = {0}; uint32_t k_n[CK_NUM_KERNELS] = {0};
+};
+
+#define CUDA_TRY(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    char b_[512]; snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    (h)->err = b_; return 1; } } while (0)
+
+static int fail(ck_handle* h, const char* msg) { h->err = msg; return 1; }
+
+struct KTimer {
+    ck_handle* h; int k;
+    KTimer(ck_handle* hh, int kk) : h(hh), k(kk) { if (h->profile) cudaEventRecord(h->ev0, h->stream); }
+    ~KTimer() {
+        if (h->profile) {
+            cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1);
+            float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->k_ms[k] += ms; h->k_n[k]++;
+        }
+    }
+};
+
+extern "C" int ck_version(void) { return 1; }
+
+extern "C" const char* ck_last_error(ck_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_bytes, uint32_t max_records,
+                         uint64_t max_aux_bytes, ck_handle** out) {
+    *out = nullptr;
+    ck_handle* h = new ck_handle();
+    auto bail = [&](const char* what, cudaError_t e) {
+        char b[512]; snprintf(b, sizeof b, "ck_create: %s: %s", what, cudaGetErrorString(e));
+        g_create_error = b; ck_destroy(h); return 1;
+    };
+    cudaError_t e;
+    h->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major != 10) { g_create_error = "ck_create: this library is built for sm_100a (B200) only"; ck_destroy(h); return 1; }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    h->max_in = max_in_bytes; h->max_out = max_out_bytes; h->max_aux = max_aux_bytes; h->max_records = max_records;
+    h->max_payloads = max_records; h->max_pubs = 2 * max_records;
+#define ALLOC(p, bytes) if ((e = cudaMalloc((void**)&(p), (bytes))) != cudaSuccess) return bail("cudaMalloc " #p, e)
+    ALLOC(h->d_in, max_in_bytes + CK_PAD);
+    ALLOC(h->d_in_off, sizeof(long long) * ((size_t)max_records + 1));
+    ALLOC(h->d_out, max_out_bytes + CK_PAD);
+    ALLOC(h->d_out_off, sizeof(long long) * ((size_t)h->max_payloads + 1));
+    ALLOC(h->d_aux, max_aux_bytes + CK_PAD);
+    ALLOC(h->d_aux_off, sizeof(long long) * ((size_t)max_records + 1));
+    ALLOC(h->d_cols, sizeof(u32) * (size_t)CK_NUM_COLS * max_records);
+    ALLOC(h->d_descs, sizeof(ck_out_desc) * (size_t)h->max_payloads);
+    ALLOC(h->d_pay_len, sizeof(u32) * (size_t)h->max_payloads);
+    ALLOC(h->d_pubs, sizeof(ck_pub) * (size_t)h->max_pubs);
+    ALLOC(h->d_tile_sum, sizeof(unsigned long long) * ((size_t)h->max_payloads / CK_SCAN_TILE + 2));
+    ALLOC(h->d_grand, sizeof(unsigned long long));
+    ALLOC(h->d_lit, 4096 + CK_PAD);
+    ALLOC(h->d_tool_cfg, sizeof(ck_tool_cfg));
+    h->hist_cap = 4096;
+    ALLOC(h->d_topic_hist, sizeof(u32) * h->hist_cap);
+#undef ALLOC
+    cudaMemsetAsync(h->d_in + max_in_bytes, 0, CK_PAD, h->stream);
+    cudaMemsetAsync(h->d_topic_hist, 0, sizeof(u32) * h->hist_cap, h->stream);
+    if ((e = cudaMallocHost((void**)&h->h_grand, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("init sync", e);
+    *out = h;
+    return 0;
+}
+
+extern "C" void ck_destroy(ck_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_cols, h->d_descs, h->d_pay_len,
+                    h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
+                    h->d_tab_len, h->d_tab_id, h->d_tab_names};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_grand) cudaFreeHost(h->h_grand);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static u32 host_fnv1a(const u8* p, u32 n) { u32 h = 2166136261u; for (u32 i = 0; i < n; i++) h = (h ^ p[i]) * 16777619u; return h ? h : 1u; }
+
+extern "C" int ck_register_topics(ck_handle* h, const uint8_t* names, const uint32_t* offsets, uint32_t n,
+                                  const int32_t* ids, uint32_t num_partitions) {
+    cudaSetDevice(h->device);
+    u32 cap = 64;
+    while (cap < 4 * n) cap <<= 1;
+    std::vector<u32> th(cap, 0), toff(cap, 0), tlen(cap, 0);
+    std::vector<int32_t> tid(cap, -1);
+    for (u32 i = 0; i < n; i++) {
+        if (ids[i] < 0) return fail(h, "ck_register_topics: ids must be >= 0");
+        u32 len = offsets[i + 1] - offsets[i];
+        u32 hh = host_fnv1a(names + offsets[i], len);
+        u32 slot = hh & (cap - 1);
+        while (th[slot] != 0) {
+            if (th[slot] == hh && tlen[slot] == len && memcmp(names + toff[slot], names + offsets[i], len) == 0) break;   // duplicate name: last wins
+            slot = (slot + 1) & (cap - 1);
+        }
+        th[slot] = hh; toff[slot] = offsets[i]; tlen[slot] = len; tid[slot] = ids[i];
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    void* olds[] = {h->d_tab_hash, h->d_tab_off, h->d_tab_len, h->d_tab_id, h->d_tab_names};
+    for (void* p : olds) if (p) cudaFree(p);
+    h->d_tab_hash = h->d_tab_off = h->d_tab_len = nullptr; h->d_tab_id = nullptr; h->d_tab_names = nullptr;
+    u32 total = n ? offsets[n] : 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_tab_hash, sizeof(u32) * cap));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_tab_off, sizeof(u32) * cap));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_tab_len, sizeof(u32) * cap));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_tab_id, sizeof(int32_t) * cap));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_tab_names, (size_t)total + CK_PAD));
+    CUDA_TRY(h, cudaMemcpy(h->d_tab_hash, th.data(), sizeof(u32) * cap, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_tab_off, toff.data(), sizeof(u32) * cap, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_tab_len, tlen.data(), sizeof(u32) * cap, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_tab_id, tid.data(), sizeof(int32_t) * cap, cudaMemcpyHostToDevice));
+    if (total) CUDA_TRY(h, cudaMemcpy(h->d_tab_names, names, total, cudaMemcpyHostToDevice));
+    h->tab.cap = cap; h->tab.hash = h->d_tab_hash; h->tab.id = h->d_tab_id; h->tab.name_off = h->d_tab_off;
+    h->tab.name_len = h->d_tab_len; h->tab.names = h->d_tab_names;
+    h->num_partitions = num_partitions;
+    return 0;
+}
+
+extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t nparts, const uint32_t* kinds,
+                                const uint8_t* blob, const uint32_t* part_offsets) {
+    cudaSetDevice(h->device);
+    if (nparts > CK_TPL_MAX_PARTS) return fail(h, "ck_set_tool_node: too many template parts");
+    std::vector<u8> pool;
+    auto put = [&](const char* s, uint32_t out[2]) { out[0] = (u32)pool.size(); out[1] = (u32)strlen(s); pool.insert(pool.end(), s, s + strlen(s)); };
+    ck_tool_cfg c{};
+    c.publish_topic_id = publish_topic_id;
+    put(",\"", c.lit_comma_q); put("\"", c.lit_q); put("\":{\"return_value\":", c.lit_open);
+    put(",\"content\":null,\"metadata\":{\"tool_call_id\":\"", c.lit_mid); put("\"},\"kind\":\"tool-return\"}", c.lit_close);
+    put("{\"return_value\":", c.lit_value_open);
+    c.tpl_nparts = nparts;
+    for (u32 k = 0; k < nparts; k++) {
+        c.tpl_kind[k] = kinds[k]; c.tpl_off[k] = (u32)pool.size(); c.tpl_len[k] = part_offsets[k + 1] - part_offsets[k];
+        pool.insert(pool.end(), blob + part_offsets[k], blob + part_offsets[k + 1]);
+    }
+    if (pool.size() > 4096) return fail(h, "ck_set_tool_node: literal pool overflow");
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(h->d_lit, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_tool_cfg, &c, sizeof c, cudaMemcpyHostToDevice));
+    h->h_tool_cfg = c; h->tool_set = true;
+    return 0;
+}
+
+static int launch_walk(ck_handle* h) {
+    KTimer t(h, CK_K_WALK);
+    if (h->n) ck_walk_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* host_off, uint32_t n) {
+    cudaSetDevice(h->device);
+    if (n > h->max_records) return fail(h, "ck_submit: batch has more records than max_records");
+    uint64_t nbytes = n ? (uint64_t)(host_off[n] - host_off[0]) : 0;
+    if (n && host_off[0] != 0) return fail(h, "ck_submit: offsets must start at 0");
+    if (nbytes > h->max_in) return fail(h, "ck_submit: batch larger than max_in_bytes");
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_in, host_in, nbytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_in_off, host_off, sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_in + nbytes, 0, 16, h->stream));
+    h->cur_in = h->d_in; h->cur_in_off = h->d_in_off; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
+    return launch_walk(h);
+}
+
+extern "C" int ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n) {
+    cudaSetDevice(h->device);
+    if (n > h->max_records) return fail(h, "ck_submit_device: batch has more records than max_records");
+    h->cur_in = dev_in; h->cur_in_off = (const long long*)dev_off; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
+    return launch_walk(h);
+}
+
+static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
+    u32 ntiles = (npay + CK_SCAN_TILE - 1) / CK_SCAN_TILE;
+    {
+        KTimer t(h, CK_K_SCAN);
+        if (npay) {
+            ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_pay_len, npay, h->d_tile_sum);
+            ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_tile_sum, ntiles, h->d_grand);
+            ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_pay_len, npay, h->d_tile_sum, h->d_out_off);
+        }
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    {
+        KTimer t(h, CK_K_EMIT);
+        if (npay) {
+            u32 warps_per_block = 256 / 32;
+            ck_emit_kernel<<<(npay + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(
+                h->cur_in, h->cur_in_off, h->d_lit, aux, h->d_descs, h->d_out_off, npay, h->d_out, (long long)h->max_out);
+        }
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    h->n_payloads = npay;
+    return 0;
+}
+
+extern "C" int ck_tool_args(ck_handle* h) {
+    cudaSetDevice(h->device);
+    if (!h->tool_set) return fail(h, "ck_tool_args: call ck_set_tool_node first");
+    {
+        KTimer t(h, CK_K_PLAN);
+        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
+            h->d_tool_cfg, h->d_lit, nullptr, 0, h->d_descs, h->d_pay_len, h->d_pubs);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    h->n_pubs = 0;
+    return scan_emit(h, h->n, nullptr);
+}
+
+static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_off) {
+    if (!h->tool_set) return fail(h, "ck_tool_plan: call ck_set_tool_node first");
+    if (h->h_tool_cfg.tpl_nparts == 0 && aux_off == nullptr) return fail(h, "ck_tool_plan: node has no device template, host results required");
+    {
+        KTimer t(h, CK_K_PLAN);
+        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
+            h->d_tool_cfg, h->d_lit, aux_off, 1, h->d_descs, h->d_pay_len, h->d_pubs);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    // NOTE: payload sizes are bounded by in + per-record constant; the caller sizes max_out accordingly
+    if (scan_emit(h, h->n, aux)) return 1;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        u32 npubs = 2 * h->n;
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->d_cols, h->n, h->d_pubs, npubs,
+            h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
+        CUDA_TRY(h, cudaGetLastError());
+        h->n_pubs = npubs;
+    }
+    return 0;
+}
+
+extern "C" int ck_tool_plan(ck_handle* h, const uint8_t* host_aux, const int64_t* host_aux_off) {
+    cudaSetDevice(h->device);
+    if (host_aux_off) {
+        uint64_t nb = (uint64_t)host_aux_off[h->n];
+        if (nb > h->max_aux) return fail(h, "ck_tool_plan: results larger than max_aux_bytes");
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_aux, host_aux, nb, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_aux_off, host_aux_off, sizeof(long long) * ((size_t)h->n + 1), cudaMemcpyHostToDevice, h->stream));
+        return tool_plan_common(h, h->d_aux, h->d_aux_off);
+    }
+    return tool_plan_common(h, nullptr, nullptr);
+}
+
+extern "C" int ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const int64_t* dev_aux_off) {
+    cudaSetDevice(h->device);
+    return tool_plan_common(h, dev_aux, (const long long*)dev_aux_off);
+}
+
+extern "C" int ck_set_agent_node(ck_handle* h, int32_t, const uint8_t*, uint32_t, const uint8_t*, uint32_t,
+                                 const uint8_t*, const uint32_t*, const uint8_t*, const uint32_t*, uint32_t) {
+    return fail(h, "ck_set_agent_node: not built yet");
+}
+extern "C" int ck_fanout_plan(ck_handle* h, uint64_t, uint64_t, uint32_t) { return fail(h, "ck_fanout_plan: not built yet"); }
+
+extern "C" int ck_sync(ck_handle* h) {
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int ck_out_size(ck_handle* h, uint64_t* out_bytes, uint32_t* n_payloads, uint32_t* n_publishes) {
+    cudaSetDevice(h->device);
+    *h->h_grand = 0;
+    if (h->n_payloads) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_grand, h->d_grand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (out_bytes) *out_bytes = *h->h_grand;
+    if (n_payloads) *n_payloads = h->n_payloads;
+    if (n_publishes) *n_publishes = h->n_pubs;
+    return 0;
+}
+
+extern "C" int ck_fetch_columns(ck_handle* h, uint32_t* host_cols) {
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(host_cols, h->d_cols, sizeof(u32) * (size_t)CK_NUM_COLS * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, ck_publish* host_pubs) {
+    cudaSetDevice(h->device);
+    uint64_t total = 0;
+    if (ck_out_size(h, &total, nullptr, nullptr)) return 1;
+    if (total > cap) return fail(h, "ck_fetch_output: host buffer too small");
+    if (total > h->max_out) return fail(h, "ck_fetch_output: device output buffer overflowed (raise max_out_bytes)");
+    if (host_out && total) CUDA_TRY(h, cudaMemcpyAsync(host_out, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
+    if (host_out_off && h->n_payloads) CUDA_TRY(h, cudaMemcpyAsync(host_out_off, h->d_out_off, sizeof(long long) * ((size_t)h->n_payloads + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (host_pubs && h->n_pubs) CUDA_TRY(h, cudaMemcpyAsync(host_pubs, h->d_pubs, sizeof(ck_pub) * (size_t)h->n_pubs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int ck_fetch_topic_hist(ck_handle* h, uint32_t* host_hist, uint32_t n) {
+    cudaSetDevice(h->device);
+    if (n > h->hist_cap) n = h->hist_cap;
+    CUDA_TRY(h, cudaMemcpyAsync(host_hist, h->d_topic_hist, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" void* ck_stream(ck_handle* h) { return (void*)h->stream; }
+
+extern "C" int ck_device_buffers(ck_handle* h, void** in, void** in_off, void** out, void** out_off, void** cols) {
+    if (in) *in = h->d_in;
+    if (in_off) *in_off = h->d_in_off;
+    if (out) *out = h->d_out;
+    if (out_off) *out_off = h->d_out_off;
+    if (cols) *cols = h->d_cols;
+    return 0;
+}
+
+extern "C" int ck_profile(ck_handle* h, int enable) { h->profile = enable != 0; return 0; }
+
+extern "C" int ck_profile_read(ck_handle* h, float* ms, uint32_t* launches, int reset) {
+    for (int k = 0; k < CK_NUM_KERNELS; k++) { ms[k] = h->k_ms[k]; launches[k] = h->k_n[k]; if (reset) { h->k_ms[k] = 0; h->k_n[k] = 0; } }
+    return 0;
+}

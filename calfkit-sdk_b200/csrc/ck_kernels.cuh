@@ -1,0 +1,456 @@
+// sm_100a kernels of the calfkit-b200 hot path.  No tensor cores: the path has no dense
+// contraction; everything here is HBM-bound byte/integer work.
+//
+//   ck_walk_kernel        decode: prove each record is a canonical Envelope + extract spans   (a2,a3,a4)
+//   ck_plan_tool_kernel   ToolNodeDef.run + _publish_action(ReturnCall|Silent) as a splice plan  (a5,a6)
+//   ck_plan_fanout_kernel Agent fan-out: one Call envelope per pending tool call               (a9,a6)
+//   ck_scan_*             exclusive prefix sum of payload lengths -> output offsets
+//   ck_emit_kernel        encode: gather segments into contiguous output payloads               (a7)
+//   ck_route_kernel       topic string -> registered topic id, Kafka partition of the key        (a8)
+#ifndef CK_KERNELS_CUH
+#define CK_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include "ck_walk.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// node configuration living in device memory
+// ------------------------------------------------------------------------------------------------
+#define CK_TPL_MAX_PARTS 6
+struct ck_tool_cfg {
+    int32_t  publish_topic_id;          // registered id of node.publish_topic, -1 = none
+    uint32_t tpl_nparts;                // 0 = results come from the host (aux blob)
+    uint32_t tpl_kind[CK_TPL_MAX_PARTS];   // 0: literal (lit pool span)  1: string argument (lit pool span = key name)
+    uint32_t tpl_off[CK_TPL_MAX_PARTS];
+    uint32_t tpl_len[CK_TPL_MAX_PARTS];
+    // fixed literals in the pool (offset, length)
+    uint32_t lit_comma_q[2];            // ,"
+    uint32_t lit_q[2];                  // "
+    uint32_t lit_open[2];               // ":{"return_value":
+    uint32_t lit_mid[2];                // ,"content":null,"metadata":{"tool_call_id":"
+    uint32_t lit_close[2];              // "},"kind":"tool-return"}
+    uint32_t lit_value_open[2];         // {"return_value":
+};
+
+struct ck_pub {                          // one publish (nodes/base.py:82-87; worker/worker.py:52-53)
+    uint32_t payload;                    // index of the payload descriptor, 0xffffffff = no publish
+    int32_t  topic_id;                   // >= 0 resolved; -1: unresolved, see topic_off/len
+    uint32_t topic_off, topic_len;       // topic string span inside the input record
+    uint32_t record;                     // source record
+    uint32_t has_key;                    // key = correlation id bytes
+    int32_t  partition;                  // murmur2(key) % num_partitions, -1 if unkeyed
+    uint32_t pad;
+};
+
+struct ck_topic_table {                  // open addressing, power-of-two capacity
+    uint32_t cap;
+    const uint32_t* hash;                // 0 = empty slot
+    const int32_t*  id;
+    const uint32_t* name_off;            // into names
+    const uint32_t* name_len;
+    const uint8_t*  names;
+};
+
+__device__ __forceinline__ u32 ck_fnv1a(const u8* p, u32 n) {
+    u32 h = 2166136261u;
+    for (u32 i = 0; i < n; i++) h = (h ^ p[i]) * 16777619u;
+    return h ? h : 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long a = off[i], b = off[i + 1];
+    WalkOut o;
+#pragma unroll
+    for (int k = 0; k < CK_NUM_COLS; k++) o.c[k] = 0;
+    u32 len = (u32)(b - a);
+    u32 status, stop = 0;
+    if (len == 0) status = CK_EMPTY;
+    else {
+        Rd r; r.init(in + a, len);
+        AnyCtx cx;
+        cx.kfill = 0;
+        status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_NOT_CANONICAL;
+    }
+    o.c[CK_COL_STATUS] = status;
+    o.c[CK_COL_ERR] = stop;
+    // SoA store: lane i of a warp writes cols[k][i] -> 128 contiguous bytes per column per warp
+#pragma unroll
+    for (int k = 0; k < CK_COL_CALL_VAL_OFF; k++) cols[(size_t)k * stride + i] = o.c[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers on validated canonical spans
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ck_span_eq(Rd& r, u32 a, u32 b, u32 len) {
+    for (u32 k = 0; k < len; k++) if (r.at(a + k) != r.at(b + k)) return false;
+    return true;
+}
+
+// look `key` (content span) up in the canonical dict object starting at `obj` ('{'); returns the
+// value span, len 0 if absent
+__device__ __forceinline__ Span ck_dict_find(Rd& r, u32 obj, u32 key_off, u32 key_len) {
+    u32 pos = obj + 1;
+    Span none = {0, 0};
+    while (pos < r.n && r.at(pos) != '}') {
+        Span k;
+        if (!ck_string(r, pos, k)) return none;
+        pos++;                                   // ':'
+        u32 v = pos;
+        ck_skip_value(r, pos);
+        if (k.len == key_len && ck_span_eq(r, k.off, key_off, key_len)) { Span s = {v, pos - v}; return s; }
+        if (pos < r.n && r.at(pos) == ',') pos++;
+    }
+    return none;
+}
+
+struct SegWriter {
+    ck_out_desc* d;
+    u32 n, total;
+    __device__ __forceinline__ void init(ck_out_desc* dd) { d = dd; n = 0; total = 0; }
+    __device__ __forceinline__ void add(u32 src, u32 off, u32 len) {
+        if (len == 0) return;
+        if (n > 0 && src == (d->len_src[n - 1] & 3u) && d->src_off[n - 1] + (d->len_src[n - 1] >> 2) == off) {
+            d->len_src[n - 1] += len << 2;        // contiguous with the previous segment: merge
+        } else if (n < CK_MAX_SEGS) {
+            d->src_off[n] = off; d->len_src[n] = (len << 2) | src; n++;
+        } else { n = CK_MAX_SEGS + 1; }
+        total += len;
+    }
+    __device__ __forceinline__ bool finish(u32 record) {
+        d->nseg = n; d->record = record; d->total_len = total;
+        return n <= CK_MAX_SEGS;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// tool node: ToolNodeDef.run (reference nodes/tool.py:37-86) + handler dispatch rule
+// (nodes/base.py:157-160) + _publish_action(ReturnCall | Silent) (nodes/base.py:105-118,137-145)
+// + prepare_context's overrides rule (nodes/base.py:66-67), expressed as a splice plan.
+//   mode 0: classify + locate the tool call; payload = the args JSON span (1 segment) so a host
+//           tool can be given its arguments (only used when the node has no device template)
+//   mode 1: classify + build the final payload from the device template or the host's results (aux)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
+                    const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
+                    const long long* __restrict__ aux_off,    // per record [n+1] spans of the host results blob, or NULL
+                    int mode, ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#define COL(k) cols[(size_t)(k) * stride + i]
+    const ck_tool_cfg& cfg = *cfgp;
+    ck_pub none; none.payload = 0xffffffffu; none.topic_id = -1; none.topic_off = none.topic_len = 0; none.record = i;
+    none.has_key = 0; none.partition = -1; none.pad = 0;
+    ck_out_desc* d = descs + i;
+    u32 status = COL(CK_COL_STATUS);
+    u32 action = CK_ACT_NONE;
+    long long a = off[i];
+    Rd r; r.init(in + a, (u32)(off[i + 1] - a));
+    pubs[2 * i] = none; pubs[2 * i + 1] = none;
+    pay_len[i] = 0; d->nseg = 0; d->total_len = 0; d->record = i;
+    if (status != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; COL(CK_COL_NOUT) = 0; return; }
+
+    u32 nframes = COL(CK_COL_NFRAMES), nargs = COL(CK_COL_NARGS), kinds = COL(CK_COL_ARGKINDS);
+    SegWriter w; w.init(d);
+    Span call = {0, 0};
+    if (nframes == 0 || nargs != 2) action = CK_ACT_RAISES;       // peek on empty stack / run() arity TypeError
+    else if (!(kinds & 1u)) {
+        u8 c0 = r.at(COL(CK_COL_ARG0_OFF));
+        action = (c0 == '[' || c0 == '{') ? CK_ACT_RAISES : CK_ACT_SILENT;   // unhashable key raises; other scalars miss
+    } else {
+        call = ck_dict_find(r, COL(CK_COL_TC_OFF), COL(CK_COL_ARG0_OFF), COL(CK_COL_ARG0_LEN));
+        action = call.len ? CK_ACT_RETURN : CK_ACT_SILENT;
+    }
+    if (action == CK_ACT_RAISES) { COL(CK_COL_ACTION) = action; COL(CK_COL_NOUT) = 0; return; }
+    if (action == CK_ACT_SILENT) {
+        if (mode == 0) { COL(CK_COL_ACTION) = action; COL(CK_COL_NOUT) = 0; return; }
+        // only the handler-return publish: the input envelope, unchanged (nodes/base.py:142, worker.py:52-53)
+        w.add(CK_SRC_INPUT, 0, r.n);
+        w.finish(i);
+        pay_len[i] = cfg.publish_topic_id >= 0 ? r.n : 0;
+        if (cfg.publish_topic_id >= 0) { ck_pub p = none; p.payload = i; p.topic_id = cfg.publish_topic_id; pubs[2 * i + 1] = p; }
+        COL(CK_COL_ACTION) = action; COL(CK_COL_NOUT) = cfg.publish_topic_id >= 0 ? 1 : 0;
+        return;
+    }
+    // ---- the ToolCallPart: {"tool_name":S,"args":V,...
+    u32 pos = call.off + 13;                      // past {"tool_name":
+    Span tname; ck_string(r, pos, tname);
+    pos += 8;                                     // past ,"args":
+    u32 args0 = pos; ck_skip_value(r, pos);
+    Span args = {args0, pos - args0};
+    COL(CK_COL_CALL_VAL_OFF) = call.off; COL(CK_COL_CALL_VAL_LEN) = call.len;
+    COL(CK_COL_TNAME_OFF) = tname.off; COL(CK_COL_TNAME_LEN) = tname.len;
+    COL(CK_COL_ARGS_OFF) = args.off; COL(CK_COL_ARGS_LEN) = args.len;
+    u32 id_off = COL(CK_COL_ARG0_OFF), id_len = COL(CK_COL_ARG0_LEN);
+    Span existing = ck_dict_find(r, COL(CK_COL_TR_OFF), id_off, id_len);
+    COL(CK_COL_RES_OFF) = existing.off; COL(CK_COL_RES_LEN) = existing.len;
+
+    // ---- the tool's return value as JSON
+    u32 rv_src[CK_TPL_MAX_PARTS], rv_off[CK_TPL_MAX_PARTS], rv_len[CK_TPL_MAX_PARTS], rv_n = 0;
+    if (mode == 0) {
+        // hand the args span to the host: payload = args JSON (1 segment); results come back in mode 1
+        w.add(CK_SRC_INPUT, args.off, args.len);
+        w.finish(i);
+        pay_len[i] = args.len;
+        COL(CK_COL_ACTION) = CK_ACT_HOST_TOOL; COL(CK_COL_NOUT) = 0;
+        return;
+    }
+    if (cfg.tpl_nparts == 0) {
+        if (aux_off == nullptr) { COL(CK_COL_ACTION) = CK_ACT_HOST_TOOL; COL(CK_COL_NOUT) = 0; return; }
+        long long r0 = aux_off[i], r1 = aux_off[i + 1];
+        rv_src[0] = CK_SRC_AUX; rv_off[0] = (u32)r0; rv_len[0] = (u32)(r1 - r0); rv_n = 1;
+    } else {
+        // device template: literal pieces + raw string arguments of the (object) args
+        bool ok = (r.at(args.off) == '{');
+        for (u32 k = 0; k < cfg.tpl_nparts && ok; k++) {
+            if (cfg.tpl_kind[k] == 0) { rv_src[rv_n] = CK_SRC_LIT; rv_off[rv_n] = cfg.tpl_off[k]; rv_len[rv_n] = cfg.tpl_len[k]; rv_n++; }
+            else {
+                // find member by name in the args object
+                u32 p = args.off + 1; bool found = false;
+                while (p < args.off + args.len && r.at(p) != '}') {
+                    Span k2; ck_string(r, p, k2); p++;
+                    u32 v = p; ck_skip_value(r, p);
+                    bool eq = (k2.len == cfg.tpl_len[k]);
+                    for (u32 b = 0; eq && b < k2.len; b++) eq = (r.at(k2.off + b) == lit[cfg.tpl_off[k] + b]);
+                    if (eq) {
+                        if (r.at(v) != '"') { ok = false; break; }          // non-string argument: host formats it
+                        rv_src[rv_n] = CK_SRC_INPUT; rv_off[rv_n] = v + 1; rv_len[rv_n] = p - v - 2; rv_n++;
+                        found = true; break;
+                    }
+                    if (p < r.n && r.at(p) == ',') p++;
+                }
+                if (!found) ok = false;
+            }
+        }
+        if (!ok) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_STATUS) = CK_UNSUPPORTED; COL(CK_COL_NOUT) = 0; return; }
+    }
+
+    // ---- splice plan
+    u32 tr_off = COL(CK_COL_TR_OFF), tr_len = COL(CK_COL_TR_LEN);
+    u32 cur;
+    if (existing.len == 0) {
+        w.add(CK_SRC_INPUT, 0, tr_off + tr_len - 1);                         // up to (not incl.) the closing '}'
+        if (tr_len > 2) w.add(CK_SRC_LIT, cfg.lit_comma_q[0], cfg.lit_comma_q[1]); else w.add(CK_SRC_LIT, cfg.lit_q[0], cfg.lit_q[1]);
+        w.add(CK_SRC_INPUT, id_off, id_len);
+        w.add(CK_SRC_LIT, cfg.lit_open[0], cfg.lit_open[1]);
+        cur = tr_off + tr_len - 1;
+    } else {
+        w.add(CK_SRC_INPUT, 0, existing.off);                                // dict assignment keeps the key's position
+        w.add(CK_SRC_LIT, cfg.lit_value_open[0], cfg.lit_value_open[1]);
+        cur = existing.off + existing.len;
+    }
+    for (u32 k = 0; k < rv_n; k++) w.add(rv_src[k], rv_off[k], rv_len[k]);
+    w.add(CK_SRC_LIT, cfg.lit_mid[0], cfg.lit_mid[1]);
+    w.add(CK_SRC_INPUT, id_off, id_len);
+    w.add(CK_SRC_LIT, cfg.lit_close[0], cfg.lit_close[1]);
+    // state.overrides <- current frame's overrides when that is set (nodes/base.py:66-67)
+    u32 fov_off = COL(CK_COL_FOV_OFF), fov_len = COL(CK_COL_FOV_LEN);
+    if (r.at(fov_off) != 'n') {
+        u32 sov_off = COL(CK_COL_SOV_OFF), sov_len = COL(CK_COL_SOV_LEN);
+        w.add(CK_SRC_INPUT, cur, sov_off - cur);
+        w.add(CK_SRC_INPUT, fov_off, fov_len);
+        cur = sov_off + sov_len;
+    }
+    // unwind the current frame (nodes/base.py:107): drop the last list element and its comma
+    u32 top_off = COL(CK_COL_TOP_OFF), top_len = COL(CK_COL_TOP_LEN);
+    u32 cut0 = nframes > 1 ? top_off - 1 : top_off;
+    w.add(CK_SRC_INPUT, cur, cut0 - cur);
+    w.add(CK_SRC_INPUT, top_off + top_len, r.n - (top_off + top_len));
+    if (!w.finish(i)) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_STATUS) = CK_UNSUPPORTED; COL(CK_COL_NOUT) = 0; d->nseg = 0; d->total_len = 0; return; }
+    pay_len[i] = w.total;
+    // publishes: callback (keyed by correlation id), then the handler return value to publish_topic
+    ck_pub p = none; p.payload = i; p.topic_off = COL(CK_COL_CB_OFF); p.topic_len = COL(CK_COL_CB_LEN); p.has_key = 1;
+    pubs[2 * i] = p;
+    u32 nout = 1;
+    if (cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = i; q.topic_id = cfg.publish_topic_id; pubs[2 * i + 1] = q; nout = 2; }
+    COL(CK_COL_ACTION) = CK_ACT_RETURN; COL(CK_COL_NOUT) = nout;
+#undef COL
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan u32 -> int64 (three small kernels; lengths are tiny next to the payload bytes)
+// ------------------------------------------------------------------------------------------------
+#define CK_SCAN_BLOCK 256
+#define CK_SCAN_ITEMS 8
+#define CK_SCAN_TILE (CK_SCAN_BLOCK * CK_SCAN_ITEMS)
+
+__device__ __forceinline__ unsigned long long ck_block_scan_excl(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long wsum[CK_SCAN_BLOCK / 32];
+    u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = lane < CK_SCAN_BLOCK / 32 ? wsum[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += y; }
+        if (lane < CK_SCAN_BLOCK / 32) wsum[lane] = s;
+    }
+    __syncthreads();
+    unsigned long long base = wid ? wsum[wid - 1] : 0;
+    *total = wsum[CK_SCAN_BLOCK / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(CK_SCAN_BLOCK)
+ck_scan_tiles_kernel(const u32* __restrict__ len, u32 n, unsigned long long* __restrict__ tile_sum) {
+    u32 base = blockIdx.x * CK_SCAN_TILE + threadIdx.x * CK_SCAN_ITEMS;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < CK_SCAN_ITEMS; k++) if (base + k < n) s += len[base + k];
+    unsigned long long total;
+    ck_block_scan_excl(s, &total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(CK_SCAN_BLOCK)
+ck_scan_sums_kernel(unsigned long long* __restrict__ tile_sum, u32 ntiles, unsigned long long* __restrict__ grand) {
+    unsigned long long carry = 0;
+    for (u32 base = 0; base < ntiles; base += CK_SCAN_BLOCK) {
+        u32 i = base + threadIdx.x;
+        unsigned long long v = i < ntiles ? tile_sum[i] : 0, total;
+        unsigned long long e = ck_block_scan_excl(v, &total);
+        if (i < ntiles) tile_sum[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+
+__global__ void __launch_bounds__(CK_SCAN_BLOCK)
+ck_scan_apply_kernel(const u32* __restrict__ len, u32 n, const unsigned long long* __restrict__ tile_sum,
+                     long long* __restrict__ out_off /* n+1 */) {
+    u32 base = blockIdx.x * CK_SCAN_TILE + threadIdx.x * CK_SCAN_ITEMS;
+    u32 v[CK_SCAN_ITEMS];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < CK_SCAN_ITEMS; k++) { v[k] = (base + k < n) ? len[base + k] : 0; s += v[k]; }
+    unsigned long long total;
+    unsigned long long e = ck_block_scan_excl(s, &total) + tile_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < CK_SCAN_ITEMS; k++) { if (base + k < n) out_off[base + k] = (long long)e; e += v[k]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == CK_SCAN_BLOCK - 1) out_off[n] = (long long)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode: one warp per payload gathers its segments into out[out_off[i] ...)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ck_warp_copy(u8* __restrict__ dst, const u8* __restrict__ src, u32 len, u32 lane) {
+    // head to 4-byte destination alignment
+    u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > len) head = len;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; len -= head;
+    u32 nw = len >> 2;
+    u32 sh = (u32)((uintptr_t)src & 3);
+    const u32* s4 = (const u32*)((uintptr_t)src - sh);
+    u32* d4 = (u32*)dst;
+    if (sh == 0) {
+        for (u32 k = lane; k < nw; k += 32) d4[k] = __ldg(s4 + k);
+    } else {
+        u32 bits = sh * 8;
+        for (u32 k = lane; k < nw; k += 32) {
+            u32 lo = __ldg(s4 + k), hi = __ldg(s4 + k + 1);     // hi may touch up to 3 bytes past the segment: inside the padded buffers
+            d4[k] = __funnelshift_r(lo, hi, bits);
+        }
+    }
+    u32 done = nw << 2;
+    u32 tail = len - done;
+    if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+__global__ void __launch_bounds__(256)
+ck_emit_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, const u8* __restrict__ lit,
+               const u8* __restrict__ aux, const ck_out_desc* __restrict__ descs, const long long* __restrict__ out_off,
+               u32 n, u8* __restrict__ out, long long out_cap) {
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    long long o0 = out_off[warp], o1 = out_off[warp + 1];
+    if (o1 == o0 || o1 > out_cap) return;    // overflow is reported by ck_fetch_output, never written
+    const ck_out_desc* d = descs + warp;
+    u32 nseg = d->nseg;
+    // lanes 0..nseg-1 fetch one segment descriptor each, then broadcast
+    u32 my_off = lane < nseg ? d->src_off[lane] : 0, my_ls = lane < nseg ? d->len_src[lane] : 0;
+    const u8* rec = in + in_off[d->record];
+    u8* dst = out + o0;
+    for (u32 s = 0; s < nseg; s++) {
+        u32 so = __shfl_sync(0xffffffffu, my_off, s), ls = __shfl_sync(0xffffffffu, my_ls, s);
+        u32 len = ls >> 2, src = ls & 3u;
+        const u8* sp = (src == CK_SRC_INPUT) ? rec + so : (src == CK_SRC_LIT ? lit + so : aux + so);
+        ck_warp_copy(dst, sp, len, lane);
+        dst += len;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// route: destination topic string -> registered topic id (hash probe + byte compare), Kafka
+// partition of the key (murmur2, the default partitioner's hash), and a per-topic histogram
+// aggregated inside the warp (match_any + popc: one atomic per distinct topic per warp).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 ck_murmur2(const u8* data, u32 len) {
+    const u32 m = 0x5bd1e995u; const int rr = 24;
+    u32 h = 0x9747b28cu ^ len;
+    u32 len4 = len >> 2;
+    for (u32 i = 0; i < len4; i++) {
+        u32 k = (u32)data[4 * i] | ((u32)data[4 * i + 1] << 8) | ((u32)data[4 * i + 2] << 16) | ((u32)data[4 * i + 3] << 24);
+        k *= m; k ^= k >> rr; k *= m; h *= m; h ^= k;
+    }
+    u32 tail = len & 3u, b = len4 << 2;
+    if (tail == 3) h ^= (u32)data[b + 2] << 16;
+    if (tail >= 2) h ^= (u32)data[b + 1] << 8;
+    if (tail >= 1) { h ^= (u32)data[b]; h *= m; }
+    h ^= h >> 13; h *= m; h ^= h >> 15;
+    return h;
+}
+
+__global__ void __launch_bounds__(256)
+ck_route_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, const u32* __restrict__ cols, u32 stride,
+                ck_pub* __restrict__ pubs, u32 npubs, ck_topic_table tab, u32 num_partitions, u32* __restrict__ topic_hist, u32 hist_cap) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = j < npubs;
+    ck_pub p;
+    if (live) { p = pubs[j]; live = (p.payload != 0xffffffffu); }
+    int tid = -1;
+    if (live) {
+        const u8* rec = in + in_off[p.record];
+        tid = p.topic_id;
+        if (tid < 0 && p.topic_len && tab.cap) {
+            u32 h = ck_fnv1a(rec + p.topic_off, p.topic_len);
+            u32 slot = h & (tab.cap - 1);
+            for (u32 probe = 0; probe < tab.cap; probe++) {
+                u32 th = tab.hash[slot];
+                if (th == 0) break;
+                if (th == h && tab.name_len[slot] == p.topic_len) {
+                    const u8* nm = tab.names + tab.name_off[slot];
+                    bool eq = true;
+                    for (u32 b = 0; b < p.topic_len; b++) if (nm[b] != rec[p.topic_off + b]) { eq = false; break; }
+                    if (eq) { tid = tab.id[slot]; break; }
+                }
+                slot = (slot + 1) & (tab.cap - 1);
+            }
+        }
+        int part = -1;
+        if (p.has_key && num_partitions) {
+            u32 co = cols[(size_t)CK_COL_CORR_OFF * stride + p.record], cl = cols[(size_t)CK_COL_CORR_LEN * stride + p.record];
+            part = (int)((ck_murmur2(rec + co, cl) & 0x7fffffffu) % num_partitions);
+        }
+        pubs[j].topic_id = tid;
+        pubs[j].partition = part;
+    }
+    // warp-aggregated histogram of destination topics
+    u32 active = __ballot_sync(0xffffffffu, live && tid >= 0 && (u32)tid < hist_cap);
+    if (live && tid >= 0 && (u32)tid < hist_cap) {
+        u32 peers = __match_any_sync(active, tid);
+        if ((threadIdx.x & 31) == (u32)(__ffs(peers) - 1)) atomicAdd(topic_hist + tid, __popc(peers));
+    }
+}
+
+#endif  // CK_KERNELS_CUH

@@ -1,0 +1,827 @@
+// Canonical-Envelope recogniser + field extractor: one sequential walker per record.
+//
+// Replaces, for records that are byte-wise fixed points of the reference codec, the work of
+//   Envelope.model_validate_json          (reference calfkit/models/envelope.py:9-17, pydantic-core)
+//   envelope.context.model_copy(deep=True) (reference calfkit/nodes/base.py:64-68)
+// by proving "this byte string is exactly what model_dump_json() would emit for a valid Envelope"
+// (key order, defaults present, compact separators, canonical scalars — SURVEY.md Appendix A) while
+// recording the spans the routing / splice kernels need.  Anything it cannot prove gets
+// CK_NOT_CANONICAL and is left to the canonicaliser; it never accepts a record the reference
+// would reject or re-emit differently.
+//
+// Written as __host__ __device__ so tests/hostsim can fuzz the *same source* against pydantic on
+// the CPU (test infrastructure only — the shipped library has no host entry point to it).
+#ifndef CK_WALK_CUH
+#define CK_WALK_CUH
+
+#include "ck_common.h"
+
+#if defined(__CUDACC__)
+#define CK_HD __host__ __device__ __forceinline__
+#define CK_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CK_HD inline __attribute__((always_inline))
+#define CK_HD_NOINLINE __attribute__((noinline))
+#endif
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct Span { u32 off, len; };
+
+// -------------------------------------------------------------------------------------------------
+// Reader: byte access to one record through aligned 8-byte global loads (one 32 B sector serves
+// four consecutive loads of a lane; L1 keeps the line for the next three).  The input buffer is
+// allocated with >= 16 bytes of tail padding and a 256 B aligned base, so aligned-down / +8 loads
+// around a record never leave the allocation.
+// -------------------------------------------------------------------------------------------------
+struct Rd {
+    const u8* g;     // record start
+    u32 n;           // record length
+    const u64* wp;   // address of the cached aligned word
+    u64 w;
+
+    CK_HD static u64 ld64(const u64* p) {
+#if defined(__CUDA_ARCH__)
+        return __ldg((const unsigned long long*)p);
+#else
+        return *p;
+#endif
+    }
+    CK_HD void init(const u8* base, u32 len) { g = base; n = len; wp = nullptr; w = 0; }
+
+    CK_HD u8 at(u32 pos) {           // caller guarantees pos < n
+        const u8* a = g + pos;
+        const u64* q = (const u64*)((uintptr_t)a & ~(uintptr_t)7);
+        if (q != wp) { wp = q; w = ld64(q); }
+        return (u8)(w >> (8 * ((uintptr_t)a & 7)));
+    }
+    // 8 bytes starting at pos, little endian; bytes at/after n are unspecified (but readable)
+    CK_HD u64 load8(u32 pos) {
+        const u8* a = g + pos;
+        u32 s = (u32)((uintptr_t)a & 7);
+        const u64* q = (const u64*)((uintptr_t)a - s);
+        u64 lo = (q == wp) ? w : ld64(q);
+        if (s == 0) { wp = q; w = lo; return lo; }
+        u64 hi = ld64(q + 1);
+        wp = q + 1; w = hi;
+        return (lo >> (8 * s)) | (hi << (64 - 8 * s));
+    }
+};
+
+#define CK_REP8(b) ((u64)(b) * 0x0101010101010101ull)
+
+// 0x80 in every byte of x that is zero; false positives only ABOVE a true hit (callers use ctz)
+CK_HD u64 ck_haszero(u64 x) { return (x - CK_REP8(0x01)) & ~x & CK_REP8(0x80); }
+// 0x80 in every byte < 0x20 (same caveat); bytes >= 0x80 are never flagged here
+CK_HD u64 ck_lt20(u64 x) { return (x - CK_REP8(0x20)) & ~x & CK_REP8(0x80); }
+
+CK_HD u32 ck_ctz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return (u32)(__ffsll((long long)x) - 1);
+#else
+    return (u32)__builtin_ctzll(x);
+#endif
+}
+
+// literal compare, 8 bytes per step; `lit`/`L` are compile-time constants at every call site so the
+// `want` words fold to immediates
+CK_HD bool ck_match(Rd& r, u32& pos, const char* lit, u32 L) {
+    if (pos + L > r.n) return false;
+#pragma unroll
+    for (u32 k = 0; k < L; k += 8) {
+        u32 m = (L - k < 8) ? (L - k) : 8;
+        u64 want = 0;
+#pragma unroll
+        for (u32 j = 0; j < m; j++) want |= (u64)(u8)lit[k + j] << (8 * j);
+        u64 got = r.load8(pos + k);
+        if (m < 8) got &= (~0ull >> (8 * (8 - m)));
+        if (got != want) return false;
+    }
+    pos += L;
+    return true;
+}
+#define M(lit) ck_match(r, pos, lit, (u32)(sizeof(lit) - 1))
+#define PEEK(c) (pos < r.n && r.at(pos) == (u8)(c))
+
+// -------------------------------------------------------------------------------------------------
+// Strings.  pos is AT the opening quote; on success pos is just after the closing quote and
+// `out` is the content span.  Accepts exactly the canonical spelling pydantic-core emits:
+// raw bytes >= 0x20 except " and \, valid UTF-8 (no surrogates / overlongs / > U+10FFFF),
+// escapes \" \\ \n \t \r \b \f, and \u00XX (lower-case hex) only for the other controls.
+// -------------------------------------------------------------------------------------------------
+CK_HD bool ck_utf8_seq(Rd& r, u32& pos) {       // pos at a byte >= 0x80
+    u8 c = r.at(pos);
+    u32 need; u8 lo = 0x80, hi = 0xBF;
+    if (c >= 0xC2 && c <= 0xDF) need = 1;
+    else if (c == 0xE0) { need = 2; lo = 0xA0; }
+    else if (c >= 0xE1 && c <= 0xEC) need = 2;
+    else if (c == 0xED) { need = 2; hi = 0x9F; }
+    else if (c >= 0xEE && c <= 0xEF) need = 2;
+    else if (c == 0xF0) { need = 3; lo = 0x90; }
+    else if (c >= 0xF1 && c <= 0xF3) need = 3;
+    else if (c == 0xF4) { need = 3; hi = 0x8F; }
+    else return false;
+    if (pos + need >= r.n) return false;
+    u8 c1 = r.at(pos + 1);
+    if (c1 < lo || c1 > hi) return false;
+    for (u32 k = 2; k <= need; k++) { u8 ck = r.at(pos + k); if (ck < 0x80 || ck > 0xBF) return false; }
+    pos += need + 1;
+    return true;
+}
+
+CK_HD bool ck_string(Rd& r, u32& pos, Span& out) {
+    if (!(pos < r.n) || r.at(pos) != '"') return false;
+    pos++;
+    u32 start = pos;
+    for (;;) {
+        if (pos >= r.n) return false;
+        u64 x = r.load8(pos);
+        u64 special = (x & CK_REP8(0x80)) | ck_haszero(x ^ CK_REP8('"')) | ck_haszero(x ^ CK_REP8('\\')) | ck_lt20(x);
+        if (special == 0) { pos += 8; continue; }
+        pos += ck_ctz64(special) >> 3;
+        if (pos >= r.n) return false;
+        u8 c = r.at(pos);
+        if (c == '"') { out.off = start; out.len = pos - start; pos++; return true; }
+        if (c == '\\') {
+            if (pos + 1 >= r.n) return false;
+            u8 e = r.at(pos + 1);
+            if (e == '"' || e == '\\' || e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f') { pos += 2; continue; }
+            if (e != 'u' || pos + 5 >= r.n) return false;
+            if (r.at(pos + 2) != '0' || r.at(pos + 3) != '0') return false;
+            u8 h1 = r.at(pos + 4), h2 = r.at(pos + 5);
+            if (h1 != '0' && h1 != '1') return false;
+            u32 v;
+            if (h2 >= '0' && h2 <= '9') v = h2 - '0';
+            else if (h2 >= 'a' && h2 <= 'f') v = h2 - 'a' + 10;
+            else return false;
+            v |= (u32)(h1 - '0') << 4;
+            if (v == 8 || v == 9 || v == 10 || v == 12 || v == 13) return false;   // have short forms
+            pos += 6;
+            continue;
+        }
+        if (c < 0x20) return false;
+        if (!ck_utf8_seq(r, pos)) return false;
+    }
+}
+
+CK_HD bool ck_null(Rd& r, u32& pos) { return M("null"); }
+
+CK_HD bool ck_string_or_null(Rd& r, u32& pos, Span& out) {
+    if (PEEK('n')) { out.off = pos; out.len = 0; return ck_null(r, pos); }
+    return ck_string(r, pos, out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Numbers.  Canonical ints: -?(0|[1-9][0-9]*) except "-0".  Floats are accepted only in the
+// positional spelling whose round trip is provable without a shortest-digits printer:
+// -?INT.FRAC with <= 15 significant digits, no trailing fractional zero (except the single ".0"),
+// magnitude in [1e-5, 1e16)  (DBL_DIG argument, DESIGN.md §canonical numbers).
+// -------------------------------------------------------------------------------------------------
+CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
+    u32 p = pos;
+    bool neg = false;
+    if (p < r.n && r.at(p) == '-') { neg = true; p++; }
+    if (p >= r.n) return false;
+    u8 c = r.at(p);
+    if (c < '0' || c > '9') return false;
+    u32 int_start = p;
+    bool int_zero = (c == '0');
+    p++;
+    if (!int_zero) { while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; p++; } }
+    else if (p < r.n) { u8 d = r.at(p); if (d >= '0' && d <= '9') return false; }   // leading zero
+    u32 int_len = p - int_start;
+    bool is_float = false;
+    u32 frac_start = 0, frac_len = 0;
+    if (p < r.n && r.at(p) == '.') {
+        is_float = true;
+        p++;
+        frac_start = p;
+        while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; p++; }
+        frac_len = p - frac_start;
+        if (frac_len == 0) return false;
+    }
+    if (p < r.n) { u8 e = r.at(p); if (e == 'e' || e == 'E') return false; }   // exponent spelling: not proven here
+    if (!is_float) {
+        if (!allow_int) return false;
+        if (neg && int_zero) return false;          // "-0" re-emits as "0"
+        if (int_len > 4000) return false;           // CPython int<->str digit limit is 4300
+        pos = p;
+        return true;
+    }
+    if (!allow_float) return false;
+    if (int_len > 16) return false;
+    u8 last = r.at(frac_start + frac_len - 1);
+    if (last == '0' && frac_len != 1) return false;
+    // significant digits: from the first non-zero digit to the last non-zero digit
+    u32 sig;
+    if (!int_zero) {
+        if (frac_len == 1 && last == '0') {         // INT.0 : trailing integer zeros are not significant
+            u32 q = int_start + int_len;
+            u32 tz = 0;
+            while (tz < int_len && r.at(q - 1 - tz) == '0') tz++;
+            sig = int_len - tz;
+        } else sig = int_len + frac_len;
+    } else {
+        u32 lz = 0;
+        while (lz < frac_len && r.at(frac_start + lz) == '0') lz++;
+        if (lz == frac_len) { if (frac_len != 1) return false; sig = 1; }   // 0.0 / -0.0 only
+        else { if (lz > 4) return false; sig = frac_len - lz; }             // < 1e-5 prints as 1e-6 ...
+    }
+    if (sig > 15) return false;
+    pos = p;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Generic canonical JSON value ("Any" subtrees: provided_deps, args, metadata, return_value ...).
+// Iterative (explicit container bit-stack); duplicate keys make a value non-canonical because the
+// reference re-emits a Python dict, so each open object keeps 32-bit key hashes in a small stack.
+// -------------------------------------------------------------------------------------------------
+#define CK_MAX_DEPTH 96          // fast-path bound; jiter's own limit (~200) is handled by the canonicaliser
+#define CK_KEYSTACK 64
+#define CK_DICT_KEYS 128     // tool_calls / tool_results entries handled on the fast path
+
+struct AnyCtx {
+    u32 kind[CK_MAX_DEPTH / 32];        // bit = 1: object, 0: array
+    u32 khash[CK_KEYSTACK];
+    u8  kbase[CK_MAX_DEPTH];            // khash fill level when the object at this depth was opened
+    u32 kfill;
+};
+
+CK_HD u32 ck_hash_span(Rd& r, u32 off, u32 len) {
+    u32 h = 2166136261u ^ len;
+    for (u32 i = 0; i < len; i++) h = (h ^ r.at(off + i)) * 16777619u;
+    return h;
+}
+
+// base_depth: nesting level of the value inside the document (root object = depth 1)
+CK_HD_NOINLINE bool ck_any(Rd& r, u32& pos_io, u32 base_depth, AnyCtx& cx) {
+    u32 pos = pos_io;
+    u32 depth = 0;
+    cx.kfill = 0;
+    Span s;
+    for (;;) {
+        // ---- parse a value
+        if (pos >= r.n) return false;
+        u8 c = r.at(pos);
+        bool opened = false;
+        if (c == '{' || c == '[') {
+            if (depth + base_depth >= CK_MAX_DEPTH) return false;
+            bool is_obj = (c == '{');
+            if (is_obj) cx.kind[depth >> 5] |= (1u << (depth & 31)); else cx.kind[depth >> 5] &= ~(1u << (depth & 31));
+            cx.kbase[depth] = (u8)cx.kfill;
+            depth++; pos++;
+            if (pos >= r.n) return false;
+            u8 d = r.at(pos);
+            if (d == (is_obj ? '}' : ']')) { pos++; depth--; cx.kfill = cx.kbase[depth]; }
+            else opened = true;
+        } else if (c == '"') { if (!ck_string(r, pos, s)) return false; }
+        else if (c == 't') { if (!M("true")) return false; }
+        else if (c == 'f') { if (!M("false")) return false; }
+        else if (c == 'n') { if (!M("null")) return false; }
+        else { if (!ck_number(r, pos, true, true)) return false; }
+
+        // ---- what follows
+        for (;;) {
+            bool in_obj;
+            if (opened) { in_obj = (cx.kind[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1; opened = false;
+                          if (!in_obj) break; /* array: first element */ }
+            else {
+                if (depth == 0) { pos_io = pos; return true; }
+                in_obj = (cx.kind[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1;
+                if (pos >= r.n) return false;
+                u8 d = r.at(pos);
+                if (d == (in_obj ? '}' : ']')) { pos++; depth--; cx.kfill = cx.kbase[depth]; continue; }
+                if (d != ',') return false;
+                pos++;
+                if (!in_obj) break;                 // next array element
+            }
+            // object member: key, duplicate check, colon
+            if (!ck_string(r, pos, s)) return false;
+            u32 h = ck_hash_span(r, s.off, s.len);
+            for (u32 k = cx.kbase[depth - 1]; k < cx.kfill; k++) if (cx.khash[k] == h) return false;
+            if (cx.kfill >= CK_KEYSTACK) return false;
+            cx.khash[cx.kfill++] = h;
+            if (!(pos < r.n) || r.at(pos) != ':') return false;
+            pos++;
+            break;
+        }
+    }
+}
+
+CK_HD bool ck_any_obj(Rd& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('{') && ck_any(r, pos, d, cx); }
+CK_HD bool ck_any_obj_or_null(Rd& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('n') ? ck_null(r, pos) : ck_any_obj(r, pos, d, cx); }
+
+// -------------------------------------------------------------------------------------------------
+// datetime: the spellings pydantic re-emits unchanged:
+//   YYYY-MM-DDTHH:MM:SS[.ffffff](Z | +HH:MM | -HH:MM | <naive>)   fraction: 6 digits, not 000000;
+//   offset != 00:00 (that prints as Z); calendar-valid date; year >= 1.
+// -------------------------------------------------------------------------------------------------
+CK_HD bool ck_2d(Rd& r, u32 p, u32& v) {
+    u8 a = r.at(p), b = r.at(p + 1);
+    if (a < '0' || a > '9' || b < '0' || b > '9') return false;
+    v = (u32)(a - '0') * 10 + (u32)(b - '0');
+    return true;
+}
+CK_HD bool ck_datetime(Rd& r, u32& pos) {
+    u32 p = pos;
+    if (p + 21 > r.n) return false;                 // "YYYY-MM-DDTHH:MM:SS" + quotes
+    if (r.at(p) != '"') return false;
+    p++;
+    u32 y1, y2, mo, d, h, mi, s;
+    if (!ck_2d(r, p, y1) || !ck_2d(r, p + 2, y2) || r.at(p + 4) != '-' || !ck_2d(r, p + 5, mo) || r.at(p + 7) != '-' ||
+        !ck_2d(r, p + 8, d) || r.at(p + 10) != 'T' || !ck_2d(r, p + 11, h) || r.at(p + 13) != ':' ||
+        !ck_2d(r, p + 14, mi) || r.at(p + 16) != ':' || !ck_2d(r, p + 17, s)) return false;
+    u32 y = y1 * 100 + y2;
+    if (y < 1 || mo < 1 || mo > 12 || d < 1 || h > 23 || mi > 59 || s > 59) return false;
+    u32 dim = (mo == 2) ? (((y % 4 == 0 && y % 100 != 0) || y % 400 == 0) ? 29 : 28)
+                        : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31);
+    if (d > dim) return false;
+    p += 19;
+    if (p >= r.n) return false;
+    u8 c = r.at(p);
+    if (c == '.') {
+        if (p + 7 >= r.n) return false;
+        bool nz = false;
+        for (u32 k = 1; k <= 6; k++) { u8 f = r.at(p + k); if (f < '0' || f > '9') return false; nz |= (f != '0'); }
+        if (!nz) return false;
+        p += 7;
+        c = r.at(p);
+    }
+    if (c == 'Z') { p++; if (p >= r.n) return false; c = r.at(p); }
+    else if (c == '+' || c == '-') {
+        if (p + 6 >= r.n) return false;
+        u32 oh, om;
+        if (!ck_2d(r, p + 1, oh) || r.at(p + 3) != ':' || !ck_2d(r, p + 4, om)) return false;
+        if (oh > 23 || om > 59 || (oh == 0 && om == 0)) return false;
+        p += 6;
+        c = r.at(p);
+    }
+    if (c != '"') return false;
+    pos = p + 1;
+    return true;
+}
+CK_HD bool ck_datetime_or_null(Rd& r, u32& pos) { return PEEK('n') ? ck_null(r, pos) : ck_datetime(r, pos); }
+
+CK_HD bool ck_bool(Rd& r, u32& pos) { return PEEK('t') ? M("true") : M("false"); }
+
+// -------------------------------------------------------------------------------------------------
+// Typed pieces of the Envelope schema, in canonical key order.
+// `d` = nesting depth of the value being recognised.
+// -------------------------------------------------------------------------------------------------
+struct ToolCallSpans { Span tool_name, args, tool_call_id; };
+
+// ToolCallPart / BuiltinToolCallPart (reference _vendor/pydantic_ai/messages.py:1187-1283)
+// returns 1 = tool-call, 2 = builtin-tool-call, 0 = no match
+CK_HD u32 ck_tool_call_part(Rd& r, u32& pos, u32 d, AnyCtx& cx, ToolCallSpans& o) {
+    Span t;
+    if (!M("{\"tool_name\":") || !ck_string(r, pos, o.tool_name) || !M(",\"args\":")) return 0;
+    o.args.off = pos;
+    if (PEEK('"')) { if (!ck_string(r, pos, t)) return 0; }
+    else if (!ck_any_obj_or_null(r, pos, d + 1, cx)) return 0;
+    o.args.len = pos - o.args.off;
+    if (!M(",\"tool_call_id\":") || !ck_string(r, pos, o.tool_call_id) || !M(",\"id\":") || !ck_string_or_null(r, pos, t) ||
+        !M(",\"provider_name\":") || !ck_string_or_null(r, pos, t) || !M(",\"provider_details\":") ||
+        !ck_any_obj_or_null(r, pos, d + 1, cx) || !M(",\"part_kind\":\"")) return 0;
+    if (M("tool-call\"}")) return 1;
+    if (M("builtin-tool-call\"}")) return 2;
+    return 0;
+}
+
+// message parts.  Returns 1 for a request-side part, 2 for a response-side part, 0 = no match.
+// (request: system-prompt / user-prompt / tool-return / retry-prompt, messages.py:112,739,883,918;
+//  response: text / tool-call / builtin-tool-call / builtin-tool-return / thinking, :1059-1283)
+CK_HD u32 ck_message_part(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+    Span t;
+    if (M("{\"content\":")) {
+        // content-first parts: system-prompt, user-prompt, retry-prompt (request) | text, thinking (response)
+        bool content_is_str = PEEK('"');
+        bool content_is_strlist = false;
+        if (content_is_str) { if (!ck_string(r, pos, t)) return 0; }
+        else {                                         // user-prompt may carry list[str]
+            if (!M("[")) return 0;
+            if (!PEEK(']')) { for (;;) { if (!ck_string(r, pos, t)) return 0; if (PEEK(',')) { pos++; continue; } break; } }
+            if (!M("]")) return 0;
+            content_is_strlist = true;
+        }
+        if (M(",\"timestamp\":")) {
+            if (!ck_datetime(r, pos)) return 0;
+            if (M(",\"dynamic_ref\":")) {
+                if (content_is_strlist) return 0;
+                if (!ck_string_or_null(r, pos, t) || !M(",\"name\":") || !ck_string_or_null(r, pos, t) ||
+                    !M(",\"part_kind\":\"system-prompt\"}")) return 0;
+                return 1;
+            }
+            if (!M(",\"name\":") || !ck_string_or_null(r, pos, t) || !M(",\"part_kind\":\"user-prompt\"}")) return 0;
+            return 1;
+        }
+        if (content_is_strlist) return 0;
+        if (M(",\"tool_name\":")) {                   // retry-prompt (str content only on the fast path)
+            if (!ck_string_or_null(r, pos, t) || !M(",\"tool_call_id\":") || !ck_string(r, pos, t) ||
+                !M(",\"timestamp\":") || !ck_datetime(r, pos) || !M(",\"part_kind\":\"retry-prompt\"}")) return 0;
+            return 1;
+        }
+        if (!M(",\"id\":") || !ck_string_or_null(r, pos, t)) return 0;
+        bool thinking = false;
+        if (M(",\"signature\":")) { thinking = true; if (!ck_string_or_null(r, pos, t)) return 0; }
+        if (!M(",\"provider_name\":") || !ck_string_or_null(r, pos, t) || !M(",\"provider_details\":") ||
+            !ck_any_obj_or_null(r, pos, d + 1, cx)) return 0;
+        if (thinking) return M(",\"part_kind\":\"thinking\"}") ? 2 : 0;
+        return M(",\"part_kind\":\"text\"}") ? 2 : 0;
+    }
+    // tool_name-first parts: tool-return (request) | tool-call, builtin-tool-call, builtin-tool-return (response)
+    u32 save = pos;
+    if (!M("{\"tool_name\":") || !ck_string(r, pos, t)) return 0;
+    if (M(",\"content\":")) {
+        if (!ck_any(r, pos, d + 1, cx) || !M(",\"tool_call_id\":") || !ck_string(r, pos, t) || !M(",\"metadata\":") ||
+            !ck_any(r, pos, d + 1, cx) || !M(",\"timestamp\":") || !ck_datetime(r, pos)) return 0;
+        if (M(",\"part_kind\":\"tool-return\"}")) return 1;
+        if (!M(",\"provider_name\":") || !ck_string_or_null(r, pos, t) || !M(",\"provider_details\":") ||
+            !ck_any_obj_or_null(r, pos, d + 1, cx) || !M(",\"part_kind\":\"builtin-tool-return\"}")) return 0;
+        return 2;
+    }
+    pos = save;
+    ToolCallSpans tc;
+    return ck_tool_call_part(r, pos, d, cx, tc) ? 2 : 0;
+}
+
+// RequestUsage (reference _vendor/pydantic_ai/usage.py)
+CK_HD bool ck_usage(Rd& r, u32& pos, AnyCtx& cx) {
+    Span t;
+    if (!M("{\"input_tokens\":") || !ck_number(r, pos, true, false) || !M(",\"cache_write_tokens\":") || !ck_number(r, pos, true, false) ||
+        !M(",\"cache_read_tokens\":") || !ck_number(r, pos, true, false) || !M(",\"output_tokens\":") || !ck_number(r, pos, true, false) ||
+        !M(",\"input_audio_tokens\":") || !ck_number(r, pos, true, false) || !M(",\"cache_audio_read_tokens\":") ||
+        !ck_number(r, pos, true, false) || !M(",\"output_audio_tokens\":") || !ck_number(r, pos, true, false) || !M(",\"details\":{")) return false;
+    if (!PEEK('}')) {
+        cx.kfill = 0;
+        for (;;) {
+            if (!ck_string(r, pos, t)) return false;
+            u32 h = ck_hash_span(r, t.off, t.len);
+            for (u32 k = 0; k < cx.kfill; k++) if (cx.khash[k] == h) return false;
+            if (cx.kfill >= CK_KEYSTACK) return false;
+            cx.khash[cx.kfill++] = h;
+            if (!M(":") || !ck_number(r, pos, true, false)) return false;
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    return M("}}");
+}
+
+// ModelMessage = ModelRequest | ModelResponse (messages.py:1014-1041, :1292-1345, :1554).
+// returns 1 = request, 2 = response, 0 = no match
+CK_HD_NOINLINE u32 ck_message(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
+    u32 pos = pos_io;
+    Span t;
+    if (!M("{\"parts\":[")) return 0;
+    u32 seen = 0;
+    if (!PEEK(']')) {
+        for (;;) {
+            u32 k = ck_message_part(r, pos, d + 2, cx);
+            if (!k) return 0;
+            seen |= k;
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    if (!M("]")) return 0;
+    u32 kind;
+    if (M(",\"timestamp\":")) {
+        if (seen & 2) return 0;
+        if (!ck_datetime_or_null(r, pos) || !M(",\"instructions\":") || !ck_string_or_null(r, pos, t) ||
+            !M(",\"kind\":\"request\",\"run_id\":") || !ck_string_or_null(r, pos, t) || !M(",\"metadata\":") ||
+            !ck_any_obj_or_null(r, pos, d + 1, cx) || !M("}")) return 0;
+        kind = 1;
+    } else {
+        if (seen & 1) return 0;
+        if (!M(",\"usage\":") || !ck_usage(r, pos, cx) || !M(",\"model_name\":") || !ck_string_or_null(r, pos, t) ||
+            !M(",\"name\":") || !ck_string_or_null(r, pos, t) || !M(",\"timestamp\":") || !ck_datetime(r, pos) ||
+            !M(",\"kind\":\"response\",\"provider_name\":") || !ck_string_or_null(r, pos, t) || !M(",\"provider_url\":") ||
+            !ck_string_or_null(r, pos, t) || !M(",\"provider_details\":") || !ck_any_obj_or_null(r, pos, d + 1, cx) ||
+            !M(",\"provider_response_id\":") || !ck_string_or_null(r, pos, t) || !M(",\"finish_reason\":")) return 0;
+        if (!PEEK('n')) {
+            if (!(M("\"stop\"") || M("\"length\"") || M("\"content_filter\"") || M("\"tool_call\"") || M("\"error\""))) return 0;
+        } else if (!ck_null(r, pos)) return 0;
+        if (!M(",\"run_id\":") || !ck_string_or_null(r, pos, t) || !M(",\"metadata\":") ||
+            !ck_any_obj_or_null(r, pos, d + 1, cx) || !M("}")) return 0;
+        kind = 2;
+    }
+    pos_io = pos;
+    return kind;
+}
+
+// ToolDefinition (reference _vendor/pydantic_ai/tools.py:474-540)
+CK_HD bool ck_tool_definition(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+    Span t;
+    if (!M("{\"name\":") || !ck_string(r, pos, t) || !M(",\"parameters_json_schema\":") || !ck_any_obj(r, pos, d + 1, cx) ||
+        !M(",\"description\":") || !ck_string_or_null(r, pos, t) || !M(",\"outer_typed_dict_key\":") || !ck_string_or_null(r, pos, t) ||
+        !M(",\"strict\":")) return false;
+    if (PEEK('n')) { if (!ck_null(r, pos)) return false; } else if (!ck_bool(r, pos)) return false;
+    if (!M(",\"sequential\":") || !ck_bool(r, pos) || !M(",\"kind\":\"")) return false;
+    if (!(M("function\"") || M("output\"") || M("external\"") || M("unapproved\""))) return false;
+    if (!M(",\"metadata\":") || !ck_any_obj_or_null(r, pos, d + 1, cx) || !M(",\"timeout\":")) return false;
+    if (PEEK('n')) { if (!ck_null(r, pos)) return false; } else if (!ck_number(r, pos, false, true)) return false;
+    return M("}");
+}
+
+// OverridesState | null (reference calfkit/models/state.py:22-26, node_schema.py:6-21)
+CK_HD_NOINLINE bool ck_overrides_or_null(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
+    u32 pos = pos_io;
+    Span t;
+    if (PEEK('n')) { if (!ck_null(r, pos)) return false; pos_io = pos; return true; }
+    if (!M("{\"override_agent_tools\":")) return false;
+    if (PEEK('n')) { if (!ck_null(r, pos)) return false; }
+    else {
+        if (!M("[")) return false;
+        if (!PEEK(']')) {
+            for (;;) {
+                if (!M("{\"node_id\":") || !ck_string(r, pos, t) || !M(",\"subscribe_topics\":[")) return false;
+                if (!PEEK(']')) { for (;;) { if (!ck_string(r, pos, t)) return false; if (PEEK(',')) { pos++; continue; } break; } }
+                if (!M("],\"publish_topic\":") || !ck_string_or_null(r, pos, t) || !M(",\"tool_schema\":") ||
+                    !ck_tool_definition(r, pos, d + 3, cx) || !M("}")) return false;
+                if (PEEK(',')) { pos++; continue; }
+                break;
+            }
+        }
+        if (!M("]")) return false;
+    }
+    if (!M("}")) return false;
+    pos_io = pos;
+    return true;
+}
+
+// final_output_parts element (reference calfkit/models/payload.py:6-35): `kind` comes first
+CK_HD bool ck_content_part(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+    Span t;
+    if (!M("{\"kind\":\"")) return false;
+    if (M("text\",\"text\":")) {
+        return ck_string(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+    }
+    if (M("data\",\"data\":")) {
+        // the field's alias is "schema": a "schema_" key is ignored on validation and re-emitted as null
+        // (SURVEY.md Appendix C item 2), so only null is a fixed point
+        return ck_any(r, pos, d + 1, cx) && M(",\"schema_\":null,\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+    }
+    if (M("file\",\"media_type\":")) {
+        return ck_string(r, pos, t) && M(",\"uri\":") && ck_string_or_null(r, pos, t) && M(",\"data\":") &&
+               ck_string_or_null(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+    }
+    if (M("tool\",\"tool_call_id\":")) {
+        return ck_string(r, pos, t) && M(",\"kwargs\":") && ck_any_obj(r, pos, d + 1, cx) && M(",\"tool_name\":") &&
+               ck_string(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+    }
+    return false;
+}
+
+// skip one already-validated canonical value (used for second looks at spans proven canonical)
+CK_HD void ck_skip_value(Rd& r, u32& pos) {
+    u32 depth = 0;
+    for (;;) {
+        if (pos >= r.n) return;
+        u8 c = r.at(pos);
+        if (c == '"') {
+            pos++;
+            for (;;) {
+                if (pos >= r.n) return;
+                u8 s = r.at(pos);
+                if (s == '\\') { pos += 2; continue; }
+                pos++;
+                if (s == '"') break;
+            }
+        } else if (c == '{' || c == '[') { depth++; pos++; continue; }
+        else if (c == '}' || c == ']') { depth--; pos++; }
+        else if (c == ',' || c == ':') { if (depth == 0) return; pos++; continue; }
+        else { pos++; while (pos < r.n) { u8 s = r.at(pos); if (s == ',' || s == '}' || s == ']' || s == ':') break; pos++; } }
+        if (depth == 0) return;
+    }
+}
+
+// tool_results value: ToolReturn | ModelRetry | RetryPromptPart (callable discriminator on
+// `kind`, then `part_kind`) with an `| Any` fallback (reference models/state.py:70,
+// _vendor/pydantic_ai/tools.py:189-210).  A value is a fixed point if it is the canonical form of
+// its tagged model, or if it carries no such tag and is generically canonical.
+CK_HD_NOINLINE bool ck_tool_result_value(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
+    u32 pos = pos_io;
+    Span t;
+    u32 start = pos;
+    if (PEEK('{')) {
+        if (M("{\"return_value\":")) {
+            if (ck_any(r, pos, d + 1, cx) && M(",\"content\":") && ck_string_or_null(r, pos, t) && M(",\"metadata\":") &&
+                ck_any(r, pos, d + 1, cx) && M(",\"kind\":\"tool-return\"}")) { pos_io = pos; return true; }
+        } else if (M("{\"message\":")) {
+            if (ck_string(r, pos, t) && M(",\"kind\":\"model-retry\"}")) { pos_io = pos; return true; }
+        } else if (M("{\"content\":")) {
+            if (ck_string(r, pos, t) && M(",\"tool_name\":") && ck_string_or_null(r, pos, t) && M(",\"tool_call_id\":") &&
+                ck_string(r, pos, t) && M(",\"timestamp\":") && ck_datetime(r, pos) && M(",\"part_kind\":\"retry-prompt\"}")) {
+                pos_io = pos; return true;
+            }
+        }
+        // not the canonical form of a tagged model: generic value, provided it carries no tag
+        pos = start;
+        if (!ck_any(r, pos, d, cx)) return false;
+        u32 end = pos;
+        u32 p = start + 1;
+        bool have_kind = false, tagged = false, part_tagged = false;
+        while (p < end && r.at(p) != '}') {
+            Span k;
+            if (!ck_string(r, p, k)) return false;
+            p++;                                       // ':'
+            u32 v = p;
+            ck_skip_value(r, p);
+            bool is_kind = (k.len == 4 && r.at(k.off) == 'k' && r.at(k.off + 1) == 'i' && r.at(k.off + 2) == 'n' && r.at(k.off + 3) == 'd');
+            u32 q = k.off;
+            bool is_pk = (k.len == 9) && ck_match(r, q, "part_kind", 9);
+            if (is_kind || is_pk) {
+                u32 vv = v;
+                bool tag = ck_match(r, vv, "\"tool-return\"", 13) || ck_match(r, vv, "\"model-retry\"", 13) ||
+                           ck_match(r, vv, "\"retry-prompt\"", 14);
+                tag = tag && (vv == p);
+                if (is_kind) { have_kind = true; tagged = tag; } else part_tagged = tag;
+            }
+            if (p < end && r.at(p) == ',') p++;
+        }
+        if (have_kind ? tagged : part_tagged) return false;   // would be validated as the model: not proven here
+        pos_io = end;
+        return true;
+    }
+    if (!ck_any(r, pos, d, cx)) return false;
+    pos_io = pos;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Whole Envelope.  On success fills cols[] (spans relative to the record start).
+// -------------------------------------------------------------------------------------------------
+struct WalkOut {
+    u32 c[CK_NUM_COLS];
+};
+
+#define SETSPAN(COL, a, b) do { o.c[COL] = (a); o.c[COL + 1] = (b) - (a); } while (0)
+
+CK_HD_NOINLINE bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
+    u32 pos = 0;
+    Span t;
+    stop = 0;
+#define FAIL do { stop = pos; return false; } while (0)
+    // ---- context.state ---------------------------------------------------------------------
+    if (!M("{\"context\":{\"state\":{\"tool_calls\":{")) FAIL;
+    u32 a = pos - 1;
+    if (!PEEK('}')) {
+        // dict[str, ToolCallPart]; keys must be unique (a Python dict on the reference side):
+        // 32-bit hashes of the raw key bytes, a (vanishingly rare) collision only costs the fast path
+        u32 nk = 0;
+        u32 kh[CK_DICT_KEYS];
+        for (;;) {
+            if (!ck_string(r, pos, t)) FAIL;
+            u32 h = ck_hash_span(r, t.off, t.len);
+            for (u32 k = 0; k < nk; k++) if (kh[k] == h) FAIL;
+            if (nk >= CK_DICT_KEYS) FAIL;
+            kh[nk++] = h;
+            ToolCallSpans tc;
+            if (!M(":") || ck_tool_call_part(r, pos, 5, cx, tc) != 1) FAIL;
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    if (!M("}")) FAIL;
+    SETSPAN(CK_COL_TC_OFF, a, pos);
+
+    if (!M(",\"tool_results\":{")) FAIL;
+    a = pos - 1;
+    if (!PEEK('}')) {
+        u32 nk = 0;
+        u32 kh[CK_DICT_KEYS];
+        for (;;) {
+            if (!ck_string(r, pos, t)) FAIL;
+            u32 h = ck_hash_span(r, t.off, t.len);
+            for (u32 k = 0; k < nk; k++) if (kh[k] == h) FAIL;
+            if (nk >= CK_DICT_KEYS) FAIL;
+            kh[nk++] = h;
+            if (!M(":") || !ck_tool_result_value(r, pos, 5, cx)) FAIL;
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    if (!M("}")) FAIL;
+    SETSPAN(CK_COL_TR_OFF, a, pos);
+
+    if (!M(",\"uncommitted_message\":")) FAIL;
+    a = pos;
+    if (PEEK('n')) { if (!ck_null(r, pos)) FAIL; } else if (!ck_message(r, pos, 4, cx)) FAIL;
+    SETSPAN(CK_COL_UNC_OFF, a, pos);
+
+    if (!M(",\"message_history\":[")) FAIL;
+    a = pos - 1;
+    if (!PEEK(']')) {
+        for (;;) {
+            if (!ck_message(r, pos, 5, cx)) FAIL;
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    if (!M("]")) FAIL;
+    SETSPAN(CK_COL_HIST_OFF, a, pos);
+
+    if (!M(",\"final_output_parts\":[")) FAIL;
+    a = pos - 1;
+    if (!PEEK(']')) {
+        for (;;) {
+            if (!ck_content_part(r, pos, 5, cx)) FAIL;
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    if (!M("]")) FAIL;
+    SETSPAN(CK_COL_FOP_OFF, a, pos);
+
+    if (!M(",\"temp_instructions\":")) FAIL;
+    a = pos;
+    if (!ck_string_or_null(r, pos, t)) FAIL;
+    SETSPAN(CK_COL_TI_OFF, a, pos);
+
+    if (!M(",\"metadata\":")) FAIL;
+    a = pos;
+    if (!ck_any(r, pos, 4, cx)) FAIL;
+    SETSPAN(CK_COL_SMETA_OFF, a, pos);
+
+    if (!M(",\"overrides\":")) FAIL;
+    a = pos;
+    if (!ck_overrides_or_null(r, pos, 4, cx)) FAIL;
+    SETSPAN(CK_COL_SOV_OFF, a, pos);
+
+    // ---- context.deps ----------------------------------------------------------------------
+    if (!M("},\"deps\":{\"correlation_id\":")) FAIL;
+    if (!ck_string(r, pos, t)) FAIL;
+    o.c[CK_COL_CORR_OFF] = t.off; o.c[CK_COL_CORR_LEN] = t.len;
+    if (!M(",\"provided_deps\":")) FAIL;
+    a = pos;
+    if (!ck_any_obj(r, pos, 4, cx)) FAIL;
+    SETSPAN(CK_COL_PD_OFF, a, pos);
+
+    // ---- internal_workflow_state -----------------------------------------------------------
+    if (!M("}},\"internal_workflow_state\":{\"call_stack\":{\"_internal_list\":[")) FAIL;
+    a = pos - 1;
+    u32 nframes = 0;
+    o.c[CK_COL_NARGS] = CK_NARGS_NULL;
+    if (!PEEK(']')) {
+        for (;;) {
+            u32 f0 = pos;
+            Span tgt, cb;
+            if (!M("{\"target_topic\":") || !ck_string(r, pos, tgt) || !M(",\"callback_topic\":") || !ck_string(r, pos, cb) ||
+                !M(",\"input_args\":")) FAIL;
+            u32 nargs = CK_NARGS_NULL, kinds = 0;
+            Span a0 = {0, 0}, a1 = {0, 0};
+            if (PEEK('n')) { if (!ck_null(r, pos)) FAIL; }
+            else {
+                if (!M("[")) FAIL;
+                nargs = 0;
+                if (!PEEK(']')) {
+                    for (;;) {
+                        u32 v0 = pos;
+                        Span sv;
+                        bool is_str = PEEK('"');
+                        if (is_str) { if (!ck_string(r, pos, sv)) FAIL; }
+                        else { if (!ck_any(r, pos, 6, cx)) FAIL; sv.off = v0; sv.len = pos - v0; }
+                        if (nargs == 0) { a0 = sv; kinds |= is_str ? 1u : 0u; }
+                        if (nargs == 1) { a1 = sv; kinds |= is_str ? 2u : 0u; }
+                        nargs++;
+                        if (PEEK(',')) { pos++; continue; }
+                        break;
+                    }
+                }
+                if (!M("]")) FAIL;
+            }
+            if (!M(",\"frame_id\":") || !ck_string(r, pos, t) || !M(",\"overrides\":")) FAIL;
+            u32 ov0 = pos;
+            if (!ck_overrides_or_null(r, pos, 6, cx)) FAIL;
+            u32 ov1 = pos;
+            if (!M("}")) FAIL;
+            nframes++;
+            // the LAST frame is the current one (Stack.peek, reference models/session_context.py:26-30)
+            SETSPAN(CK_COL_TOP_OFF, f0, pos);
+            o.c[CK_COL_TGT_OFF] = tgt.off; o.c[CK_COL_TGT_LEN] = tgt.len;
+            o.c[CK_COL_CB_OFF] = cb.off; o.c[CK_COL_CB_LEN] = cb.len;
+            o.c[CK_COL_NARGS] = nargs; o.c[CK_COL_ARGKINDS] = kinds;
+            o.c[CK_COL_ARG0_OFF] = a0.off; o.c[CK_COL_ARG0_LEN] = a0.len;
+            o.c[CK_COL_ARG1_OFF] = a1.off; o.c[CK_COL_ARG1_LEN] = a1.len;
+            SETSPAN(CK_COL_FOV_OFF, ov0, ov1);
+            if (PEEK(',')) { pos++; continue; }
+            break;
+        }
+    }
+    if (!M("]")) FAIL;
+    SETSPAN(CK_COL_FRAMES_OFF, a, pos);
+    o.c[CK_COL_NFRAMES] = nframes;
+    if (!M("},\"metadata\":")) FAIL;
+    a = pos;
+    if (!ck_any(r, pos, 3, cx)) FAIL;
+    SETSPAN(CK_COL_WFMETA_OFF, a, pos);
+    if (!M("}}")) FAIL;
+    if (pos != r.n) FAIL;                 // trailing bytes (even whitespace) are not a fixed point
+    return true;
+#undef FAIL
+}
+
+#endif  // CK_WALK_CUH

@@ -1,0 +1,105 @@
+/* calfkit_b200.h — C-ABI of libcalfkit_b200.so (sm_100a).
+ *
+ * The reference (calf-ai/calfkit-sdk v0.2.5) has no FFI for this path: its per-record hot loop is
+ *   FastStream decoder -> Envelope validation      calfkit/nodes/base.py:151, calfkit/models/envelope.py:9-17
+ *   BaseNodeDef.handler / prepare_context           calfkit/nodes/base.py:64-68,149-164
+ *   ToolNodeDef.run                                  calfkit/nodes/tool.py:37-86
+ *   BaseNodeDef._publish_action -> broker.publish    calfkit/nodes/base.py:70-147
+ *   handler return -> publisher(publish_topic)       calfkit/worker/worker.py:52-53
+ * The entry points below are what a ctypes binding underneath calfkit.worker.Worker would bind to
+ * replace that loop batch-wise (binding shown in INTEGRATION.md).  Plain C: int status (0 = ok),
+ * caller-owned buffers, no exceptions, no torch types.  A bad record never fails a batch: per-record
+ * status codes live in the column table (ck_common.h).
+ *
+ * Threading: one handle = one CUDA stream; calls on one handle must be serialised by the caller,
+ * different handles are independent (use two for double buffering).  Calls that launch work return
+ * once it is enqueued; ck_sync / ck_fetch_* wait for it.
+ */
+#ifndef CALFKIT_B200_H
+#define CALFKIT_B200_H
+
+#include <stdint.h>
+#include "../calfkit-sdk_b200/csrc/ck_common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ck_handle ck_handle;
+
+typedef struct {           /* one publish; mirrors struct ck_pub in csrc/ck_kernels.cuh */
+    uint32_t payload;      /* index into the payload offsets, 0xffffffff = slot unused */
+    int32_t  topic_id;     /* registered topic id, or -1: read the name at (record, topic_off, topic_len) */
+    uint32_t topic_off, topic_len;
+    uint32_t record;       /* input record this publish derives from */
+    uint32_t has_key;      /* 1: key = correlation id bytes (nodes/base.py:86,103,117,134) */
+    int32_t  partition;    /* murmur2(key) % num_partitions, -1 when unkeyed */
+    uint32_t pad;
+} ck_publish;
+
+/* lifecycle ------------------------------------------------------------------------------------ */
+int  ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_bytes, uint32_t max_records,
+               uint64_t max_aux_bytes, ck_handle** out);
+void ck_destroy(ck_handle* h);
+const char* ck_last_error(ck_handle* h);          /* h may be NULL: error of the last failed ck_create */
+int  ck_version(void);
+
+/* routing table: replaces the implicit "one FastStream subscriber per node.subscribe_topics"
+ * binding of Worker.register_handlers (calfkit/worker/worker.py:33-55).  names = concatenated UTF-8
+ * topic strings, offsets[n+1]; ids = caller-chosen non-negative ids. Re-registering replaces. */
+int  ck_register_topics(ck_handle* h, const uint8_t* names, const uint32_t* offsets, uint32_t n,
+                        const int32_t* ids, uint32_t num_partitions);
+
+/* configure the handle for one @agent_tool node (calfkit/nodes/tool.py:24-35,89-95).
+ * publish_topic_id: registered id of node.publish_topic or -1.
+ * Result template (optional, nparts > 0): the tool's return value is the JSON string made of
+ * literal pieces (kind 0, already JSON-escaped) and raw string arguments (kind 1, blob = key name);
+ * nparts == 0: results are supplied by the host through ck_tool_plan(aux). */
+int  ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t nparts, const uint32_t* kinds,
+                      const uint8_t* blob, const uint32_t* part_offsets);
+
+/* decode: copy a batch of records (concatenated bytes + n+1 offsets, pinned or pageable host
+ * memory) to HBM and run validate+extract.  ck_submit_device: the batch is already resident
+ * (device pointers stay owned by the caller and must outlive the following plan/emit calls). */
+int  ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* host_off, uint32_t n);
+int  ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n);
+
+/* tool node, host tools only: gather every record's tool-call `args` JSON into the output buffer
+ * (payload i = args of record i, empty when the record does not reach the tool). */
+int  ck_tool_args(ck_handle* h);
+/* tool node: run + publish plan + encode + route.  host_aux/host_aux_off: JSON return values per
+ * record (offsets[n+1]) for host tools, NULL for a device template. */
+int  ck_tool_plan(ck_handle* h, const uint8_t* host_aux, const int64_t* host_aux_off);
+/* same, aux blob already in HBM */
+int  ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const int64_t* dev_aux_off);
+
+/* agent fan-out (calfkit/nodes/agent.py:177-211 + nodes/base.py:73-88): one Call envelope per
+ * pending tool call of every record.  tool_names/topic strings: registry tool_name -> subscribe
+ * topic[0]; agent_name/callback: the agent's name and subscribe_topics[0]; frame ids are uuid7s
+ * built from (unix_ms, seed, output index). */
+int  ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const uint8_t* agent_name, uint32_t agent_name_len,
+                       const uint8_t* callback_topic, uint32_t callback_len,
+                       const uint8_t* tool_names, const uint32_t* tool_name_off,
+                       const uint8_t* tool_topics, const uint32_t* tool_topic_off, uint32_t ntools);
+int  ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout);
+
+/* results ---------------------------------------------------------------------------------------- */
+int  ck_sync(ck_handle* h);
+int  ck_out_size(ck_handle* h, uint64_t* out_bytes, uint32_t* n_payloads, uint32_t* n_publishes);  /* waits */
+int  ck_fetch_columns(ck_handle* h, uint32_t* host_cols /* CK_NUM_COLS * n, column-major */);
+int  ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off /* n_payloads+1 */,
+                     ck_publish* host_pubs /* n_publishes */);
+int  ck_fetch_topic_hist(ck_handle* h, uint32_t* host_hist, uint32_t n);
+
+/* introspection for benchmarks / tests ------------------------------------------------------------ */
+void* ck_stream(ck_handle* h);                     /* cudaStream_t of the handle */
+int  ck_device_buffers(ck_handle* h, void** in, void** in_off, void** out, void** out_off, void** cols);
+int  ck_profile(ck_handle* h, int enable);         /* record CUDA events around every kernel */
+int  ck_profile_read(ck_handle* h, float* ms /* CK_NUM_KERNELS */, uint32_t* launches /* CK_NUM_KERNELS */, int reset);
+
+enum { CK_K_WALK = 0, CK_K_PLAN, CK_K_SCAN, CK_K_EMIT, CK_K_ROUTE, CK_K_FANOUT, CK_NUM_KERNELS };
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,40 @@
+"""TEST INFRASTRUCTURE ONLY: g++ build of the device walker for CPU-side fuzzing."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(HERE, "libck_hostsim.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, "hostsim.cpp"),
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_walk.cuh"),
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_common.h")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-o", _LIB, srcs[0]])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.ck_host_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
+        _lib.ck_host_walk.restype = ctypes.c_int
+        _lib.ck_host_num_cols.restype = ctypes.c_int
+    return _lib
+
+
+def walk(payload: bytes):
+    """-> (accepted: bool, cols: np.ndarray[uint32])"""
+    L = lib()
+    cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
+    ok = L.ck_host_walk(payload, len(payload), cols.ctypes.data)
+    return bool(ok), cols

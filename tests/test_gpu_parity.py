@@ -1,0 +1,176 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle and the reference's golden
+vectors.  Bit-exact: byte equality of every payload, equality of (topic, key) of every publish."""
+import json
+import random
+
+import numpy as np
+import pytest
+from conftest import as_bytes, golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from calfkit.engine import BatchEngine
+    e = BatchEngine(device=0, max_records=1 << 16, max_in_bytes=256 << 20)
+    yield e
+    e.close()
+
+
+def _host_tool(fn):
+    import pydantic_core
+
+    def call(args_json: bytes) -> bytes:
+        v = pydantic_core.from_json(args_json)
+        if isinstance(v, str):            # args_as_dict: JSON string -> parsed (messages.py:1229-1240)
+            v = pydantic_core.from_json(v)
+        kwargs = v or {}
+        return pydantic_core.to_json(fn(**kwargs))
+    return call
+
+
+def _pubs(out):
+    return [(p.topic, p.key, p.payload) for p in out.publishes()]
+
+
+def _setup(engine, tool_name, template=None):
+    from calfkit import synth  # noqa: F401
+    topics = [f"tool.{tool_name}.input", f"tool.{tool_name}.output", "weather_agent.input"]
+    engine.register_topics(topics, num_partitions=8)
+    engine.set_tool_node(f"tool.{tool_name}.output", template)
+
+
+@pytest.mark.parametrize("use_template", [False, True])
+def test_tool_node_goldens(engine, use_template):
+    import tools_def
+    from calfkit import synth
+    from calfkit.engine import ToolTemplate
+    from calfkit.engine._lib import CK_ACT_RAISES, CK_NOT_CANONICAL, COL
+    for case in golden("tool_node.json"):
+        if use_template and case["tool"] != "get_weather":
+            continue
+        if case["name"] == "header_corr_differs":
+            continue   # header != deps.correlation_id never happens on the reference's own flows (client sets both)
+        _setup(engine, case["tool"], ToolTemplate.from_format("It's sunny in {location}") if use_template else None)
+        b = synth.pack([as_bytes(case["input"])])
+        if case["name"] == "noncanonical_valid":
+            engine.submit(b.data, b.offsets)
+            assert engine.columns()[COL["STATUS"], 0] == CK_NOT_CANONICAL   # left to the canonicaliser, loudly
+            continue
+        out = engine.run_tool_batch(b.data, b.offsets, None if use_template else _host_tool(tools_def.TOOLS[case["tool"]]))
+        if "raises" in case:
+            assert out.cols[COL["ACTION"], 0] == CK_ACT_RAISES and len(out.live()) == 0, case["name"]
+            continue
+        if use_template and case["name"] == "args_json_string":
+            # args given as a JSON *string*: the device template does not parse nested JSON -> loud, not silent
+            assert out.cols[COL["STATUS"], 0] != 0 and len(out.live()) == 0
+            continue
+        want = [(p["topic"], p["key"].encode() if p["key"] is not None else None, p["payload"].encode())
+                for p in case["publishes"]]
+        assert _pubs(out) == want, case["name"]
+
+
+def test_synthetic_batch_matches_oracle(engine):
+    import tools_def
+    from oracle import port
+    from calfkit import synth
+    from calfkit.engine import ToolTemplate
+    _setup(engine, "get_weather", ToolTemplate.from_format("It's sunny in {location}"))
+    recs = synth.tool_events(20000, seed=5) + synth.tool_events(3000, seed=6, size=None, full_history=True)
+    b = synth.pack(recs)
+    out = engine.run_tool_batch(b.data, b.offsets)
+    assert (out.cols[0] == 0).all()
+    node = port.ToolNode.of(tools_def.get_weather)
+    pubs = list(out.publishes())
+    assert len(pubs) == 2 * len(recs)
+    rng = random.Random(0)
+    for i in rng.sample(range(len(recs)), 400):
+        want = port.tool_node_event(node, recs[i])
+        assert [(p.topic, p.key, p.payload) for p in pubs[2 * i:2 * i + 2]] == [(t, k, pl) for (t, k, c, pl) in want]
+    # size-independent property at full batch size: every payload is again a canonical Envelope the
+    # engine itself accepts, one frame shorter, with exactly one more tool result
+    outs = [out.payload(i) for i in range(out.out_off.size - 1)]
+    b2 = synth.pack(outs)
+    engine.submit(b2.data, b2.offsets)
+    cols2 = engine.columns()
+    from calfkit.engine._lib import COL
+    assert (cols2[COL["STATUS"]] == 0).all()
+    assert (cols2[COL["NFRAMES"]] == out.cols[COL["NFRAMES"]] - 1).all()
+    # murmur2 partition of the key agrees with the Kafka default partitioner formula
+    live = out.live()
+    keyed = live[live["has_key"] == 1]
+    for p in keyed[:50]:
+        key = out.key_of(p)
+        assert int(p["partition"]) == (_murmur2(key) & 0x7FFFFFFF) % 8
+
+
+def _murmur2(data: bytes) -> int:
+    """Kafka's murmur2 (org.apache.kafka.common.utils.Utils.murmur2; aiokafka partitioner)."""
+    length = len(data)
+    seed = 0x9747B28C
+    m = 0x5BD1E995
+    r = 24
+    h = (seed ^ length) & 0xFFFFFFFF
+    for i in range(length // 4):
+        k = int.from_bytes(data[4 * i:4 * i + 4], "little")
+        k = (k * m) & 0xFFFFFFFF
+        k ^= k >> r
+        k = (k * m) & 0xFFFFFFFF
+        h = (h * m) & 0xFFFFFFFF
+        h ^= k
+    extra = length % 4
+    base = length & ~3
+    if extra == 3:
+        h ^= (data[base + 2] & 0xFF) << 16
+    if extra >= 2:
+        h ^= (data[base + 1] & 0xFF) << 8
+    if extra >= 1:
+        h ^= data[base] & 0xFF
+        h = (h * m) & 0xFFFFFFFF
+    h ^= h >> 13
+    h = (h * m) & 0xFFFFFFFF
+    h ^= h >> 15
+    return h
+
+
+def test_device_walker_equals_host_build_on_fuzz(engine):
+    """The g++ build of the walker was fuzzed against pydantic on the CPU (tests/test_walker_hostsim.py);
+    here the nvcc build must agree with it column for column on the same inputs."""
+    from hostsim import walk
+    from calfkit import synth
+    rng = random.Random(1)
+    seeds = [as_bytes(c["input"]) for c in golden("codec.json")] + synth.tool_events(50, seed=2) + \
+        synth.mixed_events(40, seed=3, hi=20000)
+    recs = list(seeds)
+    for _ in range(6000):
+        s = bytearray(rng.choice(seeds))
+        if not s:
+            continue
+        for _ in range(rng.choice([1, 1, 2])):
+            i = rng.randrange(len(s))
+            op = rng.randrange(3)
+            if op == 0:
+                s[i] = rng.randrange(256)
+            elif op == 1:
+                del s[i]
+            else:
+                s[i:i] = rng.choice([b'"', b"{", b"}", b",", b":", b" ", b"\\", b"0", b"null", b"1.5", b"\xc3\xa9", b"\xff"])
+            if not s:
+                break
+        recs.append(bytes(s))
+    b = synth.pack(recs)
+    engine.submit(b.data, b.offsets)
+    cols = engine.columns()
+    ncmp = 42   # walker-owned columns
+    for i, r in enumerate(recs):
+        if len(r) == 0:
+            assert cols[0, i] == 5
+            continue
+        ok, hc = walk(r)
+        assert (cols[0, i] == 0) == ok, (i, r[:200])
+        if ok:
+            assert (cols[:ncmp, i] == hc[:ncmp]).all(), i
