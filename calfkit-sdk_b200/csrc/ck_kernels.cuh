@@ -65,9 +65,7 @@ ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long a = off[i], b = off[i + 1];
-    WalkOut o;
-#pragma unroll
-    for (int k = 0; k < CK_NUM_COLS; k++) o.c[k] = 0;
+    WalkOut o; o.base = cols + i; o.stride = stride;
     u32 len = (u32)(b - a);
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
@@ -77,11 +75,8 @@ ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32
         cx.kfill = 0;
         status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_NOT_CANONICAL;
     }
-    o.c[CK_COL_STATUS] = status;
-    o.c[CK_COL_ERR] = stop;
-    // SoA store: lane i of a warp writes cols[k][i] -> 128 contiguous bytes per column per warp
-#pragma unroll
-    for (int k = 0; k < CK_COL_CALL_VAL_OFF; k++) cols[(size_t)k * stride + i] = o.c[k];
+    o.set(CK_COL_STATUS, status);
+    o.set(CK_COL_ERR, stop);
 }
 
 // ------------------------------------------------------------------------------------------------

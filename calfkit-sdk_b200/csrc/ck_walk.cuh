@@ -85,20 +85,46 @@ CK_HD u32 ck_ctz64(u64 x) {
 #endif
 }
 
-// literal compare, 8 bytes per step; `lit`/`L` are compile-time constants at every call site so the
-// `want` words fold to immediates
+// literal compare.  The literal is folded at compile time into 64-bit immediates; the unaligned
+// fetch + compare lives in two small out-of-line functions (8 and 16 bytes per call) so that the
+// ~150 literal sites of the schema cost a handful of instructions each instead of an inlined
+// unaligned-load sequence (instruction-cache footprint).
+CK_HD_NOINLINE bool ck_match8_core(const u8* g, u32 pos, u64 want, u64 mask) {
+    const u8* a = g + pos;
+    u32 s = (u32)((uintptr_t)a & 7);
+    const u64* q = (const u64*)((uintptr_t)a - s);
+    u64 got = Rd::ld64(q);
+    if (s) got = (got >> (8 * s)) | (Rd::ld64(q + 1) << (64 - 8 * s));
+    return ((got ^ want) & mask) == 0;
+}
+CK_HD_NOINLINE bool ck_match16_core(const u8* g, u32 pos, u64 want0, u64 want1, u64 mask1) {
+    const u8* a = g + pos;
+    u32 s = (u32)((uintptr_t)a & 7);
+    const u64* q = (const u64*)((uintptr_t)a - s);
+    u64 w0 = Rd::ld64(q), w1 = Rd::ld64(q + 1);
+    u64 g0 = w0, g1 = w1;
+    if (s) {
+        u64 w2 = Rd::ld64(q + 2);
+        g0 = (w0 >> (8 * s)) | (w1 << (64 - 8 * s));
+        g1 = (w1 >> (8 * s)) | (w2 << (64 - 8 * s));
+    }
+    return (g0 == want0) & (((g1 ^ want1) & mask1) == 0);
+}
+CK_HD u64 ck_lit_word(const char* lit, u32 L, u32 k) {      // bytes [k, k+8) of the literal, zero padded
+    u64 w = 0;
+#pragma unroll
+    for (u32 j = 0; j < 8; j++) if (k + j < L) w |= (u64)(u8)lit[k + j] << (8 * j);
+    return w;
+}
+CK_HD u64 ck_lit_mask(u32 L, u32 k) { return (L - k >= 8) ? ~0ull : (~0ull >> (8 * (8 - (L - k)))); }
 CK_HD bool ck_match(Rd& r, u32& pos, const char* lit, u32 L) {
     if (pos + L > r.n) return false;
+    u32 k = 0;
 #pragma unroll
-    for (u32 k = 0; k < L; k += 8) {
-        u32 m = (L - k < 8) ? (L - k) : 8;
-        u64 want = 0;
-#pragma unroll
-        for (u32 j = 0; j < m; j++) want |= (u64)(u8)lit[k + j] << (8 * j);
-        u64 got = r.load8(pos + k);
-        if (m < 8) got &= (~0ull >> (8 * (8 - m)));
-        if (got != want) return false;
+    for (; k + 8 < L; k += 16) {
+        if (!ck_match16_core(r.g, pos + k, ck_lit_word(lit, L, k), ck_lit_word(lit, L, k + 8), ck_lit_mask(L, k + 8))) return false;
     }
+    if (k < L) { if (!ck_match8_core(r.g, pos + k, ck_lit_word(lit, L, k), ck_lit_mask(L, k))) return false; }
     pos += L;
     return true;
 }
@@ -131,10 +157,12 @@ CK_HD bool ck_utf8_seq(Rd& r, u32& pos) {       // pos at a byte >= 0x80
     return true;
 }
 
-CK_HD bool ck_string(Rd& r, u32& pos, Span& out) {
-    if (!(pos < r.n) || r.at(pos) != '"') return false;
+// returns the position just after the closing quote, 0 on failure.  One out-of-line copy: the
+// walker calls it ~100 times per record and the code must stay inside the instruction cache.
+CK_HD_NOINLINE u32 ck_string_core(const u8* g, u32 n, u32 pos) {
+    Rd r; r.init(g, n);
+    if (!(pos < r.n) || r.at(pos) != '"') return 0;
     pos++;
-    u32 start = pos;
     for (;;) {
         if (pos >= r.n) return false;
         u64 x = r.load8(pos);
@@ -143,7 +171,7 @@ CK_HD bool ck_string(Rd& r, u32& pos, Span& out) {
         pos += ck_ctz64(special) >> 3;
         if (pos >= r.n) return false;
         u8 c = r.at(pos);
-        if (c == '"') { out.off = start; out.len = pos - start; pos++; return true; }
+        if (c == '"') return pos + 1;
         if (c == '\\') {
             if (pos + 1 >= r.n) return false;
             u8 e = r.at(pos + 1);
@@ -166,6 +194,13 @@ CK_HD bool ck_string(Rd& r, u32& pos, Span& out) {
     }
 }
 
+CK_HD bool ck_string(Rd& r, u32& pos, Span& out) {
+    u32 e = ck_string_core(r.g, r.n, pos);
+    if (!e) return false;
+    out.off = pos + 1; out.len = e - pos - 2; pos = e;
+    return true;
+}
+
 CK_HD bool ck_null(Rd& r, u32& pos) { return M("null"); }
 
 CK_HD bool ck_string_or_null(Rd& r, u32& pos, Span& out) {
@@ -179,7 +214,8 @@ CK_HD bool ck_string_or_null(Rd& r, u32& pos, Span& out) {
 // -?INT.FRAC with <= 15 significant digits, no trailing fractional zero (except the single ".0"),
 // magnitude in [1e-5, 1e16)  (DBL_DIG argument, DESIGN.md §canonical numbers).
 // -------------------------------------------------------------------------------------------------
-CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
+CK_HD_NOINLINE u32 ck_number_core(const u8* g, u32 n, u32 pos, bool allow_int, bool allow_float) {
+    Rd r; r.init(g, n);
     u32 p = pos;
     bool neg = false;
     if (p < r.n && r.at(p) == '-') { neg = true; p++; }
@@ -207,8 +243,7 @@ CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
         if (!allow_int) return false;
         if (neg && int_zero) return false;          // "-0" re-emits as "0"
         if (int_len > 4000) return false;           // CPython int<->str digit limit is 4300
-        pos = p;
-        return true;
+        return p;
     }
     if (!allow_float) return false;
     if (int_len > 16) return false;
@@ -230,9 +265,15 @@ CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
         else { if (lz > 4) return false; sig = frac_len - lz; }             // < 1e-5 prints as 1e-6 ...
     }
     if (sig > 15) return false;
-    pos = p;
+    return p;
+}
+CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
+    u32 e = ck_number_core(r.g, r.n, pos, allow_int, allow_float);
+    if (!e) return false;
+    pos = e;
     return true;
 }
+
 
 // -------------------------------------------------------------------------------------------------
 // Generic canonical JSON value ("Any" subtrees: provided_deps, args, metadata, return_value ...).
@@ -257,8 +298,9 @@ CK_HD u32 ck_hash_span(Rd& r, u32 off, u32 len) {
 }
 
 // base_depth: nesting level of the value inside the document (root object = depth 1)
-CK_HD_NOINLINE bool ck_any(Rd& r, u32& pos_io, u32 base_depth, AnyCtx& cx) {
-    u32 pos = pos_io;
+CK_HD_NOINLINE u32 ck_any_core(const u8* g, u32 n, u32 pos, u32 base_depth, AnyCtx* cxp) {
+    Rd r; r.init(g, n);
+    AnyCtx& cx = *cxp;
     u32 depth = 0;
     cx.kfill = 0;
     Span s;
@@ -289,7 +331,7 @@ CK_HD_NOINLINE bool ck_any(Rd& r, u32& pos_io, u32 base_depth, AnyCtx& cx) {
             if (opened) { in_obj = (cx.kind[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1; opened = false;
                           if (!in_obj) break; /* array: first element */ }
             else {
-                if (depth == 0) { pos_io = pos; return true; }
+                if (depth == 0) return pos;
                 in_obj = (cx.kind[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1;
                 if (pos >= r.n) return false;
                 u8 d = r.at(pos);
@@ -311,6 +353,12 @@ CK_HD_NOINLINE bool ck_any(Rd& r, u32& pos_io, u32 base_depth, AnyCtx& cx) {
     }
 }
 
+CK_HD bool ck_any(Rd& r, u32& pos, u32 base_depth, AnyCtx& cx) {
+    u32 e = ck_any_core(r.g, r.n, pos, base_depth, &cx);
+    if (!e) return false;
+    pos = e;
+    return true;
+}
 CK_HD bool ck_any_obj(Rd& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('{') && ck_any(r, pos, d, cx); }
 CK_HD bool ck_any_obj_or_null(Rd& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('n') ? ck_null(r, pos) : ck_any_obj(r, pos, d, cx); }
 
@@ -325,7 +373,8 @@ CK_HD bool ck_2d(Rd& r, u32 p, u32& v) {
     v = (u32)(a - '0') * 10 + (u32)(b - '0');
     return true;
 }
-CK_HD bool ck_datetime(Rd& r, u32& pos) {
+CK_HD_NOINLINE u32 ck_datetime_core(const u8* g, u32 n, u32 pos) {
+    Rd r; r.init(g, n);
     u32 p = pos;
     if (p + 21 > r.n) return false;                 // "YYYY-MM-DDTHH:MM:SS" + quotes
     if (r.at(p) != '"') return false;
@@ -360,7 +409,12 @@ CK_HD bool ck_datetime(Rd& r, u32& pos) {
         c = r.at(p);
     }
     if (c != '"') return false;
-    pos = p + 1;
+    return p + 1;
+}
+CK_HD bool ck_datetime(Rd& r, u32& pos) {
+    u32 e = ck_datetime_core(r.g, r.n, pos);
+    if (!e) return false;
+    pos = e;
     return true;
 }
 CK_HD bool ck_datetime_or_null(Rd& r, u32& pos) { return PEEK('n') ? ck_null(r, pos) : ck_datetime(r, pos); }
@@ -472,8 +526,9 @@ CK_HD bool ck_usage(Rd& r, u32& pos, AnyCtx& cx) {
 
 // ModelMessage = ModelRequest | ModelResponse (messages.py:1014-1041, :1292-1345, :1554).
 // returns 1 = request, 2 = response, 0 = no match
-CK_HD_NOINLINE u32 ck_message(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
-    u32 pos = pos_io;
+CK_HD_NOINLINE u32 ck_message_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* cxp) {   // -> end | kind << 30
+    Rd r; r.init(g, n);
+    AnyCtx& cx = *cxp;
     Span t;
     if (!M("{\"parts\":[")) return 0;
     u32 seen = 0;
@@ -508,8 +563,13 @@ CK_HD_NOINLINE u32 ck_message(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
             !ck_any_obj_or_null(r, pos, d + 1, cx) || !M("}")) return 0;
         kind = 2;
     }
-    pos_io = pos;
-    return kind;
+    return pos | (kind << 30);
+}
+CK_HD u32 ck_message(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+    u32 e = ck_message_core(r.g, r.n, pos, d, &cx);
+    if (!e) return 0;
+    pos = e & 0x3fffffffu;
+    return e >> 30;
 }
 
 // ToolDefinition (reference _vendor/pydantic_ai/tools.py:474-540)
@@ -527,10 +587,11 @@ CK_HD bool ck_tool_definition(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
 }
 
 // OverridesState | null (reference calfkit/models/state.py:22-26, node_schema.py:6-21)
-CK_HD_NOINLINE bool ck_overrides_or_null(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
-    u32 pos = pos_io;
+CK_HD_NOINLINE u32 ck_overrides_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* cxp) {
+    Rd r; r.init(g, n);
+    AnyCtx& cx = *cxp;
     Span t;
-    if (PEEK('n')) { if (!ck_null(r, pos)) return false; pos_io = pos; return true; }
+    if (PEEK('n')) { if (!ck_null(r, pos)) return 0; return pos; }
     if (!M("{\"override_agent_tools\":")) return false;
     if (PEEK('n')) { if (!ck_null(r, pos)) return false; }
     else {
@@ -547,8 +608,13 @@ CK_HD_NOINLINE bool ck_overrides_or_null(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) 
         }
         if (!M("]")) return false;
     }
-    if (!M("}")) return false;
-    pos_io = pos;
+    if (!M("}")) return 0;
+    return pos;
+}
+CK_HD bool ck_overrides_or_null(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+    u32 e = ck_overrides_core(r.g, r.n, pos, d, &cx);
+    if (!e) return false;
+    pos = e;
     return true;
 }
 
@@ -602,20 +668,21 @@ CK_HD void ck_skip_value(Rd& r, u32& pos) {
 // `kind`, then `part_kind`) with an `| Any` fallback (reference models/state.py:70,
 // _vendor/pydantic_ai/tools.py:189-210).  A value is a fixed point if it is the canonical form of
 // its tagged model, or if it carries no such tag and is generically canonical.
-CK_HD_NOINLINE bool ck_tool_result_value(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) {
-    u32 pos = pos_io;
+CK_HD_NOINLINE u32 ck_tool_result_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* cxp) {
+    Rd r; r.init(g, n);
+    AnyCtx& cx = *cxp;
     Span t;
     u32 start = pos;
     if (PEEK('{')) {
         if (M("{\"return_value\":")) {
             if (ck_any(r, pos, d + 1, cx) && M(",\"content\":") && ck_string_or_null(r, pos, t) && M(",\"metadata\":") &&
-                ck_any(r, pos, d + 1, cx) && M(",\"kind\":\"tool-return\"}")) { pos_io = pos; return true; }
+                ck_any(r, pos, d + 1, cx) && M(",\"kind\":\"tool-return\"}")) return pos;
         } else if (M("{\"message\":")) {
-            if (ck_string(r, pos, t) && M(",\"kind\":\"model-retry\"}")) { pos_io = pos; return true; }
+            if (ck_string(r, pos, t) && M(",\"kind\":\"model-retry\"}")) return pos;
         } else if (M("{\"content\":")) {
             if (ck_string(r, pos, t) && M(",\"tool_name\":") && ck_string_or_null(r, pos, t) && M(",\"tool_call_id\":") &&
                 ck_string(r, pos, t) && M(",\"timestamp\":") && ck_datetime(r, pos) && M(",\"part_kind\":\"retry-prompt\"}")) {
-                pos_io = pos; return true;
+                return pos;
             }
         }
         // not the canonical form of a tagged model: generic value, provided it carries no tag
@@ -643,24 +710,31 @@ CK_HD_NOINLINE bool ck_tool_result_value(Rd& r, u32& pos_io, u32 d, AnyCtx& cx) 
             if (p < end && r.at(p) == ',') p++;
         }
         if (have_kind ? tagged : part_tagged) return false;   // would be validated as the model: not proven here
-        pos_io = end;
-        return true;
+        return end;
     }
-    if (!ck_any(r, pos, d, cx)) return false;
-    pos_io = pos;
+    if (!ck_any(r, pos, d, cx)) return 0;
+    return pos;
+}
+CK_HD bool ck_tool_result_value(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+    u32 e = ck_tool_result_core(r.g, r.n, pos, d, &cx);
+    if (!e) return false;
+    pos = e;
     return true;
 }
 
 // -------------------------------------------------------------------------------------------------
 // Whole Envelope.  On success fills cols[] (spans relative to the record start).
 // -------------------------------------------------------------------------------------------------
+// column sink: device = the SoA table in HBM (lane i of a warp owns element i of every column, so
+// a convergent warp writes 128 contiguous bytes per column); host tests = a plain array (stride 1)
 struct WalkOut {
-    u32 c[CK_NUM_COLS];
+    u32* base; size_t stride;
+    CK_HD void set(u32 col, u32 v) { base[(size_t)col * stride] = v; }
 };
 
-#define SETSPAN(COL, a, b) do { o.c[COL] = (a); o.c[COL + 1] = (b) - (a); } while (0)
+#define SETSPAN(COL, a, b) do { o.set(COL, (a)); o.set(COL + 1, (b) - (a)); } while (0)
 
-CK_HD_NOINLINE bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
+CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     u32 pos = 0;
     Span t;
     stop = 0;
@@ -754,7 +828,7 @@ CK_HD_NOINLINE bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     // ---- context.deps ----------------------------------------------------------------------
     if (!M("},\"deps\":{\"correlation_id\":")) FAIL;
     if (!ck_string(r, pos, t)) FAIL;
-    o.c[CK_COL_CORR_OFF] = t.off; o.c[CK_COL_CORR_LEN] = t.len;
+    o.set(CK_COL_CORR_OFF, t.off); o.set(CK_COL_CORR_LEN, t.len);
     if (!M(",\"provided_deps\":")) FAIL;
     a = pos;
     if (!ck_any_obj(r, pos, 4, cx)) FAIL;
@@ -764,7 +838,7 @@ CK_HD_NOINLINE bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M("}},\"internal_workflow_state\":{\"call_stack\":{\"_internal_list\":[")) FAIL;
     a = pos - 1;
     u32 nframes = 0;
-    o.c[CK_COL_NARGS] = CK_NARGS_NULL;
+    o.set(CK_COL_NARGS, CK_NARGS_NULL);
     if (!PEEK(']')) {
         for (;;) {
             u32 f0 = pos;
@@ -801,11 +875,11 @@ CK_HD_NOINLINE bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             nframes++;
             // the LAST frame is the current one (Stack.peek, reference models/session_context.py:26-30)
             SETSPAN(CK_COL_TOP_OFF, f0, pos);
-            o.c[CK_COL_TGT_OFF] = tgt.off; o.c[CK_COL_TGT_LEN] = tgt.len;
-            o.c[CK_COL_CB_OFF] = cb.off; o.c[CK_COL_CB_LEN] = cb.len;
-            o.c[CK_COL_NARGS] = nargs; o.c[CK_COL_ARGKINDS] = kinds;
-            o.c[CK_COL_ARG0_OFF] = a0.off; o.c[CK_COL_ARG0_LEN] = a0.len;
-            o.c[CK_COL_ARG1_OFF] = a1.off; o.c[CK_COL_ARG1_LEN] = a1.len;
+            o.set(CK_COL_TGT_OFF, tgt.off); o.set(CK_COL_TGT_LEN, tgt.len);
+            o.set(CK_COL_CB_OFF, cb.off); o.set(CK_COL_CB_LEN, cb.len);
+            o.set(CK_COL_NARGS, nargs); o.set(CK_COL_ARGKINDS, kinds);
+            o.set(CK_COL_ARG0_OFF, a0.off); o.set(CK_COL_ARG0_LEN, a0.len);
+            o.set(CK_COL_ARG1_OFF, a1.off); o.set(CK_COL_ARG1_LEN, a1.len);
             SETSPAN(CK_COL_FOV_OFF, ov0, ov1);
             if (PEEK(',')) { pos++; continue; }
             break;
@@ -813,7 +887,7 @@ CK_HD_NOINLINE bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     }
     if (!M("]")) FAIL;
     SETSPAN(CK_COL_FRAMES_OFF, a, pos);
-    o.c[CK_COL_NFRAMES] = nframes;
+    o.set(CK_COL_NFRAMES, nframes);
     if (!M("},\"metadata\":")) FAIL;
     a = pos;
     if (!ck_any(r, pos, 3, cx)) FAIL;

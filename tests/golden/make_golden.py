@@ -105,7 +105,17 @@ def main():
     add("existing_same_result_last", "get_weather",
         base.replace('"tool_results":{}', '"tool_results":{' + other + ',' + same + '}').encode())
     # args given as a JSON string, as null (-> {}), and empty object
-    add("args_json_string", "get_weather", base.replace('"args":{"location":', '"args":"{\\"location\\": \\"Rome\\"}","zz":{"location":', 1).encode())
+    # args given as a JSON string / null (args_as_dict: str -> from_json, falsy -> {}), canonical and
+    # with an unknown key alongside (valid but not a fixed point: the key is dropped on re-emit)
+    a0 = base.index('"args":{"location":')
+    a1 = base.index('}', a0) + 1
+    add("args_json_string", "get_weather", (base[:a0] + '"args":"{\\"location\\": \\"Rome\\"}"' + base[a1:]).encode())
+    add("args_json_string_unknown_key", "get_weather", base.replace('"args":{"location":', '"args":"{\\"location\\": \\"Rome\\"}","zz":{"location":', 1).encode())
+    na = synth.tool_events(1, seed=16, size=None, tool_name="no_args")[0].decode()
+    n0 = na.index('"args":{"location":')
+    n1 = na.index('}', n0) + 1
+    add("no_args_tool_args_null", "no_args", (na[:n0] + '"args":null' + na[n1:]).encode())
+    add("no_args_tool_args_empty", "no_args", (na[:n0] + '"args":{}' + na[n1:]).encode())
     # frame overrides replace state.overrides (prepare_context)
     ov = ('{"override_agent_tools":[{"node_id":"tool_x","subscribe_topics":["tool.x.input"],"publish_topic":null,'
           '"tool_schema":{"name":"x","parameters_json_schema":{"type":"object","properties":{}},"description":null,'
@@ -120,10 +130,8 @@ def main():
     add("any_values", "get_weather", base.replace('"temp_instructions":null,"metadata":null',
         '"temp_instructions":"be brief","metadata":{"n":[1,-2,3.5,1e+22,1e-7,-0.0,12345678901234567890123],"s":"é\\n","o":{"a":null,"b":true}}').encode())
     add("wf_metadata", "get_weather", (base[:-len('"metadata":null}}')] + '"metadata":{"trace":["a",1]}}}').encode())
-    add("no_args_tool", "no_args", synth.tool_events(1, seed=16, size=None, tool_name="no_args")[0].replace(b'{"location":', b'{"unused":') if False else
-        synth.tool_events(1, seed=16, size=None, tool_name="no_args")[0].replace(b'"args":{"location":', b'"args":null,"zz":{"location":', 1))
     # three frames deep
-    deep = base.replace('"_internal_list":[', '"_internal_list":[' + synth.frame("root.input", "calf-client-reply-0", ["a", 1, None, {"k": [1.5]}], "0" * 32) + ",")
+    deep = base.replace('"_internal_list":[', '"_internal_list":[' + synth.frame("root.input", "calf-client-reply-0", ["ARGS"], "0" * 32).replace('["ARGS"]', '["a",1,null,{"k":[1.5]}]') + ",")
     add("three_frames", "get_weather", deep.encode())
     # header correlation id differing from deps (key comes from the header value)
     add("header_corr_differs", "get_weather", base.encode(), header_corr="header-corr-id")

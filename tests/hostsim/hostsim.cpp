@@ -17,13 +17,13 @@ extern "C" int ck_host_walk(const uint8_t* buf, uint32_t len, uint32_t* cols /* 
     uint8_t* rec = base + 64 + (len % 7);     // vary the alignment of the record start
     memcpy(rec, buf, len);
     Rd r; r.init(rec, len);
-    WalkOut o; memset(&o, 0, sizeof o);
+    memset(cols, 0, sizeof(uint32_t) * CK_NUM_COLS);
+    WalkOut o; o.base = cols; o.stride = 1;
     AnyCtx cx; memset(&cx, 0, sizeof cx);
     u32 stop = 0;
     bool ok = ck_walk_envelope(r, o, cx, stop);
-    o.c[CK_COL_STATUS] = ok ? CK_OK : CK_NOT_CANONICAL;
-    o.c[CK_COL_ERR] = stop;
-    memcpy(cols, o.c, sizeof o.c);
+    cols[CK_COL_STATUS] = ok ? CK_OK : CK_NOT_CANONICAL;
+    cols[CK_COL_ERR] = stop;
     return ok ? 1 : 0;
 }
 extern "C" int ck_host_num_cols() { return CK_NUM_COLS; }
