@@ -92,15 +92,35 @@ class BatchOutput:
                           int(p["partition"]))
 
 
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def device_uuid7_hex(unix_ms: int, seed: int, index: int) -> str:
+    """The frame id the fan-out kernel writes for payload slot `index` (csrc/ck_kernels.cuh
+    ck_uuid7_hex) — exposed so parity tests can inject the same ids into the oracle."""
+    r0, r1 = _splitmix64((seed + 2 * index) & _M64), _splitmix64((seed + 2 * index + 1) & _M64)
+    hi = ((unix_ms & 0xFFFFFFFFFFFF) << 16) | 0x7000 | (r0 & 0xFFF)
+    lo = (0x2 << 62) | (r1 & 0x3FFFFFFFFFFFFFFF)
+    return f"{hi:016x}{lo:016x}"
+
+
 class BatchEngine:
     def __init__(self, device: int = 0, max_records: int = 1 << 16, max_in_bytes: int = 128 << 20,
-                 max_out_bytes: int | None = None, max_aux_bytes: int | None = None):
+                 max_out_bytes: int | None = None, max_aux_bytes: int | None = None, max_payloads: int | None = None):
         self.lib = _lib.load()
         self.max_records, self.max_in = max_records, max_in_bytes
+        self.max_payloads = max_payloads if max_payloads is not None else max_records
         self.max_out = max_out_bytes if max_out_bytes is not None else max_in_bytes + 512 * max_records
-        self.max_aux = max_aux_bytes if max_aux_bytes is not None else max(1 << 20, max_in_bytes // 4)
+        self.max_aux = max_aux_bytes if max_aux_bytes is not None else max(1 << 20, max_in_bytes // 4, 32 * self.max_payloads)
         h = C.c_void_p()
-        if self.lib.ck_create(device, self.max_in, self.max_out, max_records, self.max_aux, C.byref(h)):
+        if self.lib.ck_create(device, self.max_in, self.max_out, max_records, self.max_payloads, self.max_aux, C.byref(h)):
             raise EngineError(self.lib.ck_last_error(None).decode())
         self.h = h
         self.topic_names: dict[int, str] = {}
@@ -154,6 +174,30 @@ class BatchEngine:
         offs = np.zeros(len(template.pieces) + 1, dtype=np.uint32)
         np.cumsum([len(p) for p in template.pieces], out=offs[1:])
         self._check(self.lib.ck_set_tool_node(self.h, pid, len(kinds), ptr(kinds), ptr(blob), ptr(offs)))
+
+    def set_agent_node(self, agent_name: str, callback_topic: str, publish_topic: str | None,
+                       registry: dict[str, str]) -> None:
+        """registry: tool_name -> the tool node's subscribe_topics[0] (reference nodes/agent.py:71-75)."""
+        missing = [t for t in list(registry.values()) + ([publish_topic] if publish_topic else []) if t not in self.topic_ids]
+        if missing:
+            raise EngineError(f"topics not registered: {missing}")
+        esc = lambda s: json.dumps(s, ensure_ascii=False)[1:-1].encode()   # noqa: E731  spliced inside JSON strings
+        names = [esc(k) for k in registry]
+        topics = [esc(v) for v in registry.values()]
+        nb = np.frombuffer(b"".join(names) or b"\0", dtype=np.uint8)
+        tb = np.frombuffer(b"".join(topics) or b"\0", dtype=np.uint8)
+        no = np.zeros(len(names) + 1, dtype=np.uint32); np.cumsum([len(x) for x in names], out=no[1:])
+        to = np.zeros(len(topics) + 1, dtype=np.uint32); np.cumsum([len(x) for x in topics], out=to[1:])
+        an, cb = esc(agent_name), esc(callback_topic)
+        anb, cbb = np.frombuffer(an, dtype=np.uint8), np.frombuffer(cb, dtype=np.uint8)
+        pid = self.topic_ids[publish_topic] if publish_topic else -1
+        self._check(self.lib.ck_set_agent_node(self.h, pid, ptr(anb), len(an), ptr(cbb), len(cb), ptr(nb), ptr(no),
+                                               ptr(tb), ptr(to), len(names)))
+        ids = np.asarray([self.topic_ids[v] for v in registry.values()], dtype=np.uint32)
+        self._check(self.lib.ck_set_agent_tool_topic_ids(self.h, ptr(ids), len(ids)))
+
+    def fanout_plan(self, unix_ms: int, seed: int, max_fanout: int = 128) -> None:
+        self._check(self.lib.ck_fanout_plan(self.h, unix_ms, seed, max_fanout))
 
     # ------------------------------------------------------------------------------------------
     def submit(self, data: np.ndarray, offsets: np.ndarray) -> None:

@@ -11,6 +11,7 @@
 
 static_assert(sizeof(ck_publish) == sizeof(ck_pub), "ck_publish must mirror ck_pub");
 
+#define CK_LIT_CAP (256 * 1024)
 #define CK_PAD 256   // tail padding of every byte buffer (readers may touch a few bytes past a span)
 
 static thread_local std::string g_create_error;
@@ -27,7 +28,9 @@ struct ck_handle {
     u8* d_aux = nullptr; long long* d_aux_off = nullptr;
     u32* d_cols = nullptr; ck_out_desc* d_descs = nullptr; u32* d_pay_len = nullptr; ck_pub* d_pubs = nullptr;
     unsigned long long* d_tile_sum = nullptr; unsigned long long* d_grand = nullptr;
-    u8* d_lit = nullptr; ck_tool_cfg* d_tool_cfg = nullptr;
+    u8* d_lit = nullptr; ck_tool_cfg* d_tool_cfg = nullptr; ck_agent_cfg* d_agent_cfg = nullptr;
+    u32* d_counts = nullptr; long long* d_slot_base = nullptr; u32* d_agent_tables = nullptr;
+    bool agent_set = false; ck_agent_cfg h_agent_cfg{};
     u32* d_topic_hist = nullptr;
     // topic table
     ck_topic_table tab{}; u32 *d_tab_hash = nullptr, *d_tab_off = nullptr, *d_tab_len = nullptr; int32_t* d_tab_id = nullptr; u8* d_tab_names = nullptr;
@@ -37,9 +40,12 @@ struct ck_handle {
     uint32_t n = 0, n_payloads = 0, n_pubs = 0;
     bool tool_set = false; ck_tool_cfg h_tool_cfg{};
     unsigned long long* h_grand = nullptr;   // pinned
-    // profiling
+    // profiling: asynchronous event pairs around every kernel, read back (and summed) on demand so
+    // that timing the kernels does not serialise the stream during a timed region
     bool profile = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;                    // 2 events per recorded launch
+    std::vector<int> ev_kernel;                          // kernel id of each recorded pair
+    size_t ev_used = 0;
     float k_ms[CK_NUM_KERNELS] = {0}; uint32_t k_n[CK_NUM_KERNELS] = {0};
 };
 
@@ -50,22 +56,32 @@ struct ck_handle {
 static int fail(ck_handle* h, const char* msg) { h->err = msg; return 1; }
 
 struct KTimer {
-    ck_handle* h; int k;
-    KTimer(ck_handle* hh, int kk) : h(hh), k(kk) { if (h->profile) cudaEventRecord(h->ev0, h->stream); }
-    ~KTimer() {
-        if (h->profile) {
-            cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1);
-            float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->k_ms[k] += ms; h->k_n[k]++;
+    ck_handle* h; int k; size_t slot;
+    KTimer(ck_handle* hh, int kk) : h(hh), k(kk), slot(0) {
+        if (!h->profile) return;
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            for (int j = 0; j < 64; j++) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
         }
+        slot = h->ev_used; h->ev_used += 2; h->ev_kernel.push_back(k);
+        cudaEventRecord(h->ev_pool[slot], h->stream);
     }
+    ~KTimer() { if (h->profile) cudaEventRecord(h->ev_pool[slot + 1], h->stream); }
 };
+static void profile_collect(ck_handle* h) {
+    cudaStreamSynchronize(h->stream);
+    for (size_t p = 0; p * 2 < h->ev_used; p++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[2 * p], h->ev_pool[2 * p + 1]) == cudaSuccess) { h->k_ms[h->ev_kernel[p]] += ms; h->k_n[h->ev_kernel[p]]++; }
+    }
+    h->ev_used = 0; h->ev_kernel.clear();
+}
 
 extern "C" int ck_version(void) { return 1; }
 
 extern "C" const char* ck_last_error(ck_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_bytes, uint32_t max_records,
-                         uint64_t max_aux_bytes, ck_handle** out) {
+                         uint32_t max_payloads, uint64_t max_aux_bytes, ck_handle** out) {
     *out = nullptr;
     ck_handle* h = new ck_handle();
     auto bail = [&](const char* what, cudaError_t e) {
@@ -80,7 +96,7 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     if (prop.major != 10) { g_create_error = "ck_create: this library is built for sm_100a (B200) only"; ck_destroy(h); return 1; }
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     h->max_in = max_in_bytes; h->max_out = max_out_bytes; h->max_aux = max_aux_bytes; h->max_records = max_records;
-    h->max_payloads = max_records; h->max_pubs = 2 * max_records;
+    h->max_payloads = max_payloads > max_records ? max_payloads : max_records; h->max_pubs = 2 * h->max_payloads;
 #define ALLOC(p, bytes) if ((e = cudaMalloc((void**)&(p), (bytes))) != cudaSuccess) return bail("cudaMalloc " #p, e)
     ALLOC(h->d_in, max_in_bytes + CK_PAD);
     ALLOC(h->d_in_off, sizeof(long long) * ((size_t)max_records + 1));
@@ -94,16 +110,17 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     ALLOC(h->d_pubs, sizeof(ck_pub) * (size_t)h->max_pubs);
     ALLOC(h->d_tile_sum, sizeof(unsigned long long) * ((size_t)h->max_payloads / CK_SCAN_TILE + 2));
     ALLOC(h->d_grand, sizeof(unsigned long long));
-    ALLOC(h->d_lit, 4096 + CK_PAD);
+    ALLOC(h->d_lit, CK_LIT_CAP + CK_PAD);
     ALLOC(h->d_tool_cfg, sizeof(ck_tool_cfg));
+    ALLOC(h->d_agent_cfg, sizeof(ck_agent_cfg));
+    ALLOC(h->d_counts, sizeof(u32) * (size_t)max_records);
+    ALLOC(h->d_slot_base, sizeof(long long) * ((size_t)max_records + 1));
     h->hist_cap = 4096;
     ALLOC(h->d_topic_hist, sizeof(u32) * h->hist_cap);
 #undef ALLOC
     cudaMemsetAsync(h->d_in + max_in_bytes, 0, CK_PAD, h->stream);
     cudaMemsetAsync(h->d_topic_hist, 0, sizeof(u32) * h->hist_cap, h->stream);
     if ((e = cudaMallocHost((void**)&h->h_grand, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMallocHost", e);
-    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("init sync", e);
     *out = h;
     return 0;
@@ -114,12 +131,11 @@ extern "C" void ck_destroy(ck_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_cols, h->d_descs, h->d_pay_len,
-                    h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
+                    h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_agent_cfg, h->d_counts, h->d_slot_base, h->d_agent_tables, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
                     h->d_tab_len, h->d_tab_id, h->d_tab_names};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_grand) cudaFreeHost(h->h_grand);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -181,11 +197,11 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
         c.tpl_kind[k] = kinds[k]; c.tpl_off[k] = (u32)pool.size(); c.tpl_len[k] = part_offsets[k + 1] - part_offsets[k];
         pool.insert(pool.end(), blob + part_offsets[k], blob + part_offsets[k + 1]);
     }
-    if (pool.size() > 4096) return fail(h, "ck_set_tool_node: literal pool overflow");
+    if (pool.size() > CK_LIT_CAP) return fail(h, "ck_set_tool_node: literal pool overflow");
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaMemcpy(h->d_lit, pool.data(), pool.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->d_tool_cfg, &c, sizeof c, cudaMemcpyHostToDevice));
-    h->h_tool_cfg = c; h->tool_set = true;
+    h->h_tool_cfg = c; h->tool_set = true; h->agent_set = false;
     return 0;
 }
 
@@ -216,17 +232,20 @@ extern "C" int ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64
     return launch_walk(h);
 }
 
-static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
-    u32 ntiles = (npay + CK_SCAN_TILE - 1) / CK_SCAN_TILE;
-    {
-        KTimer t(h, CK_K_SCAN);
-        if (npay) {
-            ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_pay_len, npay, h->d_tile_sum);
-            ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_tile_sum, ntiles, h->d_grand);
-            ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_pay_len, npay, h->d_tile_sum, h->d_out_off);
-        }
-        CUDA_TRY(h, cudaGetLastError());
+static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off) {
+    KTimer t(h, CK_K_SCAN);
+    u32 ntiles = (n + CK_SCAN_TILE - 1) / CK_SCAN_TILE;
+    if (n) {
+        ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum);
+        ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_tile_sum, ntiles, h->d_grand);
+        ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum, out_off);
     }
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
+    if (run_scan(h, h->d_pay_len, npay, h->d_out_off)) return 1;
     {
         KTimer t(h, CK_K_EMIT);
         if (npay) {
@@ -292,11 +311,98 @@ extern "C" int ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const i
     return tool_plan_common(h, dev_aux, (const long long*)dev_aux_off);
 }
 
-extern "C" int ck_set_agent_node(ck_handle* h, int32_t, const uint8_t*, uint32_t, const uint8_t*, uint32_t,
-                                 const uint8_t*, const uint32_t*, const uint8_t*, const uint32_t*, uint32_t) {
-    return fail(h, "ck_set_agent_node: not built yet");
+extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const uint8_t* agent_name, uint32_t agent_name_len,
+                                 const uint8_t* callback_topic, uint32_t callback_len,
+                                 const uint8_t* tool_names, const uint32_t* tool_name_off,
+                                 const uint8_t* tool_topics, const uint32_t* tool_topic_off, uint32_t ntools) {
+    // agent_name / callback_topic / tool topics are spliced into JSON strings: the caller passes them
+    // already JSON-escaped (the Python binding does); tool_names are compared against raw JSON bytes.
+    cudaSetDevice(h->device);
+    std::vector<u8> pool;
+    auto puts = [&](const std::string& s, uint32_t out[2]) { out[0] = (u32)pool.size(); out[1] = (u32)s.size(); pool.insert(pool.end(), s.begin(), s.end()); };
+    ck_agent_cfg c{};
+    c.publish_topic_id = publish_topic_id;
+    c.ntools = ntools;
+    std::string an((const char*)agent_name, agent_name_len), cb((const char*)callback_topic, callback_len);
+    puts(",", c.lit_comma);
+    puts("\",\"" + an + "\"],\"frame_id\":\"", c.lit_mid);
+    puts("\",\"overrides\":null}", c.lit_tail);
+    std::vector<u32> tab(5 * (size_t)ntools);
+    for (u32 k = 0; k < ntools; k++) {
+        std::string nm((const char*)tool_names + tool_name_off[k], tool_name_off[k + 1] - tool_name_off[k]);
+        std::string tp((const char*)tool_topics + tool_topic_off[k], tool_topic_off[k + 1] - tool_topic_off[k]);
+        uint32_t sp[2];
+        puts(nm, sp); tab[k] = sp[0]; tab[ntools + k] = sp[1];
+        puts("{\"target_topic\":\"" + tp + "\",\"callback_topic\":\"" + cb + "\",\"input_args\":[\"", sp);
+        tab[2 * ntools + k] = sp[0]; tab[3 * ntools + k] = sp[1];
+        // registered id of the tool's topic, if any (host-side probe of the same table the device uses is
+        // not needed: ids are resolved by the route kernel when this is 0xffffffff)
+        tab[4 * ntools + k] = 0xffffffffu;
+    }
+    if (pool.size() > CK_LIT_CAP) return fail(h, "ck_set_agent_node: literal pool overflow");
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->d_agent_tables) { cudaFree(h->d_agent_tables); h->d_agent_tables = nullptr; }
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_agent_tables, sizeof(u32) * (tab.size() + 1)));
+    CUDA_TRY(h, cudaMemcpy(h->d_agent_tables, tab.data(), sizeof(u32) * tab.size(), cudaMemcpyHostToDevice));
+    c.tool_name_off = h->d_agent_tables; c.tool_name_len = h->d_agent_tables + ntools;
+    c.tool_lit_off = h->d_agent_tables + 2 * ntools; c.tool_lit_len = h->d_agent_tables + 3 * ntools;
+    c.tool_topic_id = h->d_agent_tables + 4 * ntools;
+    CUDA_TRY(h, cudaMemcpy(h->d_lit, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_agent_cfg, &c, sizeof c, cudaMemcpyHostToDevice));
+    h->h_agent_cfg = c; h->agent_set = true; h->tool_set = false;
+    return 0;
 }
-extern "C" int ck_fanout_plan(ck_handle* h, uint64_t, uint64_t, uint32_t) { return fail(h, "ck_fanout_plan: not built yet"); }
+
+extern "C" int ck_set_agent_tool_topic_ids(ck_handle* h, const uint32_t* ids, uint32_t ntools) {
+    cudaSetDevice(h->device);
+    if (!h->agent_set || ntools != h->h_agent_cfg.ntools) return fail(h, "ck_set_agent_tool_topic_ids: agent node not set / size mismatch");
+    CUDA_TRY(h, cudaMemcpy(h->d_agent_tables + 4 * (size_t)ntools, ids, sizeof(u32) * ntools, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout) {
+    cudaSetDevice(h->device);
+    if (!h->agent_set) return fail(h, "ck_fanout_plan: call ck_set_agent_node first");
+    u32 n = h->n;
+    {
+        KTimer t(h, CK_K_FANOUT);
+        if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, n, h->d_cols, n, h->d_agent_cfg, max_fanout, h->d_counts);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_counts, n, h->d_slot_base)) return 1;
+    *h->h_grand = 0;
+    if (n) CUDA_TRY(h, cudaMemcpyAsync(h->h_grand, h->d_grand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    unsigned long long slots = *h->h_grand;
+    if (slots > h->max_payloads) return fail(h, "ck_fanout_plan: more payloads than max_payloads");
+    if (slots * 32 > h->max_aux) return fail(h, "ck_fanout_plan: max_aux_bytes too small for the frame ids (32 B per payload)");
+    {
+        KTimer t(h, CK_K_FANOUT);
+        if (n) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
+            h->d_slot_base, unix_ms, seed, h->d_aux, h->d_descs, h->d_pay_len, h->d_pubs);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (scan_emit(h, (u32)slots, h->d_aux)) return 1;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        u32 npubs = 2 * (u32)slots;
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->d_cols, n, h->d_pubs, npubs,
+            h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
+        CUDA_TRY(h, cudaGetLastError());
+        h->n_pubs = npubs;
+    }
+    return 0;
+}
+
+extern "C" int ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64_t* dev_src_off, const int64_t* dev_src_len,
+                               uint32_t n, uint8_t* dev_dst, const int64_t* dev_dst_off) {
+    cudaSetDevice(h->device);
+    KTimer t(h, CK_K_EMIT);
+    if (n) ck_gather_spans_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(dev_src, (const long long*)dev_src_off, (const long long*)dev_src_len, n,
+                                                                     dev_dst, (const long long*)dev_dst_off);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
 
 extern "C" int ck_sync(ck_handle* h) {
     cudaSetDevice(h->device);
@@ -347,6 +453,13 @@ extern "C" int ck_fetch_topic_hist(ck_handle* h, uint32_t* host_hist, uint32_t n
 
 extern "C" void* ck_stream(ck_handle* h) { return (void*)h->stream; }
 
+extern "C" int ck_device_buffers2(ck_handle* h, void** pubs, void** pay_len, void** descs) {
+    if (pubs) *pubs = h->d_pubs;
+    if (pay_len) *pay_len = h->d_pay_len;
+    if (descs) *descs = h->d_descs;
+    return 0;
+}
+
 extern "C" int ck_device_buffers(ck_handle* h, void** in, void** in_off, void** out, void** out_off, void** cols) {
     if (in) *in = h->d_in;
     if (in_off) *in_off = h->d_in_off;
@@ -356,9 +469,11 @@ extern "C" int ck_device_buffers(ck_handle* h, void** in, void** in_off, void** 
     return 0;
 }
 
-extern "C" int ck_profile(ck_handle* h, int enable) { h->profile = enable != 0; return 0; }
+extern "C" int ck_profile(ck_handle* h, int enable) { cudaSetDevice(h->device); profile_collect(h); h->profile = enable != 0; return 0; }
 
 extern "C" int ck_profile_read(ck_handle* h, float* ms, uint32_t* launches, int reset) {
+    cudaSetDevice(h->device);
+    profile_collect(h);
     for (int k = 0; k < CK_NUM_KERNELS; k++) { ms[k] = h->k_ms[k]; launches[k] = h->k_n[k]; if (reset) { h->k_ms[k] = 0; h->k_n[k] = 0; } }
     return 0;
 }

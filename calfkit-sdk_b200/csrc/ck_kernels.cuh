@@ -269,6 +269,156 @@ ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off
 }
 
 // ------------------------------------------------------------------------------------------------
+// agent fan-out: Agent.run's list[Call] branch (reference nodes/agent.py:177-211) followed by
+// _publish_action's fan-out branch (nodes/base.py:73-88): every pending tool call (in tool_calls,
+// not yet in tool_results) becomes one envelope = input state + one pushed CallFrame
+//   {target_topic: registry[tool_name].subscribe_topics[0], callback_topic: self.subscribe_topics[0],
+//    input_args: [tool_call_id, agent_name], frame_id: fresh uuid7, overrides: null}
+// (models/session_context.py:33-39,62-70).  One pending call -> a single Call whose envelope is
+// also the handler's return value; >1 -> list[Call] and the handler returns the ORIGINAL envelope.
+// ------------------------------------------------------------------------------------------------
+struct ck_agent_cfg {
+    int32_t  publish_topic_id;
+    uint32_t lit_comma[2];             // ,
+    uint32_t lit_mid[2];               // ","<agent_name>"],"frame_id":"
+    uint32_t lit_tail[2];              // ","overrides":null}
+    uint32_t ntools;
+    // per tool k (device arrays): name span + frame-prefix literal span in the pool:
+    //   {"target_topic":"<topic_k>","callback_topic":"<callback>","input_args":["
+    const uint32_t* tool_name_off; const uint32_t* tool_name_len;
+    const uint32_t* tool_lit_off;  const uint32_t* tool_lit_len;
+    const uint32_t* tool_topic_id;     // registered id of the tool's subscribe topic (or 0xffffffff)
+};
+
+__device__ __forceinline__ unsigned long long ck_splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// uuid7 hex (RFC 9562): 48-bit unix ms | 0x7 | 12 random | 0b10 | 62 random, from (seed, index)
+__device__ __forceinline__ void ck_uuid7_hex(unsigned long long unix_ms, unsigned long long seed, unsigned long long idx, u8* out32) {
+    unsigned long long r0 = ck_splitmix64(seed + 2 * idx), r1 = ck_splitmix64(seed + 2 * idx + 1);
+    unsigned long long hi = ((unix_ms & 0xFFFFFFFFFFFFull) << 16) | 0x7000ull | (r0 & 0xFFFull);
+    unsigned long long lo = (0x2ull << 62) | (r1 & 0x3FFFFFFFFFFFFFFFull);
+    const char* hx = "0123456789abcdef";
+#pragma unroll
+    for (int k = 0; k < 16; k++) { out32[k] = hx[(hi >> (60 - 4 * k)) & 15]; out32[16 + k] = hx[(lo >> (60 - 4 * k)) & 15]; }
+}
+
+// pass 1: how many payloads does each record produce (pending + 1 for the handler return)
+__global__ void __launch_bounds__(128)
+ck_fanout_count_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
+                       const ck_agent_cfg* __restrict__ cfgp, u32 max_fanout, u32* __restrict__ counts) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#define COL(k) cols[(size_t)(k) * stride + i]
+    counts[i] = 0;
+    COL(CK_COL_NOUT) = 0;
+    if (COL(CK_COL_STATUS) != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; return; }
+    long long a = off[i];
+    Rd r; r.init(in + a, (u32)(off[i + 1] - a));
+    if (COL(CK_COL_NFRAMES) == 0) { COL(CK_COL_ACTION) = CK_ACT_RAISES; return; }
+    u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF);
+    u32 pos = tc + 1, pending = 0;
+    while (pos < r.n && r.at(pos) != '}') {
+        Span k; ck_string(r, pos, k); pos++;
+        ck_skip_value(r, pos);
+        if (ck_dict_find(r, tr, k.off, k.len).len == 0) pending++;
+        if (pos < r.n && r.at(pos) == ',') pos++;
+    }
+    if (pending == 0 || pending > max_fanout) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_STATUS) = CK_UNSUPPORTED; return; }
+    u32 extra = (cfgp->publish_topic_id >= 0 && pending > 1) ? 1u : 0u;   // list[Call]: the input envelope is the return value
+    counts[i] = pending + extra;
+    COL(CK_COL_ACTION) = pending == 1 ? CK_ACT_CALL : CK_ACT_FANOUT;
+    COL(CK_COL_NOUT) = pending + ((cfgp->publish_topic_id >= 0) ? 1u : 0u);
+#undef COL
+}
+
+// pass 2: descriptors.  slot_base = exclusive scan of counts (payload slots), one publish per payload
+// except a single Call whose payload is published twice (target + publish_topic): pubs are sized 2/slot.
+__global__ void __launch_bounds__(128)
+ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
+                      const ck_agent_cfg* __restrict__ cfgp, const u8* __restrict__ lit, const long long* __restrict__ slot_base,
+                      unsigned long long unix_ms, unsigned long long seed, u8* __restrict__ aux /* 32 B per payload slot */,
+                      ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#define COL(k) cols[(size_t)(k) * stride + i]
+    u32 action = COL(CK_COL_ACTION);
+    if (COL(CK_COL_STATUS) != CK_OK || (action != CK_ACT_CALL && action != CK_ACT_FANOUT)) return;
+    const ck_agent_cfg& cfg = *cfgp;
+    long long a = off[i];
+    Rd r; r.init(in + a, (u32)(off[i + 1] - a));
+    u32 slot = (u32)slot_base[i];
+    u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF);
+    u32 frames_off = COL(CK_COL_FRAMES_OFF), frames_len = COL(CK_COL_FRAMES_LEN), nframes = COL(CK_COL_NFRAMES);
+    u32 fov_off = COL(CK_COL_FOV_OFF), fov_len = COL(CK_COL_FOV_LEN), sov_off = COL(CK_COL_SOV_OFF), sov_len = COL(CK_COL_SOV_LEN);
+    bool ov = r.at(fov_off) != 'n';
+    u32 list_end = frames_off + frames_len - 1;            // position of the closing ']'
+    ck_pub none; none.payload = 0xffffffffu; none.topic_id = -1; none.topic_off = none.topic_len = 0; none.record = i;
+    none.has_key = 0; none.partition = -1; none.pad = 0;
+    u32 pos = tc + 1, j = 0;
+    bool bad = false;
+    while (pos < r.n && r.at(pos) != '}') {
+        Span k; ck_string(r, pos, k); pos++;
+        u32 v = pos;
+        ck_skip_value(r, pos);
+        if (ck_dict_find(r, tr, k.off, k.len).len == 0) {
+            // tool_name of this ToolCallPart -> registry
+            u32 p2 = v + 13; Span tn; ck_string(r, p2, tn);
+            u32 tool = 0xffffffffu;
+            for (u32 t = 0; t < cfg.ntools; t++) {
+                if (cfg.tool_name_len[t] != tn.len) continue;
+                bool eq = true;
+                for (u32 b = 0; b < tn.len; b++) if (lit[cfg.tool_name_off[t] + b] != r.at(tn.off + b)) { eq = false; break; }
+                if (eq) { tool = t; break; }
+            }
+            u32 s = slot + j;
+            ck_out_desc* d = descs + s;
+            SegWriter w; w.init(d);
+            if (tool == 0xffffffffu) { bad = true; w.finish(i); pay_len[s] = 0; pubs[2 * s] = none; pubs[2 * s + 1] = none; j++; }
+            else {
+                ck_uuid7_hex(unix_ms, seed, (unsigned long long)s, aux + (size_t)s * 32);
+                u32 cur = 0;
+                if (ov) { w.add(CK_SRC_INPUT, 0, sov_off); w.add(CK_SRC_INPUT, fov_off, fov_len); cur = sov_off + sov_len; }
+                w.add(CK_SRC_INPUT, cur, list_end - cur);
+                if (nframes > 0) w.add(CK_SRC_LIT, cfg.lit_comma[0], cfg.lit_comma[1]);
+                w.add(CK_SRC_LIT, cfg.tool_lit_off[tool], cfg.tool_lit_len[tool]);
+                w.add(CK_SRC_INPUT, k.off, k.len);                       // tool_call_id (raw JSON string content)
+                w.add(CK_SRC_LIT, cfg.lit_mid[0], cfg.lit_mid[1]);
+                w.add(CK_SRC_AUX, s * 32, 32);
+                w.add(CK_SRC_LIT, cfg.lit_tail[0], cfg.lit_tail[1]);
+                w.add(CK_SRC_INPUT, list_end, r.n - list_end);
+                w.finish(i);
+                pay_len[s] = w.total;
+                ck_pub p = none; p.payload = s; p.topic_id = (int32_t)cfg.tool_topic_id[tool]; p.has_key = 1;
+                pubs[2 * s] = p; pubs[2 * s + 1] = none;
+                if (action == CK_ACT_CALL && cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = s; q.topic_id = cfg.publish_topic_id; pubs[2 * s + 1] = q; }
+                j++;
+            }
+        }
+        if (pos < r.n && r.at(pos) == ',') pos++;
+    }
+    if (action == CK_ACT_FANOUT && cfg.publish_topic_id >= 0) {
+        // handler return value of the list[Call] branch: the original envelope (nodes/base.py:88)
+        u32 s = slot + j;
+        SegWriter w; w.init(descs + s);
+        w.add(CK_SRC_INPUT, 0, r.n); w.finish(i);
+        pay_len[s] = r.n;
+        ck_pub q = none; q.payload = s; q.topic_id = cfg.publish_topic_id; pubs[2 * s] = q; pubs[2 * s + 1] = none;
+    }
+    if (bad) { COL(CK_COL_STATUS) = CK_UNSUPPORTED; }
+#undef COL
+}
+
+// generic span gather (used to pack cross-partition payloads for the NCCL all-to-all): one warp per span
+__global__ void __launch_bounds__(256)
+ck_gather_spans_kernel(const u8* __restrict__ src, const long long* __restrict__ src_off, const long long* __restrict__ src_len,
+                       u32 n, u8* __restrict__ dst, const long long* __restrict__ dst_off);
+
+// ------------------------------------------------------------------------------------------------
 // exclusive scan u32 -> int64 (three small kernels; lengths are tiny next to the payload bytes)
 // ------------------------------------------------------------------------------------------------
 #define CK_SCAN_BLOCK 256
@@ -360,6 +510,16 @@ __device__ __forceinline__ void ck_warp_copy(u8* __restrict__ dst, const u8* __r
     u32 done = nw << 2;
     u32 tail = len - done;
     if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+__global__ void __launch_bounds__(256)
+ck_gather_spans_kernel(const u8* __restrict__ src, const long long* __restrict__ src_off, const long long* __restrict__ src_len,
+                       u32 n, u8* __restrict__ dst, const long long* __restrict__ dst_off) {
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    long long len = src_len[warp];
+    if (len <= 0) return;
+    ck_warp_copy(dst + dst_off[warp], src + src_off[warp], (u32)len, lane);
 }
 
 __global__ void __launch_bounds__(256)

@@ -39,6 +39,7 @@ typedef struct {           /* one publish; mirrors struct ck_pub in csrc/ck_kern
 
 /* lifecycle ------------------------------------------------------------------------------------ */
 int  ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_bytes, uint32_t max_records,
+               uint32_t max_payloads /* >= max_records; fan-out needs records * (fanout + 1) */,
                uint64_t max_aux_bytes, ck_handle** out);
 void ck_destroy(ck_handle* h);
 const char* ck_last_error(ck_handle* h);          /* h may be NULL: error of the last failed ck_create */
@@ -81,7 +82,12 @@ int  ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const uint8_t* ag
                        const uint8_t* callback_topic, uint32_t callback_len,
                        const uint8_t* tool_names, const uint32_t* tool_name_off,
                        const uint8_t* tool_topics, const uint32_t* tool_topic_off, uint32_t ntools);
+int  ck_set_agent_tool_topic_ids(ck_handle* h, const uint32_t* ids /* 0xffffffff = unregistered */, uint32_t ntools);
 int  ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout);
+/* copy n spans src[src_off[i] .. +src_len[i]) -> dst[dst_off[i] ..) on the handle's stream (device pointers);
+ * used to pack cross-partition payloads before the NCCL all-to-all */
+int  ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64_t* dev_src_off, const int64_t* dev_src_len,
+                     uint32_t n, uint8_t* dev_dst, const int64_t* dev_dst_off);
 
 /* results ---------------------------------------------------------------------------------------- */
 int  ck_sync(ck_handle* h);
@@ -94,7 +100,8 @@ int  ck_fetch_topic_hist(ck_handle* h, uint32_t* host_hist, uint32_t n);
 /* introspection for benchmarks / tests ------------------------------------------------------------ */
 void* ck_stream(ck_handle* h);                     /* cudaStream_t of the handle */
 int  ck_device_buffers(ck_handle* h, void** in, void** in_off, void** out, void** out_off, void** cols);
-int  ck_profile(ck_handle* h, int enable);         /* record CUDA events around every kernel */
+int  ck_device_buffers2(ck_handle* h, void** pubs, void** pay_len, void** descs);
+int  ck_profile(ck_handle* h, int enable);         /* record (asynchronous) CUDA events around every kernel */
 int  ck_profile_read(ck_handle* h, float* ms /* CK_NUM_KERNELS */, uint32_t* launches /* CK_NUM_KERNELS */, int reset);
 
 enum { CK_K_WALK = 0, CK_K_PLAN, CK_K_SCAN, CK_K_EMIT, CK_K_ROUTE, CK_K_FANOUT, CK_NUM_KERNELS };

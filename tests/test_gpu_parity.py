@@ -181,3 +181,44 @@ def test_device_walker_equals_host_build_on_fuzz(engine):
         assert (cols[0, i] == 0) == ok, (i, r[:200])
         if ok:
             assert (cols[:ncmp, i] == hc[:ncmp]).all(), i
+
+
+def test_fanout_matches_oracle(engine):
+    """Agent fan-out (config 3): every pending tool call -> one Call envelope, frame ids injected into
+    the oracle from the device's own uuid7 generator (seed, slot index)."""
+    from oracle import port
+    from calfkit import _ids, synth
+    from calfkit.engine.batch import device_uuid7_hex
+    from calfkit.engine import BatchEngine
+    F = 16
+    recs = synth.fanout_events(40, seed=9, fanout=F) + synth.fanout_events(5, seed=10, fanout=1) + \
+        [as_bytes(golden("actions.json")[0]["input"])]
+    registry = {f"tool_{j:02d}": f"tool.tool_{j:02d}.input" for j in range(64)}
+    e = BatchEngine(0, max_records=256, max_in_bytes=8 << 20, max_out_bytes=256 << 20, max_payloads=256 * (F + 1))
+    try:
+        e.register_topics(list(registry.values()) + ["planner.input", "planner.output"], num_partitions=8)
+        e.set_agent_node("planner", "planner.input", "planner.output", registry)
+        b = synth.pack(recs)
+        ms, seed = 1767225600000, 1234
+        e.submit(b.data, b.offsets)
+        e.fanout_plan(ms, seed, max_fanout=64)
+        out = e.fetch()
+        assert (out.cols[0] == 0).all()
+        pubs = list(out.publishes())
+        slot = 0
+        k = 0
+        for i, rec in enumerate(recs):
+            npend = len(port.decode(rec).context.state.tool_calls)
+            ids = iter([device_uuid7_hex(ms, seed, slot + j) for j in range(npend)])
+            _ids.set_id_source(lambda: next(ids))
+            try:
+                want = port.agent_fanout("planner", "planner.input", "planner.output", registry, rec)
+            finally:
+                _ids.set_id_source(None)
+            got = [(p.topic, p.key, p.payload) for p in pubs[k:k + len(want)]]
+            assert got == [(t, kk, pl) for (t, kk, c, pl) in want], i
+            k += len(want)
+            slot += npend + (1 if npend > 1 else 0)
+        assert k == len(pubs)
+    finally:
+        e.close()
