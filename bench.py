@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py — agent-events/sec of the calfkit hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the tool-node hot path (decode -> ToolNodeDef.run -> _publish_action ->
+encode -> route) over one batch of `--events` synthetic 1 KB-class agent events per GPU
+(BASELINE.json configs[1]: "1M synthetic 1 KB agent-event JSON, single @agent_tool node").
+`value`     : whole-job events/s with the batch resident in HBM when the timed region starts.
+`e2e`       : the same through the public BatchEngine API with pinned HOST buffers — H2D of the
+              batch and D2H of every payload + the publish table inside the timed region.
+`roofline`  : dominant kernel, algorithmic bytes / its CUDA-event duration (events recorded on the
+              engine's own stream inside the timed region) vs the measured HBM peak.
+`cpu_baseline`: the oracle port (reference algorithm on pydantic-core) on all host cores, bounded sample.
+N > 1: records shard by Kafka partition (murmur2(correlation_id) % 8 -> GPU), weak scaling; a
+fraction (--cross, default 1/8) of each rank's records arrive on the "wrong" partition (the
+reference's unkeyed first publish, client/base.py:147) and their keyed outputs are forwarded to the
+owning GPU with one variable-size NCCL all-to-all per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "calfkit-sdk_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent_events_per_sec"
+UNIT = "events/s"
+NUM_PARTITIONS = 8
+TOOL_FMT = "It's sunny in {location}"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(chunk):
+    from oracle import port
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tools_def
+    node = port.ToolNode.of(tools_def.get_weather)
+    nbytes = 0
+    for rec in chunk:
+        for (_t, _k, _c, payload) in port.tool_node_event(node, rec):
+            nbytes += len(payload)
+    return len(chunk), nbytes
+
+
+def cpu_arm(records, cores: int, start: str = "fork"):
+    """events/s of the oracle port over `records`, split over `cores` processes."""
+    import multiprocessing as mp
+    chunks = [records[i::cores] for i in range(cores)]
+    ctx = mp.get_context(start)
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [c[:8] for c in chunks])          # import + warm-up outside the timing
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, chunks)
+        dt = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    return n / dt, dt, n
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    from calfkit import synth
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 400, 2000)
+    recs = synth.tool_events(per_step, seed=77)
+    for _ in range(args.warmup):
+        cpu_arm(recs[: max(cores * 16, 64)], cores)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        _v, dt, n = cpu_arm(recs, cores)
+        t_total += dt
+        n_total += n
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "tool_event_1k: 1152+-16 B tool-stage Envelope JSON, one @agent_tool node (get_weather)",
+                   "events_per_step": per_step, "note": "reference's own CPU path restated on pydantic-core (oracle/port.py); "
+                   "broker I/O excluded on both arms (FastStream/aiokafka are not installable offline)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} events/step x {args.steps} steps over {cores} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+class CudaArray:
+    """wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__"""
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": tuple(shape), "typestr": typestr, "version": 3}
+
+
+def np_murmur2_32(keys):
+    """vectorised Kafka murmur2 over fixed-width keys: uint8 [n, L] with L % 4 == 0"""
+    import numpy as np
+    n, L = keys.shape
+    w = keys.reshape(n, L // 4, 4).astype(np.uint32)
+    k = w[:, :, 0] | (w[:, :, 1] << 8) | (w[:, :, 2] << 16) | (w[:, :, 3] << 24)
+    m = np.uint32(0x5BD1E995)
+    h = np.full(n, np.uint32(0x9747B28C) ^ np.uint32(L), dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        for i in range(L // 4):
+            kk = k[:, i] * m
+            kk ^= kk >> np.uint32(24)
+            kk *= m
+            h *= m
+            h ^= kk
+        h ^= h >> np.uint32(13)
+        h *= m
+        h ^= h >> np.uint32(15)
+    return h
+
+
+def place_on_partitions(batch, corr_off, rank: int, world: int, cross: float, seed: int):
+    """Rewrites each record's 32-hex correlation id in place so that murmur2(id) % 8 % world == rank
+    for (1 - cross) of the records and != rank for the rest (arrived on the 'wrong' partition)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n = batch.n
+    data = batch.data.copy()
+    want_home = np.full(n, rank, dtype=np.int64)
+    if world > 1:
+        away = rng.random(n) < cross
+        want_home[away] = (rank + 1 + rng.integers(0, world - 1, size=int(away.sum()))) % world
+    pos = batch.offsets[:-1] + corr_off.astype(np.int64)
+    todo = np.arange(n)
+    hexd = np.frombuffer(b"0123456789abcdef", dtype=np.uint8)
+    while todo.size:
+        cand = hexd[rng.integers(0, 16, size=(todo.size, 32))]
+        home = (np_murmur2_32(cand) & np.uint32(0x7FFFFFFF)) % np.uint32(NUM_PARTITIONS) % np.uint32(world)
+        ok = home == want_home[todo]
+        idx = todo[ok]
+        if idx.size:
+            cols = pos[idx][:, None] + np.arange(32)[None, :]
+            data[cols] = cand[ok]
+        todo = todo[~ok]
+    batch.data = data
+    return batch
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--events", type=int, default=1_000_000, help="events per GPU per step (config 2: 1M)")
+    ap.add_argument("--cross", type=float, default=0.125, help="fraction of records on a foreign partition (N > 1)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="events for the cpu_baseline leg (0 = auto)")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from calfkit import synth
+    from calfkit.engine import BatchEngine, ToolTemplate
+    from calfkit.engine._lib import COL, PUB_DTYPE
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.events
+    recs = synth.tool_events(n, seed=1000 + rank)
+    batch = synth.pack(recs)
+    del recs
+    in_bytes = int(batch.data.nbytes)
+    eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096)
+    topics = ["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"]
+    eng.register_topics(topics, num_partitions=NUM_PARTITIONS)
+    eng.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))
+    if world > 1:
+        eng.submit(batch.data, batch.offsets)
+        corr_off = eng.columns()[COL["CORR_OFF"]]
+        batch = place_on_partitions(batch, corr_off, rank, world, args.cross, seed=2000 + rank)
+
+    h_in = torch.from_numpy(batch.data.copy()).pin_memory()
+    h_off = torch.from_numpy(batch.offsets.copy()).pin_memory()
+    d_in = h_in.to(dev)
+    d_off = h_off.to(dev)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    bufs = eng.device_buffers()
+    import ctypes as C
+    p_pubs, p_len, p_desc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    eng.lib.ck_device_buffers2(eng.h, C.byref(p_pubs), C.byref(p_len), C.byref(p_desc))
+    t_pubs = torch.as_tensor(CudaArray(p_pubs.value, (2 * n, 8), "<i4"), device=dev)
+    t_out_off = torch.as_tensor(CudaArray(bufs["out_off"], (n + 1,), "<i8"), device=dev)
+    out_cap = eng.max_out
+    t_out = torch.as_tensor(CudaArray(bufs["out"], (out_cap,), "|u1"), device=dev)
+    send_buf = torch.empty(int(out_cap * min(1.0, args.cross * 2 + 0.05)) + (1 << 20), dtype=torch.uint8, device=dev) if world > 1 else None
+    recv_buf = torch.empty_like(send_buf) if world > 1 else None
+    launches = [0]
+
+    def exchange():
+        """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
+        keyed = (t_pubs[:, 5] == 1) & (t_pubs[:, 0] != -1)
+        dest = (t_pubs[:, 6] % world).to(torch.int64)
+        sel = torch.nonzero(keyed & (dest != rank)).squeeze(1)
+        d_sel = dest[sel]
+        order = torch.argsort(d_sel, stable=True)
+        sel, d_sel = sel[order], d_sel[order]
+        pay = t_pubs[sel, 0].to(torch.int64)
+        src_off = t_out_off[pay]
+        lens = t_out_off[pay + 1] - src_off
+        dst_off = torch.cumsum(lens, 0) - lens
+        counts = torch.bincount(d_sel, minlength=world)
+        bytes_per = torch.zeros(world, dtype=torch.int64, device=dev).scatter_add_(0, d_sel, lens)
+        eng._check(eng.lib.ck_gather_spans(eng.h, t_out.data_ptr(), src_off.data_ptr(), lens.data_ptr(), int(sel.numel()),
+                                           send_buf.data_ptr(), dst_off.data_ptr()))
+        launches[0] += 1
+        meta_out = torch.stack([counts, bytes_per], 1).contiguous()
+        meta_in = torch.empty_like(meta_out)
+        dist.all_to_all_single(meta_in, meta_out)
+        mo, mi = meta_out.tolist(), meta_in.tolist()
+        sb, rb = [x[1] for x in mo], [x[1] for x in mi]
+        sc, rc = [x[0] for x in mo], [x[0] for x in mi]
+        dist.all_to_all_single(recv_buf[: sum(rb)], send_buf[: sum(sb)], rb, sb)
+        rlens = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(rlens, lens, rc, sc)
+        return sum(rc), sum(rb)
+
+    def step_device():
+        eng.submit_device(d_in, d_off, n)
+        eng.tool_plan()
+        launches[0] += 7            # walk, plan, 3 x scan, emit, route
+        if world > 1:
+            with torch.cuda.stream(stream):
+                return exchange()
+        return 0, 0
+
+    h_out = torch.empty(out_cap, dtype=torch.uint8).pin_memory()
+    h_out_np = h_out.numpy()
+    d2h_bytes = [0]
+
+    def step_e2e():
+        eng.submit(h_in.numpy(), h_off.numpy())            # H2D of the batch + decode
+        eng.tool_plan()
+        extra = 0
+        if world > 1:
+            with torch.cuda.stream(stream):
+                _rc, rbytes = exchange()
+                extra = rbytes
+                if rbytes:
+                    h_out[out_cap - rbytes:].copy_(recv_buf[:rbytes], non_blocking=True)
+        out, off, pubs = eng._fetch(out_buf=h_out_np)      # D2H of payload bytes, offsets, publish table (waits)
+        d2h_bytes[0] = int(out.nbytes + off.nbytes + pubs.nbytes + extra)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    eng.sync()
+    eng.profile(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches[0] = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    prof = eng.profile_read()
+    eng.profile(False)
+    gpu_launches = launches[0]
+    out_bytes, npay, npub = eng.out_size()
+    cols = eng.columns()
+    ok_frac = float((cols[COL["STATUS"]] == 0).mean())
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step / 1e3)
+
+    # ---- end to end (host buffers) -----------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 5))
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            step_e2e()
+        e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0].item()) / e2e_steps
+    e2e_value = world * n / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ncols_walk = COL["CALL_VAL_OFF"]
+    algo = {   # algorithmic bytes per launch
+        "walk": in_bytes + 8 * (n + 1) + 4 * ncols_walk * n,
+        "plan": 4 * 24 * n + 160 * n + 2 * 32 * n + 4 * n,
+        "scan": 3 * 4 * n + 8 * n,
+        "emit": 2 * out_bytes + 160 * n + 8 * n,
+        "route": 2 * 2 * 32 * n,
+    }
+    kern = {}
+    for k, (ms, cnt) in prof.items():
+        if cnt and k in algo:
+            kern[k] = {"ms_per_launch": ms / cnt, "launches": cnt, "algo_bytes": algo[k],
+                       "gbs": algo[k] / (ms / cnt) / 1e6 if k != "scan" else None}
+    kern_step_ms = sum(v[0] for v in prof.values()) / args.steps
+    dom = max((k for k in kern if k != "scan"), key=lambda k: kern[k]["ms_per_launch"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if dom in tj:
+            traffic = tj[dom]["dram_bytes_per_record"] * n
+    achieved = kern[dom]["gbs"]
+    roofline = {"kernel": f"ck_{dom}_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": kern[dom]["ms_per_launch"] / ms_step,
+                "pipeline": {"algo_bytes_per_event": (in_bytes + out_bytes) / n,
+                             "achieved": (in_bytes + out_bytes) / ms_step / 1e6, "frac": (in_bytes + out_bytes) / ms_step / 1e6 / peak},
+                "kernels": kern, "sum_kernel_ms_per_step": kern_step_ms}
+
+    # ---- CPU baseline: the oracle port on a bounded sample, all host cores ----------------------------
+    cores = os.cpu_count() or 1
+    sample_n = args.cpu_sample or max(cores * 600, 4000)
+    sample = [batch.record(i) for i in range(min(sample_n, n))]
+    cpu_value, cpu_dt, cpu_n = cpu_arm(sample, cores, start="spawn")   # CUDA is initialised in this process: no fork
+    # parity spot check against the oracle on the same bytes (byte-exact), outside all timed regions
+    from oracle import port
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tools_def
+    small = synth.pack(sample[:256])
+    chk = eng.run_tool_batch(small.data, small.offsets)
+    node = port.ToolNode.of(tools_def.get_weather)
+    pubs = [(p.topic, p.key, p.payload) for p in chk.publishes()]
+    want = [(tp, k, pl) for r in sample[:256] for (tp, k, _c, pl) in port.tool_node_event(node, r)]
+    parity_ok = pubs == want
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": "tool_event_1k: tool-stage Envelope JSON (1152+-16 B), single @agent_tool node get_weather "
+                               "(BASELINE.json configs[1])",
+                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "out_bytes_mean": out_bytes / max(npay, 1),
+                   "publishes_per_event": 2, "partitions": NUM_PARTITIONS, "cross_partition_fraction": args.cross if world > 1 else 0.0,
+                   "sharding": "records by Kafka partition -> GPU" if world > 1 else "single GPU",
+                   "l2": "inputs (%.2f GB) and outputs larger than the 126 MB L2: every step streams from HBM" % (in_bytes / 1e9),
+                   "tool": "device template " + repr(TOOL_FMT), "accepted_fraction": ok_frac, "parity_spot_check_256": parity_ok},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h_bytes[0],
+                "ms_per_step": e2e_ms, "api": "BatchEngine.submit(host) + tool_plan + fetch(host)", "steps": e2e_steps},
+        "gpu_launches": gpu_launches,
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes (oracle/port.py)"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
