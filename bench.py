@@ -127,7 +127,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def summary(self):
         s = sorted(self.samples)
@@ -405,7 +405,7 @@ def main() -> None:
 
     # ---- CPU baseline: the oracle port on a bounded sample, all host cores ----------------------------
     cores = os.cpu_count() or 1
-    sample_n = args.cpu_sample or max(cores * 600, 4000)
+    sample_n = args.cpu_sample or max(cores * 8000, 20000)       # ~10-20 s of CPU work on all cores
     sample = [batch.record(i) for i in range(min(sample_n, n))]
     cpu_value, cpu_dt, cpu_n = cpu_arm(sample, cores, start="spawn")   # CUDA is initialised in this process: no fork
     # parity spot check against the oracle on the same bytes (byte-exact), outside all timed regions

@@ -838,8 +838,11 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M("}},\"internal_workflow_state\":{\"call_stack\":{\"_internal_list\":[")) FAIL;
     a = pos - 1;
     u32 nframes = 0;
-    o.set(CK_COL_NARGS, CK_NARGS_NULL);
-    if (!PEEK(']')) {
+    if (PEEK(']')) {
+        // empty stack: the current-frame columns are defined (zero) even though no frame exists
+        for (u32 c = CK_COL_TOP_OFF; c <= CK_COL_FOV_LEN; c++) o.set(c, 0);
+        o.set(CK_COL_NARGS, CK_NARGS_NULL);
+    } else {
         for (;;) {
             u32 f0 = pos;
             Span tgt, cb;

@@ -180,7 +180,7 @@ def test_device_walker_equals_host_build_on_fuzz(engine):
         ok, hc = walk(r)
         assert (cols[0, i] == 0) == ok, (i, r[:200])
         if ok:
-            assert (cols[:ncmp, i] == hc[:ncmp]).all(), i
+            assert (cols[2:ncmp, i] == hc[2:ncmp]).all(), i   # columns 0/1 (status/action) are owned by the kernels
 
 
 def test_fanout_matches_oracle(engine):
