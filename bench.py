@@ -252,33 +252,17 @@ def main() -> None:
     recv_buf = torch.empty_like(send_buf) if world > 1 else None
     launches = [0]
 
+    from calfkit.engine.exchange import exchange as run_exchange, plan_exchange
+
+    def gather(plan, buf):
+        eng._check(eng.lib.ck_gather_spans(eng.h, t_out.data_ptr(), plan.src_off.data_ptr(), plan.lens.data_ptr(),
+                                           int(plan.sel.numel()), buf.data_ptr(), plan.dst_off.data_ptr()))
+        launches[0] += 1
+
     def exchange():
         """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
-        keyed = (t_pubs[:, 5] == 1) & (t_pubs[:, 0] != -1)
-        dest = (t_pubs[:, 6] % world).to(torch.int64)
-        sel = torch.nonzero(keyed & (dest != rank)).squeeze(1)
-        d_sel = dest[sel]
-        order = torch.argsort(d_sel, stable=True)
-        sel, d_sel = sel[order], d_sel[order]
-        pay = t_pubs[sel, 0].to(torch.int64)
-        src_off = t_out_off[pay]
-        lens = t_out_off[pay + 1] - src_off
-        dst_off = torch.cumsum(lens, 0) - lens
-        counts = torch.bincount(d_sel, minlength=world)
-        bytes_per = torch.zeros(world, dtype=torch.int64, device=dev).scatter_add_(0, d_sel, lens)
-        eng._check(eng.lib.ck_gather_spans(eng.h, t_out.data_ptr(), src_off.data_ptr(), lens.data_ptr(), int(sel.numel()),
-                                           send_buf.data_ptr(), dst_off.data_ptr()))
-        launches[0] += 1
-        meta_out = torch.stack([counts, bytes_per], 1).contiguous()
-        meta_in = torch.empty_like(meta_out)
-        dist.all_to_all_single(meta_in, meta_out)
-        mo, mi = meta_out.tolist(), meta_in.tolist()
-        sb, rb = [x[1] for x in mo], [x[1] for x in mi]
-        sc, rc = [x[0] for x in mo], [x[0] for x in mi]
-        dist.all_to_all_single(recv_buf[: sum(rb)], send_buf[: sum(sb)], rb, sb)
-        rlens = torch.empty(sum(rc), dtype=torch.int64, device=dev)
-        dist.all_to_all_single(rlens, lens, rc, sc)
-        return sum(rc), sum(rb)
+        nrecv, rbytes, _rlens = run_exchange(plan_exchange(t_pubs, t_out_off, rank, world), gather, send_buf, recv_buf)
+        return nrecv, rbytes
 
     def step_device():
         eng.submit_device(d_in, d_off, n)
@@ -363,10 +347,21 @@ def main() -> None:
     e2e_ms = float(t[0].item()) / e2e_steps
     e2e_value = world * n / (e2e_ms / 1e3)
 
+    def shutdown():
+        # orderly teardown, then leave without running interpreter finalisers (pinned tensors wrapping
+        # foreign device memory must not outlive the CUDA context)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        try:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                dist.destroy_process_group()
+        finally:
+            os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        shutdown()
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -439,8 +434,7 @@ def main() -> None:
                          "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes (oracle/port.py)"},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -225,6 +225,9 @@ class BatchEngine:
     def tool_plan(self, aux: np.ndarray | None = None, aux_off: np.ndarray | None = None) -> None:
         self._check(self.lib.ck_tool_plan(self.h, ptr(aux), ptr(aux_off)))
 
+    def return_plan(self) -> None:
+        self._check(self.lib.ck_return_plan(self.h))
+
     def tool_plan_device(self, dev_aux, dev_aux_off) -> None:
         self._check(self.lib.ck_tool_plan_device(self.h, ptr(dev_aux), ptr(dev_aux_off)))
 

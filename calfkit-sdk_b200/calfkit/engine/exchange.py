@@ -1,0 +1,63 @@
+"""Cross-partition exchange: records shard by Kafka partition across the GPUs of a
+box; the only data-path collective is ONE variable-size all-to-all per batch that forwards the keyed
+payloads whose partition (murmur2(correlation_id) % num_partitions, computed by ck_route_kernel) is
+owned by another rank.  Reference analogue: the record would simply be produced to a topic-partition
+that a different worker process consumes (calfkit/nodes/base.py:82-87 key=correlation_id).
+
+The planning below is plain tensor bookkeeping (device-agnostic torch ops: it runs on CUDA tensors in
+production and on CPU tensors under the gloo tests); the byte movement is ck_gather_spans (CUDA) and
+torch.distributed.all_to_all_single (NCCL over NVLink)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ExchangePlan:
+    sel: torch.Tensor        # indices into the publish table, ordered by destination rank
+    src_off: torch.Tensor    # int64 payload start in the output buffer
+    lens: torch.Tensor       # int64 payload length
+    dst_off: torch.Tensor    # int64 offset in the send buffer
+    counts: torch.Tensor     # int64 [world] payloads per destination
+    nbytes: torch.Tensor     # int64 [world] bytes per destination
+
+
+def plan_exchange(pubs: torch.Tensor, out_off: torch.Tensor, rank: int, world: int) -> ExchangePlan:
+    """pubs: int32 [npubs, 8] view of the ck_publish table (payload, topic_id, topic_off, topic_len,
+    record, has_key, partition, pad); out_off: int64 [npayloads + 1]."""
+    keyed = (pubs[:, 5] == 1) & (pubs[:, 0] != -1)
+    dest = (pubs[:, 6] % world).to(torch.int64)
+    sel = torch.nonzero(keyed & (dest != rank)).squeeze(1)
+    d_sel = dest[sel]
+    order = torch.argsort(d_sel, stable=True)
+    sel, d_sel = sel[order], d_sel[order]
+    pay = pubs[sel, 0].to(torch.int64)
+    src_off = out_off[pay]
+    lens = out_off[pay + 1] - src_off
+    dst_off = torch.cumsum(lens, 0) - lens
+    counts = torch.bincount(d_sel, minlength=world)
+    nbytes = torch.zeros(world, dtype=torch.int64, device=pubs.device).scatter_add_(0, d_sel, lens)
+    return ExchangePlan(sel, src_off, lens, dst_off, counts, nbytes)
+
+
+def exchange(plan: ExchangePlan, gather: Callable[[ExchangePlan, torch.Tensor], None], send_buf: torch.Tensor,
+             recv_buf: torch.Tensor) -> tuple[int, int, torch.Tensor]:
+    """gather(plan, send_buf) packs the selected payloads; returns (n received payloads, received bytes,
+    their lengths)."""
+    gather(plan, send_buf)
+    meta_out = torch.stack([plan.counts, plan.nbytes], 1).contiguous()
+    meta_in = torch.empty_like(meta_out)
+    dist.all_to_all_single(meta_in, meta_out)
+    mo, mi = meta_out.tolist(), meta_in.tolist()
+    sc, sb = [x[0] for x in mo], [x[1] for x in mo]
+    rc, rb = [x[0] for x in mi], [x[1] for x in mi]
+    if sum(rb) > recv_buf.numel() or sum(sb) > send_buf.numel():
+        raise RuntimeError("exchange buffers too small")
+    dist.all_to_all_single(recv_buf[: sum(rb)], send_buf[: sum(sb)], rb, sb)
+    rlens = torch.empty(sum(rc), dtype=torch.int64, device=plan.lens.device)
+    dist.all_to_all_single(rlens, plan.lens.contiguous(), rc, sc)
+    return sum(rc), sum(rb), rlens

@@ -201,7 +201,7 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaMemcpy(h->d_lit, pool.data(), pool.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->d_tool_cfg, &c, sizeof c, cudaMemcpyHostToDevice));
-    h->h_tool_cfg = c; h->tool_set = true; h->agent_set = false;
+    h->h_tool_cfg = c; h->tool_set = true;
     return 0;
 }
 
@@ -306,6 +306,29 @@ extern "C" int ck_tool_plan(ck_handle* h, const uint8_t* host_aux, const int64_t
     return tool_plan_common(h, nullptr, nullptr);
 }
 
+// ReturnCall of the state as it is on the wire (Agent final output): pop the frame, publish to the
+// callback topic and to publish_topic (nodes/base.py:105-118, worker/worker.py:52-53)
+extern "C" int ck_return_plan(ck_handle* h) {
+    cudaSetDevice(h->device);
+    if (!h->tool_set) return fail(h, "ck_return_plan: call ck_set_tool_node (publish topic) first");
+    {
+        KTimer t(h, CK_K_PLAN);
+        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
+            h->d_tool_cfg, h->d_lit, nullptr, 2, h->d_descs, h->d_pay_len, h->d_pubs);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (scan_emit(h, h->n, nullptr)) return 1;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        u32 npubs = 2 * h->n;
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->d_cols, h->n, h->d_pubs, npubs,
+            h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
+        CUDA_TRY(h, cudaGetLastError());
+        h->n_pubs = npubs;
+    }
+    return 0;
+}
+
 extern "C" int ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const int64_t* dev_aux_off) {
     cudaSetDevice(h->device);
     return tool_plan_common(h, dev_aux, (const long long*)dev_aux_off);
@@ -349,7 +372,7 @@ extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const u
     c.tool_topic_id = h->d_agent_tables + 4 * ntools;
     CUDA_TRY(h, cudaMemcpy(h->d_lit, pool.data(), pool.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->d_agent_cfg, &c, sizeof c, cudaMemcpyHostToDevice));
-    h->h_agent_cfg = c; h->agent_set = true; h->tool_set = false;
+    h->h_agent_cfg = c; h->agent_set = true;
     return 0;
 }
 

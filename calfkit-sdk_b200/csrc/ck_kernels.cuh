@@ -154,6 +154,26 @@ ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off
     u32 nframes = COL(CK_COL_NFRAMES), nargs = COL(CK_COL_NARGS), kinds = COL(CK_COL_ARGKINDS);
     SegWriter w; w.init(d);
     Span call = {0, 0};
+    if (mode == 2) {
+        // plain ReturnCall(state) of a node whose run() left the state as it is on the wire
+        // (Agent final output after the host LLM step): overrides rule + unwind + two publishes
+        if (nframes == 0) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_NOUT) = 0; return; }
+        u32 cur2 = 0;
+        u32 fo = COL(CK_COL_FOV_OFF), fl = COL(CK_COL_FOV_LEN);
+        if (r.at(fo) != 'n') { u32 so = COL(CK_COL_SOV_OFF), sl = COL(CK_COL_SOV_LEN); w.add(CK_SRC_INPUT, 0, so); w.add(CK_SRC_INPUT, fo, fl); cur2 = so + sl; }
+        u32 to = COL(CK_COL_TOP_OFF), tl = COL(CK_COL_TOP_LEN);
+        u32 c0 = nframes > 1 ? to - 1 : to;
+        w.add(CK_SRC_INPUT, cur2, c0 - cur2);
+        w.add(CK_SRC_INPUT, to + tl, r.n - (to + tl));
+        w.finish(i);
+        pay_len[i] = w.total;
+        ck_pub p = none; p.payload = i; p.topic_off = COL(CK_COL_CB_OFF); p.topic_len = COL(CK_COL_CB_LEN); p.has_key = 1;
+        pubs[2 * i] = p;
+        u32 no = 1;
+        if (cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = i; q.topic_id = cfg.publish_topic_id; pubs[2 * i + 1] = q; no = 2; }
+        COL(CK_COL_ACTION) = CK_ACT_RETURN; COL(CK_COL_NOUT) = no;
+        return;
+    }
     if (nframes == 0 || nargs != 2) action = CK_ACT_RAISES;       // peek on empty stack / run() arity TypeError
     else if (!(kinds & 1u)) {
         u8 c0 = r.at(COL(CK_COL_ARG0_OFF));

@@ -71,7 +71,10 @@ int  ck_tool_args(ck_handle* h);
 /* tool node: run + publish plan + encode + route.  host_aux/host_aux_off: JSON return values per
  * record (offsets[n+1]) for host tools, NULL for a device template. */
 int  ck_tool_plan(ck_handle* h, const uint8_t* host_aux, const int64_t* host_aux_off);
-/* same, aux blob already in HBM */
+/* ReturnCall of the state as it is on the wire (e.g. an Agent's final output after the host LLM step):
+ * pop the current frame, publish to its callback topic and to the node's publish_topic. */
+int  ck_return_plan(ck_handle* h);
+/* same as ck_tool_plan, aux blob already in HBM */
 int  ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const int64_t* dev_aux_off);
 
 /* agent fan-out (calfkit/nodes/agent.py:177-211 + nodes/base.py:73-88): one Call envelope per

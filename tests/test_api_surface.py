@@ -1,0 +1,111 @@
+"""The drop-in surface of the hot path (SURVEY.md §8b "upward" face): names, signatures and the
+error behaviour the reference pins.  CPU only: nothing here launches a kernel."""
+import inspect
+
+import pytest
+
+
+def test_public_names():
+    import calfkit
+    for name in ["Client", "InvocationHandle", "NodeResult", "ToolContext", "Agent", "BaseNodeDef", "NodeDef", "ToolNodeDef",
+                 "agent_tool", "Worker"]:          # reference calfkit/__init__.py:10-30 (providers are out of scope)
+        assert hasattr(calfkit, name), name
+
+
+def test_worker_signature_and_guard():
+    from calfkit import Client, Worker
+    sig = inspect.signature(Worker.__init__)
+    assert list(sig.parameters)[:7] == ["self", "client", "nodes", "max_workers", "group_id", "extra_publish_kwargs",
+                                        "extra_subscribe_kwargs"]       # reference worker/worker.py:13-21
+    assert sig.parameters["max_workers"].default == 1 and sig.parameters["group_id"].default is None
+    client = Client.connect("localhost")
+    w = Worker(client, nodes=[])
+    w.register_handlers()
+    with pytest.raises(RuntimeError, match="already called"):                 # worker.py:34-35
+        w.register_handlers()
+    assert inspect.iscoroutinefunction(Worker.run)
+
+
+def test_agent_tool_naming_and_schema():
+    from calfkit import agent_tool
+
+    @agent_tool
+    def get_weather(location: str) -> str:
+        """Get the current weather at a location"""
+        return f"It's sunny in {location}"
+
+    assert get_weather.node_id == "tool_get_weather"                            # nodes/tool.py:30
+    assert get_weather.subscribe_topics == ["tool.get_weather.input"]           # nodes/tool.py:91
+    assert get_weather.publish_topic == "tool.get_weather.output"               # nodes/tool.py:92
+    td = get_weather.tool_schema
+    assert td.name == "get_weather" and td.description == "Get the current weather at a location"
+    assert td.parameters_json_schema["properties"]["location"]["type"] == "string"
+    assert td.parameters_json_schema["required"] == ["location"]
+    assert get_weather.name == get_weather.id == "tool_get_weather"
+    assert get_weather._return_topic == "tool_get_weather.private.return"       # nodes/base.py:174-176
+
+
+def test_client_connect_and_signatures():
+    from calfkit import Client
+    c = Client.connect()
+    assert c.reply_topic.startswith("calf-client-reply-") and len(c.reply_topic) == len("calf-client-reply-") + 32
+    assert c.broker is c._connection
+    c2 = Client.connect("k:9092", reply_topic="my-replies")
+    assert c2.reply_topic == "my-replies"
+    p = inspect.signature(Client.execute_node).parameters                         # client/client.py:154-218
+    assert list(p)[:3] == ["self", "user_prompt", "topic"]
+    for kw in ["tool_overrides", "output_type", "reply_topic", "correlation_id", "temp_instructions", "message_history",
+               "run_args", "deps", "timeout"]:
+        assert p[kw].kind is inspect.Parameter.KEYWORD_ONLY
+    assert "timeout" not in inspect.signature(Client.invoke_node).parameters
+
+
+def test_call_input_args_rule():
+    from calfkit.models import Call, State
+    assert Call("t", State()).input_args is None                                  # models/actions.py:66
+    assert Call("t", State(), "a", "b").input_args == ("a", "b")
+
+
+def test_first_envelope_is_unkeyed_and_canonical():
+    """client/base.py:140-147: one frame (target, callback=reply topic), unkeyed publish; the bytes are
+    a fixed point of the codec, which is what the device walker accepts."""
+    import asyncio
+    from calfkit import Client
+    from hostsim import walk
+
+    async def go():
+        c = Client.connect()
+        h = await c.invoke_node("What's the weather in Tokyo?", "weather_agent.input", deps={"k": 1})
+        rec = c.broker.queues["weather_agent.input"][0]
+        assert rec.key is None and rec.correlation_id == h.correlation_id
+        ok, cols = walk(rec.value)
+        assert ok, rec.value[int(cols[2]) - 30:int(cols[2]) + 30]
+        with pytest.raises(RuntimeError, match="Duplicate correlation_id"):
+            await c.invoke_node("x", "weather_agent.input", correlation_id=h.correlation_id)
+        await c.close()
+    asyncio.run(go())
+
+
+def test_tool_template_and_uuid7():
+    from calfkit.engine.batch import ToolTemplate, device_uuid7_hex
+    t = ToolTemplate.from_format('It\'s "sunny"\n in {location}!')
+    assert t.kinds == [0, 1, 0] and t.pieces == [b'"It\'s \\"sunny\\"\\n in ', b"location", b'!"']
+    u = device_uuid7_hex(1767225600000, 7, 3)
+    assert len(u) == 32 and u[12] == "7" and u[16] in "89ab" and int(u[:12], 16) == 1767225600000
+
+
+def test_murmur2_vectorised_matches_kafka_reference():
+    import numpy as np
+    sys_path_hack = __import__("sys").path
+    sys_path_hack.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    from bench import np_murmur2_32
+    from test_gpu_parity import _murmur2
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 256, size=(200, 32), dtype=np.uint8)
+    got = np_murmur2_32(keys)
+    assert [int(x) for x in got] == [_murmur2(bytes(k)) for k in keys]
+    # known answers of Kafka's Utils.murmur2 (kafka-python / aiokafka partitioner test vectors)
+    assert _murmur2(b"21") == 0xFFFFFFFF & -973932308
+    assert _murmur2(b"foobar") == 0xFFFFFFFF & -790332482
+    assert _murmur2(b"a-little-bit-long-string") == 0xFFFFFFFF & -985981536
+    assert _murmur2(b"") == 275646681

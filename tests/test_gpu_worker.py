@@ -1,0 +1,73 @@
+"""Config 1 (BASELINE.json configs[0]) end to end on the B200 worker: quickstart weather agent +
+get_weather tool, 100 events through Client -> Worker.run -> Agent/ToolNode batch plans -> reply."""
+import asyncio
+import importlib.util
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _skip_without_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_quickstart_100_events():
+    _skip_without_cuda()
+    spec = importlib.util.spec_from_file_location("quickstart", os.path.join(ROOT, "examples", "quickstart", "run_quickstart.py"))
+    qs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(qs)
+    outs = asyncio.run(qs.main(100))
+    cities = ["Tokyo", "Paris", "São Paulo", "Kraków", "北京"]
+    assert outs == [f"It's sunny in {cities[i % 5]}" for i in range(100)]
+
+
+def test_parallel_fanout_three_tools_and_aggregation():
+    """reference tests/test_concurrent_tool_calls.py:12-36: one model turn asks for 3 tools at once; every
+    tool's value must reach the final answer and the last tool-call message carries 3 calls."""
+    _skip_without_cuda()
+    from calfkit import Agent, Client, Worker, agent_tool
+    from calfkit.models.messages import ModelResponse, TextPart, ToolCallPart, ToolReturnPart
+    from calfkit.nodes import FunctionModelClient
+
+    @agent_tool
+    def tool_a(x: str) -> str:
+        """a"""
+        return f"A<{x}>"
+
+    @agent_tool(device_template="B<{x}>")
+    def tool_b(x: str) -> str:
+        """b"""
+        return f"B<{x}>"
+
+    @agent_tool
+    def tool_c(ctx, x: str) -> str:
+        """c: contextual tool reading provided deps"""
+        return f"C<{x}:{ctx.deps.provided_deps['tenant']}>"
+
+    def llm(messages, tools):
+        rets = [p for p in getattr(messages[-1], "parts", []) if isinstance(p, ToolReturnPart)]
+        if rets:
+            return ModelResponse(parts=[TextPart(content=" | ".join(str(r.content) for r in rets))])
+        return ModelResponse(parts=[ToolCallPart(tool_name=t.name, args={"x": "v"}) for t in tools])
+
+    async def go():
+        client = Client.connect()
+        agent = Agent("planner", subscribe_topics="planner.input", publish_topic="planner.output",
+                      model_client=FunctionModelClient(llm), tools=[tool_a, tool_b, tool_c])
+        worker = Worker(client, nodes=[agent, tool_a, tool_b, tool_c])
+        hs = [await client.invoke_node("go", "planner.input", deps={"tenant": f"t{i}"}) for i in range(20)]
+        await worker.run(until_idle=True)
+        res = [await h.result(timeout=5) for h in hs]
+        await client.close()
+        return res
+
+    res = asyncio.run(go())
+    for i, r in enumerate(res):
+        assert r.output == f"A<v> | B<v> | C<v:t{i}>"
+        calls = [m for m in r.message_history if getattr(m, "kind", "") == "response" and m.tool_calls]
+        assert len(calls[-1].tool_calls) == 3
