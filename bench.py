@@ -70,7 +70,7 @@ def run_reference(args, rank: int, world: int) -> None:
         return
     from calfkit import synth
     cores = os.cpu_count() or 1
-    per_step = max(cores * 400, 2000)
+    per_step = max(cores * 2000, 8000)                 # ~2 s of work per step on all cores
     recs = synth.tool_events(per_step, seed=77)
     for _ in range(args.warmup):
         cpu_arm(recs[: max(cores * 16, 64)], cores)
@@ -246,6 +246,7 @@ def main() -> None:
     eng.lib.ck_device_buffers2(eng.h, C.byref(p_pubs), C.byref(p_len), C.byref(p_desc))
     t_pubs = torch.as_tensor(CudaArray(p_pubs.value, (2 * n, 8), "<i4"), device=dev)
     t_out_off = torch.as_tensor(CudaArray(bufs["out_off"], (n + 1,), "<i8"), device=dev)
+    t_out_len = torch.as_tensor(CudaArray(p_len.value, (n,), "<i4"), device=dev)
     out_cap = eng.max_out
     t_out = torch.as_tensor(CudaArray(bufs["out"], (out_cap,), "|u1"), device=dev)
     send_buf = torch.empty(int(out_cap * min(1.0, args.cross * 2 + 0.05)) + (1 << 20), dtype=torch.uint8, device=dev) if world > 1 else None
@@ -261,7 +262,7 @@ def main() -> None:
 
     def exchange():
         """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
-        nrecv, rbytes, _rlens = run_exchange(plan_exchange(t_pubs, t_out_off, rank, world), gather, send_buf, recv_buf)
+        nrecv, rbytes, _rlens = run_exchange(plan_exchange(t_pubs, t_out_off, t_out_len, rank, world), gather, send_buf, recv_buf)
         return nrecv, rbytes
 
     def step_device():
@@ -287,8 +288,8 @@ def main() -> None:
                 extra = rbytes
                 if rbytes:
                     h_out[out_cap - rbytes:].copy_(recv_buf[:rbytes], non_blocking=True)
-        out, off, pubs = eng._fetch(out_buf=h_out_np)      # D2H of payload bytes, offsets, publish table (waits)
-        d2h_bytes[0] = int(out.nbytes + off.nbytes + pubs.nbytes + extra)
+        out, off, ln, pubs = eng._fetch(out_buf=h_out_np)      # D2H of payload bytes, offsets, publish table (waits)
+        d2h_bytes[0] = int(out.nbytes + off.nbytes + ln.nbytes + pubs.nbytes + extra)
 
     def barrier():
         if world > 1:
@@ -369,7 +370,7 @@ def main() -> None:
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    ncols_walk = COL["CALL_VAL_OFF"]
+    ncols_walk = COL["NOUT"]
     algo = {   # algorithmic bytes per launch
         "walk": in_bytes + 8 * (n + 1) + 4 * ncols_walk * n,
         "plan": 4 * 24 * n + 160 * n + 2 * 32 * n + 4 * n,

@@ -75,7 +75,7 @@ def load() -> C.CDLL:
         "ck_sync": (C.c_int, [vp]),
         "ck_out_size": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "ck_fetch_columns": (C.c_int, [vp, u32p]),
-        "ck_fetch_output": (C.c_int, [vp, u8p, C.c_uint64, i64p, vp]),
+        "ck_fetch_output": (C.c_int, [vp, u8p, C.c_uint64, i64p, u32p, vp]),
         "ck_fetch_topic_hist": (C.c_int, [vp, u32p, C.c_uint32]),
         "ck_stream": (vp, [vp]),
         "ck_device_buffers": (C.c_int, [vp] + [C.POINTER(vp)] * 5),

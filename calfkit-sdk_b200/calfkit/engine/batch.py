@@ -60,13 +60,13 @@ class Publish:
 class BatchOutput:
     """Result of one plan+emit: unique payloads + the publish table that references them."""
 
-    def __init__(self, engine: "BatchEngine", out: np.ndarray, out_off: np.ndarray, pubs: np.ndarray,
+    def __init__(self, engine: "BatchEngine", out: np.ndarray, out_off: np.ndarray, out_len: np.ndarray, pubs: np.ndarray,
                  in_data: np.ndarray | None, in_off: np.ndarray | None, cols: np.ndarray | None):
-        self.engine, self.out, self.out_off, self.pubs = engine, out, out_off, pubs
+        self.engine, self.out, self.out_off, self.out_len, self.pubs = engine, out, out_off, out_len, pubs
         self.in_data, self.in_off, self.cols = in_data, in_off, cols
 
     def payload(self, i: int) -> bytes:
-        return self.out[self.out_off[i]:self.out_off[i + 1]].tobytes()
+        return self.out[self.out_off[i]:self.out_off[i] + self.out_len[i]].tobytes()
 
     def live(self) -> np.ndarray:
         return self.pubs[self.pubs["payload"] != 0xFFFFFFFF]
@@ -117,7 +117,7 @@ class BatchEngine:
         self.lib = _lib.load()
         self.max_records, self.max_in = max_records, max_in_bytes
         self.max_payloads = max_payloads if max_payloads is not None else max_records
-        self.max_out = max_out_bytes if max_out_bytes is not None else max_in_bytes + 512 * max_records
+        self.max_out = max_out_bytes if max_out_bytes is not None else max_in_bytes + 528 * max_records
         self.max_aux = max_aux_bytes if max_aux_bytes is not None else max(1 << 20, max_in_bytes // 4, 32 * self.max_payloads)
         h = C.c_void_p()
         if self.lib.ck_create(device, self.max_in, self.max_out, max_records, self.max_payloads, self.max_aux, C.byref(h)):
@@ -219,8 +219,8 @@ class BatchEngine:
     def tool_args(self) -> tuple[np.ndarray, np.ndarray]:
         """(blob, offsets[n+1]): the `args` JSON of every record that reaches the tool (host tools)."""
         self._check(self.lib.ck_tool_args(self.h))
-        out, off, _ = self._fetch(want_pubs=False)
-        return out, off
+        out, off, ln, _ = self._fetch(want_pubs=False)
+        return out, off, ln
 
     def tool_plan(self, aux: np.ndarray | None = None, aux_off: np.ndarray | None = None) -> None:
         self._check(self.lib.ck_tool_plan(self.h, ptr(aux), ptr(aux_off)))
@@ -249,15 +249,16 @@ class BatchEngine:
         nb, npay, npub = self.out_size()
         out = out_buf if out_buf is not None else np.empty(max(nb, 1), dtype=np.uint8)
         off = np.zeros(npay + 1, dtype=np.int64)
+        ln = np.zeros(npay, dtype=np.uint32)
         pubs = np.zeros(npub if want_pubs else 0, dtype=PUB_DTYPE)
         self._check(self.lib.ck_fetch_output(self.h, ptr(out), out.nbytes, ptr(off) if npay else None,
-                                             ptr(pubs) if (want_pubs and npub) else None))
-        return out[:nb], off, pubs
+                                             ptr(ln) if npay else None, ptr(pubs) if (want_pubs and npub) else None))
+        return out[:nb], off, ln, pubs
 
     def fetch(self, out_buf: np.ndarray | None = None, with_columns: bool = True) -> BatchOutput:
-        out, off, pubs = self._fetch(out_buf=out_buf)
+        out, off, ln, pubs = self._fetch(out_buf=out_buf)
         cols = self.columns() if with_columns else None
-        return BatchOutput(self, out, off, pubs, self._in_data, self._in_off, cols)
+        return BatchOutput(self, out, off, ln, pubs, self._in_data, self._in_off, cols)
 
     # ------------------------------------------------------------------------------------------
     def stream_ptr(self) -> int:
@@ -285,9 +286,8 @@ class BatchEngine:
         if host_tool is None:
             self.tool_plan()
         else:
-            blob, off = self.tool_args()
-            results = [host_tool(blob[off[i]:off[i + 1]].tobytes()) if off[i + 1] > off[i] else b""
-                       for i in range(self.n)]
+            blob, off, ln = self.tool_args()
+            results = [host_tool(blob[off[i]:off[i] + ln[i]].tobytes()) if ln[i] else b"" for i in range(self.n)]
             aux_off = np.zeros(self.n + 1, dtype=np.int64)
             np.cumsum([len(r) for r in results], out=aux_off[1:])
             aux = np.frombuffer(b"".join(results) or b"\0", dtype=np.uint8)

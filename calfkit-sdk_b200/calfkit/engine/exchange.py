@@ -26,9 +26,10 @@ class ExchangePlan:
     nbytes: torch.Tensor     # int64 [world] bytes per destination
 
 
-def plan_exchange(pubs: torch.Tensor, out_off: torch.Tensor, rank: int, world: int) -> ExchangePlan:
+def plan_exchange(pubs: torch.Tensor, out_off: torch.Tensor, out_len: torch.Tensor, rank: int, world: int) -> ExchangePlan:
     """pubs: int32 [npubs, 8] view of the ck_publish table (payload, topic_id, topic_off, topic_len,
-    record, has_key, partition, pad); out_off: int64 [npayloads + 1]."""
+    record, has_key, partition, pad); out_off: int64 [npayloads + 1] (16-byte aligned starts);
+    out_len: payload lengths."""
     keyed = (pubs[:, 5] == 1) & (pubs[:, 0] != -1)
     dest = (pubs[:, 6] % world).to(torch.int64)
     sel = torch.nonzero(keyed & (dest != rank)).squeeze(1)
@@ -37,7 +38,7 @@ def plan_exchange(pubs: torch.Tensor, out_off: torch.Tensor, rank: int, world: i
     sel, d_sel = sel[order], d_sel[order]
     pay = pubs[sel, 0].to(torch.int64)
     src_off = out_off[pay]
-    lens = out_off[pay + 1] - src_off
+    lens = out_len[pay].to(torch.int64)
     dst_off = torch.cumsum(lens, 0) - lens
     counts = torch.bincount(d_sel, minlength=world)
     nbytes = torch.zeros(world, dtype=torch.int64, device=pubs.device).scatter_add_(0, d_sel, lens)

@@ -113,14 +113,14 @@ class ToolNodeDef(BaseToolNodeDef):
         if self._template is not None:
             engine.tool_plan()
         else:
-            blob, off = engine.tool_args()
+            blob, off, ln = engine.tool_args()
             cols = engine.columns()
             mv = memoryview(data)
             results: list[bytes] = []
             for i in range(len(records)):
                 if cols[COL["ACTION"], i] == CK_ACT_HOST_TOOL:
                     rec = mv[offsets[i]:offsets[i + 1]]
-                    results.append(self._call_host(blob[off[i]:off[i + 1]].tobytes(), rec, cols, i))
+                    results.append(self._call_host(blob[off[i]:off[i] + ln[i]].tobytes(), rec, cols, i))
                 else:
                     results.append(b"")
             aux_off = np.zeros(len(records) + 1, dtype=np.int64)

@@ -232,20 +232,20 @@ extern "C" int ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64
     return launch_walk(h);
 }
 
-static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off) {
+static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad) {
     KTimer t(h, CK_K_SCAN);
     u32 ntiles = (n + CK_SCAN_TILE - 1) / CK_SCAN_TILE;
     if (n) {
-        ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum);
+        ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum, pad);
         ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_tile_sum, ntiles, h->d_grand);
-        ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum, out_off);
+        ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum, out_off, pad);
     }
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
 
 static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
-    if (run_scan(h, h->d_pay_len, npay, h->d_out_off)) return 1;
+    if (run_scan(h, h->d_pay_len, npay, h->d_out_off, 15)) return 1;   // payloads start 16-byte aligned
     {
         KTimer t(h, CK_K_EMIT);
         if (npay) {
@@ -392,7 +392,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
         if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, n, h->d_cols, n, h->d_agent_cfg, max_fanout, h->d_counts);
         CUDA_TRY(h, cudaGetLastError());
     }
-    if (run_scan(h, h->d_counts, n, h->d_slot_base)) return 1;
+    if (run_scan(h, h->d_counts, n, h->d_slot_base, 0)) return 1;
     *h->h_grand = 0;
     if (n) CUDA_TRY(h, cudaMemcpyAsync(h->h_grand, h->d_grand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -453,7 +453,8 @@ extern "C" int ck_fetch_columns(ck_handle* h, uint32_t* host_cols) {
     return 0;
 }
 
-extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, ck_publish* host_pubs) {
+extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, uint32_t* host_out_len,
+                               ck_publish* host_pubs) {
     cudaSetDevice(h->device);
     uint64_t total = 0;
     if (ck_out_size(h, &total, nullptr, nullptr)) return 1;
@@ -461,6 +462,7 @@ extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, in
     if (total > h->max_out) return fail(h, "ck_fetch_output: device output buffer overflowed (raise max_out_bytes)");
     if (host_out && total) CUDA_TRY(h, cudaMemcpyAsync(host_out, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
     if (host_out_off && h->n_payloads) CUDA_TRY(h, cudaMemcpyAsync(host_out_off, h->d_out_off, sizeof(long long) * ((size_t)h->n_payloads + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (host_out_len && h->n_payloads) CUDA_TRY(h, cudaMemcpyAsync(host_out_len, h->d_pay_len, sizeof(u32) * (size_t)h->n_payloads, cudaMemcpyDeviceToHost, h->stream));
     if (host_pubs && h->n_pubs) CUDA_TRY(h, cudaMemcpyAsync(host_pubs, h->d_pubs, sizeof(ck_pub) * (size_t)h->n_pubs, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;

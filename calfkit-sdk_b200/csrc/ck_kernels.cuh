@@ -60,7 +60,7 @@ __device__ __forceinline__ u32 ck_fnv1a(const u8* p, u32 n) {
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -179,7 +179,7 @@ ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off
         u8 c0 = r.at(COL(CK_COL_ARG0_OFF));
         action = (c0 == '[' || c0 == '{') ? CK_ACT_RAISES : CK_ACT_SILENT;   // unhashable key raises; other scalars miss
     } else {
-        call = ck_dict_find(r, COL(CK_COL_TC_OFF), COL(CK_COL_ARG0_OFF), COL(CK_COL_ARG0_LEN));
+        call.off = COL(CK_COL_CALL_VAL_OFF); call.len = COL(CK_COL_CALL_VAL_LEN);   // resolved by the walker
         action = call.len ? CK_ACT_RETURN : CK_ACT_SILENT;
     }
     if (action == CK_ACT_RAISES) { COL(CK_COL_ACTION) = action; COL(CK_COL_NOUT) = 0; return; }
@@ -193,18 +193,10 @@ ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off
         COL(CK_COL_ACTION) = action; COL(CK_COL_NOUT) = cfg.publish_topic_id >= 0 ? 1 : 0;
         return;
     }
-    // ---- the ToolCallPart: {"tool_name":S,"args":V,...
-    u32 pos = call.off + 13;                      // past {"tool_name":
-    Span tname; ck_string(r, pos, tname);
-    pos += 8;                                     // past ,"args":
-    u32 args0 = pos; ck_skip_value(r, pos);
-    Span args = {args0, pos - args0};
-    COL(CK_COL_CALL_VAL_OFF) = call.off; COL(CK_COL_CALL_VAL_LEN) = call.len;
-    COL(CK_COL_TNAME_OFF) = tname.off; COL(CK_COL_TNAME_LEN) = tname.len;
-    COL(CK_COL_ARGS_OFF) = args.off; COL(CK_COL_ARGS_LEN) = args.len;
+    // ---- the ToolCallPart and an existing result for the same id (spans resolved by the walker)
+    Span args = {COL(CK_COL_ARGS_OFF), COL(CK_COL_ARGS_LEN)};
     u32 id_off = COL(CK_COL_ARG0_OFF), id_len = COL(CK_COL_ARG0_LEN);
-    Span existing = ck_dict_find(r, COL(CK_COL_TR_OFF), id_off, id_len);
-    COL(CK_COL_RES_OFF) = existing.off; COL(CK_COL_RES_LEN) = existing.len;
+    Span existing = {COL(CK_COL_RES_OFF), COL(CK_COL_RES_LEN)};
 
     // ---- the tool's return value as JSON
     u32 rv_src[CK_TPL_MAX_PARTS], rv_off[CK_TPL_MAX_PARTS], rv_len[CK_TPL_MAX_PARTS], rv_n = 0;
@@ -466,12 +458,13 @@ __device__ __forceinline__ unsigned long long ck_block_scan_excl(unsigned long l
     return base + x - v;
 }
 
+// pad = 15: every length is rounded up to a multiple of 16 so that payloads start 16-byte aligned
 __global__ void __launch_bounds__(CK_SCAN_BLOCK)
-ck_scan_tiles_kernel(const u32* __restrict__ len, u32 n, unsigned long long* __restrict__ tile_sum) {
+ck_scan_tiles_kernel(const u32* __restrict__ len, u32 n, unsigned long long* __restrict__ tile_sum, u32 pad) {
     u32 base = blockIdx.x * CK_SCAN_TILE + threadIdx.x * CK_SCAN_ITEMS;
     unsigned long long s = 0;
 #pragma unroll
-    for (int k = 0; k < CK_SCAN_ITEMS; k++) if (base + k < n) s += len[base + k];
+    for (int k = 0; k < CK_SCAN_ITEMS; k++) if (base + k < n) s += (len[base + k] + pad) & ~pad;
     unsigned long long total;
     ck_block_scan_excl(s, &total);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
@@ -492,12 +485,12 @@ ck_scan_sums_kernel(unsigned long long* __restrict__ tile_sum, u32 ntiles, unsig
 
 __global__ void __launch_bounds__(CK_SCAN_BLOCK)
 ck_scan_apply_kernel(const u32* __restrict__ len, u32 n, const unsigned long long* __restrict__ tile_sum,
-                     long long* __restrict__ out_off /* n+1 */) {
+                     long long* __restrict__ out_off /* n+1 */, u32 pad) {
     u32 base = blockIdx.x * CK_SCAN_TILE + threadIdx.x * CK_SCAN_ITEMS;
     u32 v[CK_SCAN_ITEMS];
     unsigned long long s = 0;
 #pragma unroll
-    for (int k = 0; k < CK_SCAN_ITEMS; k++) { v[k] = (base + k < n) ? len[base + k] : 0; s += v[k]; }
+    for (int k = 0; k < CK_SCAN_ITEMS; k++) { v[k] = (base + k < n) ? ((len[base + k] + pad) & ~pad) : 0; s += v[k]; }
     unsigned long long total;
     unsigned long long e = ck_block_scan_excl(s, &total) + tile_sum[blockIdx.x];
 #pragma unroll
@@ -508,27 +501,44 @@ ck_scan_apply_kernel(const u32* __restrict__ len, u32 n, const unsigned long lon
 // ------------------------------------------------------------------------------------------------
 // encode: one warp per payload gathers its segments into out[out_off[i] ...)
 // ------------------------------------------------------------------------------------------------
+// warp-cooperative byte copy.  Short pieces (the literal / id segments of a splice, <= 128 B) go one
+// byte per lane; long pieces go as 16-byte destination-aligned vector stores, each assembled from two
+// source-aligned 16-byte loads with a warp-uniform byte shift (src and dst are generally misaligned
+// relative to each other: JSON spans start anywhere).
+__device__ __forceinline__ u32 ck_fsr(u32 lo, u32 hi, u32 bits) { return __funnelshift_r(lo, hi, bits); }
+
 __device__ __forceinline__ void ck_warp_copy(u8* __restrict__ dst, const u8* __restrict__ src, u32 len, u32 lane) {
-    // head to 4-byte destination alignment
-    u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3);
-    if (head > len) head = len;
+    if (len <= 128) {
+#pragma unroll
+        for (u32 k = 0; k < 4; k++) { u32 idx = lane + 32 * k; if (idx < len) dst[idx] = src[idx]; }
+        return;
+    }
+    u32 head = (u32)((16 - ((uintptr_t)dst & 15)) & 15);
     if (lane < head) dst[lane] = src[lane];
     dst += head; src += head; len -= head;
-    u32 nw = len >> 2;
-    u32 sh = (u32)((uintptr_t)src & 3);
-    const u32* s4 = (const u32*)((uintptr_t)src - sh);
-    u32* d4 = (u32*)dst;
-    if (sh == 0) {
-        for (u32 k = lane; k < nw; k += 32) d4[k] = __ldg(s4 + k);
-    } else {
-        u32 bits = sh * 8;
-        for (u32 k = lane; k < nw; k += 32) {
-            u32 lo = __ldg(s4 + k), hi = __ldg(s4 + k + 1);     // hi may touch up to 3 bytes past the segment: inside the padded buffers
-            d4[k] = __funnelshift_r(lo, hi, bits);
+    u32 nvec = len >> 4;
+    u32 sh = (u32)((uintptr_t)src & 15);
+    const uint4* s16 = (const uint4*)((uintptr_t)src - sh);
+    uint4* d16 = (uint4*)dst;
+    u32 q = sh >> 2, bits = (sh & 3) * 8;
+    for (u32 v = lane; v < nvec; v += 32) {
+        uint4 a = __ldg(s16 + v);
+        uint4 o;
+        if (sh == 0) o = a;
+        else {
+            uint4 b = __ldg(s16 + v + 1);       // may touch <= 31 bytes past the span: inside the padded buffers
+            u32 w0, w1, w2, w3, w4;
+            switch (q) {                        // warp-uniform
+                case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+                case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+                case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+                default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+            }
+            o.x = ck_fsr(w0, w1, bits); o.y = ck_fsr(w1, w2, bits); o.z = ck_fsr(w2, w3, bits); o.w = ck_fsr(w3, w4, bits);
         }
+        d16[v] = o;
     }
-    u32 done = nw << 2;
-    u32 tail = len - done;
+    u32 done = nvec << 4, tail = len - done;
     if (lane < tail) dst[done + lane] = src[done + lane];
 }
 
@@ -552,10 +562,18 @@ ck_emit_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, 
     if (o1 == o0 || o1 > out_cap) return;    // overflow is reported by ck_fetch_output, never written
     const ck_out_desc* d = descs + warp;
     u32 nseg = d->nseg;
+    if (nseg > CK_MAX_SEGS) return;
     // lanes 0..nseg-1 fetch one segment descriptor each, then broadcast
     u32 my_off = lane < nseg ? d->src_off[lane] : 0, my_ls = lane < nseg ? d->len_src[lane] : 0;
     const u8* rec = in + in_off[d->record];
     u8* dst = out + o0;
+    // pull the whole source record towards L1 with one wave of independent requests, so that the
+    // segment copies below (a dependent load->store chain per segment) hit L1 instead of each exposing
+    // a full HBM latency
+    {
+        u32 rec_len = (u32)(in_off[d->record + 1] - in_off[d->record]);
+        for (u32 o = lane * 128; o < rec_len; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + o));
+    }
     for (u32 s = 0; s < nseg; s++) {
         u32 so = __shfl_sync(0xffffffffu, my_off, s), ls = __shfl_sync(0xffffffffu, my_ls, s);
         u32 len = ls >> 2, src = ls & 3u;

@@ -738,6 +738,11 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     u32 pos = 0;
     Span t;
     stop = 0;
+    // keys of the two id-keyed dicts: 32-bit hash (uniqueness check: the reference holds Python dicts)
+    // + span, so that tool_calls[input_args[0]] / tool_results[...] can be resolved at the end of the
+    // walk without scanning the dicts again
+    u32 tc_kh[CK_DICT_KEYS], tc_koff[CK_DICT_KEYS], tc_n = 0;     // key length is re-derived from the closing quote
+    u32 tr_kh[CK_DICT_KEYS], tr_koff[CK_DICT_KEYS], tr_n = 0;
 #define FAIL do { stop = pos; return false; } while (0)
     // ---- context.state ---------------------------------------------------------------------
     if (!M("{\"context\":{\"state\":{\"tool_calls\":{")) FAIL;
@@ -745,14 +750,12 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!PEEK('}')) {
         // dict[str, ToolCallPart]; keys must be unique (a Python dict on the reference side):
         // 32-bit hashes of the raw key bytes, a (vanishingly rare) collision only costs the fast path
-        u32 nk = 0;
-        u32 kh[CK_DICT_KEYS];
         for (;;) {
             if (!ck_string(r, pos, t)) FAIL;
             u32 h = ck_hash_span(r, t.off, t.len);
-            for (u32 k = 0; k < nk; k++) if (kh[k] == h) FAIL;
-            if (nk >= CK_DICT_KEYS) FAIL;
-            kh[nk++] = h;
+            for (u32 k = 0; k < tc_n; k++) if (tc_kh[k] == h) FAIL;
+            if (tc_n >= CK_DICT_KEYS) FAIL;
+            tc_kh[tc_n] = h; tc_koff[tc_n] = t.off; tc_n++;
             ToolCallSpans tc;
             if (!M(":") || ck_tool_call_part(r, pos, 5, cx, tc) != 1) FAIL;
             if (PEEK(',')) { pos++; continue; }
@@ -765,14 +768,12 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M(",\"tool_results\":{")) FAIL;
     a = pos - 1;
     if (!PEEK('}')) {
-        u32 nk = 0;
-        u32 kh[CK_DICT_KEYS];
         for (;;) {
             if (!ck_string(r, pos, t)) FAIL;
             u32 h = ck_hash_span(r, t.off, t.len);
-            for (u32 k = 0; k < nk; k++) if (kh[k] == h) FAIL;
-            if (nk >= CK_DICT_KEYS) FAIL;
-            kh[nk++] = h;
+            for (u32 k = 0; k < tr_n; k++) if (tr_kh[k] == h) FAIL;
+            if (tr_n >= CK_DICT_KEYS) FAIL;
+            tr_kh[tr_n] = h; tr_koff[tr_n] = t.off; tr_n++;
             if (!M(":") || !ck_tool_result_value(r, pos, 5, cx)) FAIL;
             if (PEEK(',')) { pos++; continue; }
             break;
@@ -838,11 +839,10 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M("}},\"internal_workflow_state\":{\"call_stack\":{\"_internal_list\":[")) FAIL;
     a = pos - 1;
     u32 nframes = 0;
-    if (PEEK(']')) {
-        // empty stack: the current-frame columns are defined (zero) even though no frame exists
-        for (u32 c = CK_COL_TOP_OFF; c <= CK_COL_FOV_LEN; c++) o.set(c, 0);
-        o.set(CK_COL_NARGS, CK_NARGS_NULL);
-    } else {
+    // the LAST frame is the current one (Stack.peek, reference models/session_context.py:26-30)
+    u32 top0 = 0, top1 = 0, fov0 = 0, fov1 = 0, top_nargs = CK_NARGS_NULL, top_kinds = 0;
+    Span top_tgt = {0, 0}, top_cb = {0, 0}, top_a0 = {0, 0}, top_a1 = {0, 0};
+    if (!PEEK(']')) {
         for (;;) {
             u32 f0 = pos;
             Span tgt, cb;
@@ -876,18 +876,19 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             u32 ov1 = pos;
             if (!M("}")) FAIL;
             nframes++;
-            // the LAST frame is the current one (Stack.peek, reference models/session_context.py:26-30)
-            SETSPAN(CK_COL_TOP_OFF, f0, pos);
-            o.set(CK_COL_TGT_OFF, tgt.off); o.set(CK_COL_TGT_LEN, tgt.len);
-            o.set(CK_COL_CB_OFF, cb.off); o.set(CK_COL_CB_LEN, cb.len);
-            o.set(CK_COL_NARGS, nargs); o.set(CK_COL_ARGKINDS, kinds);
-            o.set(CK_COL_ARG0_OFF, a0.off); o.set(CK_COL_ARG0_LEN, a0.len);
-            o.set(CK_COL_ARG1_OFF, a1.off); o.set(CK_COL_ARG1_LEN, a1.len);
-            SETSPAN(CK_COL_FOV_OFF, ov0, ov1);
+            top0 = f0; top1 = pos; fov0 = ov0; fov1 = ov1; top_nargs = nargs; top_kinds = kinds;
+            top_tgt = tgt; top_cb = cb; top_a0 = a0; top_a1 = a1;
             if (PEEK(',')) { pos++; continue; }
             break;
         }
     }
+    SETSPAN(CK_COL_TOP_OFF, top0, top1);
+    o.set(CK_COL_TGT_OFF, top_tgt.off); o.set(CK_COL_TGT_LEN, top_tgt.len);
+    o.set(CK_COL_CB_OFF, top_cb.off); o.set(CK_COL_CB_LEN, top_cb.len);
+    o.set(CK_COL_NARGS, top_nargs); o.set(CK_COL_ARGKINDS, top_kinds);
+    o.set(CK_COL_ARG0_OFF, top_a0.off); o.set(CK_COL_ARG0_LEN, top_a0.len);
+    o.set(CK_COL_ARG1_OFF, top_a1.off); o.set(CK_COL_ARG1_LEN, top_a1.len);
+    SETSPAN(CK_COL_FOV_OFF, fov0, fov1);
     if (!M("]")) FAIL;
     SETSPAN(CK_COL_FRAMES_OFF, a, pos);
     o.set(CK_COL_NFRAMES, nframes);
@@ -897,6 +898,45 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     SETSPAN(CK_COL_WFMETA_OFF, a, pos);
     if (!M("}}")) FAIL;
     if (pos != r.n) FAIL;                 // trailing bytes (even whitespace) are not a fixed point
+    // resolve tool_calls[input_args[0]] and tool_results[input_args[0]] (what ToolNodeDef.run looks up,
+    // reference nodes/tool.py:45, models/state.py:78-79) from the recorded key spans
+    u32 call0 = 0, call1 = 0, res0 = 0, res1 = 0;
+    Span tn = {0, 0}, ar = {0, 0};
+    if (nframes > 0 && top_nargs == 2 && (top_kinds & 1u)) {
+        u32 h = ck_hash_span(r, top_a0.off, top_a0.len);
+        // the hash covers the length, so a hit is (almost surely) the key: verify bytes + closing quote
+        for (u32 k = 0; k < tc_n; k++) {
+            if (tc_kh[k] != h) continue;
+            u32 ko = tc_koff[k];
+            if (ko + top_a0.len >= r.n || r.at(ko + top_a0.len) != '"') continue;
+            bool eq = true;
+            for (u32 b = 0; b < top_a0.len; b++) if (r.at(ko + b) != r.at(top_a0.off + b)) { eq = false; break; }
+            if (!eq) continue;
+            u32 p2 = ko + top_a0.len + 2;
+            call0 = p2;
+            ToolCallSpans tcs;
+            ck_tool_call_part(r, p2, 5, cx, tcs);
+            call1 = p2; tn = tcs.tool_name; ar = tcs.args;
+            break;
+        }
+        for (u32 k = 0; k < tr_n; k++) {
+            if (tr_kh[k] != h) continue;
+            u32 ko = tr_koff[k];
+            if (ko + top_a0.len >= r.n || r.at(ko + top_a0.len) != '"') continue;
+            bool eq = true;
+            for (u32 b = 0; b < top_a0.len; b++) if (r.at(ko + b) != r.at(top_a0.off + b)) { eq = false; break; }
+            if (!eq) continue;
+            u32 p2 = ko + top_a0.len + 2;
+            res0 = p2;
+            ck_tool_result_value(r, p2, 5, cx);
+            res1 = p2;
+            break;
+        }
+    }
+    SETSPAN(CK_COL_CALL_VAL_OFF, call0, call1);
+    o.set(CK_COL_TNAME_OFF, tn.off); o.set(CK_COL_TNAME_LEN, tn.len);
+    o.set(CK_COL_ARGS_OFF, ar.off); o.set(CK_COL_ARGS_LEN, ar.len);
+    SETSPAN(CK_COL_RES_OFF, res0, res1);
     return true;
 #undef FAIL
 }

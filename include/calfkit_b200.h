@@ -96,8 +96,11 @@ int  ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64_t* dev_sr
 int  ck_sync(ck_handle* h);
 int  ck_out_size(ck_handle* h, uint64_t* out_bytes, uint32_t* n_payloads, uint32_t* n_publishes);  /* waits */
 int  ck_fetch_columns(ck_handle* h, uint32_t* host_cols /* CK_NUM_COLS * n, column-major */);
+/* payload i = host_out[host_out_off[i] .. + host_out_len[i]); starts are 16-byte aligned, so
+ * host_out_off[i+1] - host_out_off[i] is the length rounded up to 16 and *out_bytes of ck_out_size is
+ * the padded total */
 int  ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off /* n_payloads+1 */,
-                     ck_publish* host_pubs /* n_publishes */);
+                     uint32_t* host_out_len /* n_payloads */, ck_publish* host_pubs /* n_publishes */);
 int  ck_fetch_topic_hist(ck_handle* h, uint32_t* host_hist, uint32_t n);
 
 /* introspection for benchmarks / tests ------------------------------------------------------------ */

@@ -24,7 +24,7 @@ def _worker(rank: int, world: int, port: int, q):
     for i in range(n):                      # slot 2i: keyed callback publish, 2i+1: unkeyed publish_topic copy
         pubs[2 * i] = torch.tensor([i, 2, 0, 0, i, 1, int(part[i]), 0], dtype=torch.int32)
         pubs[2 * i + 1] = torch.tensor([i, 1, 0, 0, i, 0, -1, 0], dtype=torch.int32)
-    plan = plan_exchange(pubs, out_off, rank, world)
+    plan = plan_exchange(pubs, out_off, torch.from_numpy(lens.astype(np.int32)), rank, world)
     expect_sel = [2 * i for d in range(world) for i in range(n) if part[i] % world == d and d != rank]
     assert plan.sel.tolist() == expect_sel
     send, recv = torch.zeros(4096, dtype=torch.uint8), torch.zeros(4096, dtype=torch.uint8)

@@ -172,7 +172,7 @@ def test_device_walker_equals_host_build_on_fuzz(engine):
     b = synth.pack(recs)
     engine.submit(b.data, b.offsets)
     cols = engine.columns()
-    ncmp = 42   # walker-owned columns
+    ncmp = 50   # walker-owned columns (incl. the resolved tool call / existing result spans)
     for i, r in enumerate(recs):
         if len(r) == 0:
             assert cols[0, i] == 5
@@ -222,3 +222,41 @@ def test_fanout_matches_oracle(engine):
         assert k == len(pubs)
     finally:
         e.close()
+
+
+def test_mixed_sizes_and_edge_batches(engine):
+    """config 5 shapes (128 B .. 64 KB, 256 topics' worth of tools, UTF-8 + escapes) and degenerate
+    batches: empty batch, zero-length record, a batch of one."""
+    import tools_def
+    from oracle import port
+    from calfkit import synth
+    from calfkit.engine import ToolTemplate
+    from calfkit.engine._lib import COL
+    tools = [f"tool_{j:02d}" for j in range(32)]
+    topics = [f"tool.{t}.input" for t in tools] + ["tool.out", "weather_agent.input"]
+    engine.register_topics(topics, num_partitions=8)
+    engine.set_tool_node("tool.out", ToolTemplate.from_format("It's sunny in {location}"))
+    recs = synth.mixed_events(300, seed=21, lo=128, hi=65536, n_tools=32) + [b""]
+    b = synth.pack(recs)
+    out = engine.run_tool_batch(b.data, b.offsets)
+    st = out.cols[COL["STATUS"]]
+    assert (st[:-1] == 0).all() and st[-1] == 5                 # the empty record is CK_EMPTY, the batch goes on
+    assert max(len(r) for r in recs) > 40000
+    pubs = list(out.publishes())
+    assert len(pubs) == 2 * (len(recs) - 1)
+
+    def get_weather(location: str) -> str:
+        return f"It's sunny in {location}"
+    k = 0
+    for i, r in enumerate(recs[:-1]):
+        tname = port.decode(r).internal_workflow_state.current_frame.target_topic.split(".")[1]
+        node = port.ToolNode(get_weather, f"tool_{tname}", [f"tool.{tname}.input"], "tool.out")
+        want = port.tool_node_event(node, r)
+        assert [(p.topic, p.key, p.payload) for p in pubs[k:k + 2]] == [(t, kk, pl) for (t, kk, c, pl) in want], i
+        k += 2
+    # empty batch and a batch of one
+    e0 = synth.pack([])
+    out0 = engine.run_tool_batch(e0.data if e0.data.size else np.zeros(1, dtype=np.uint8), e0.offsets)
+    assert len(out0.live()) == 0
+    one = synth.pack(recs[:1])
+    assert len(list(engine.run_tool_batch(one.data, one.offsets).publishes())) == 2
