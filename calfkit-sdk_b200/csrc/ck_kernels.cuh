@@ -12,6 +12,7 @@
 
 #include <cuda_runtime.h>
 #include "ck_walk.cuh"
+#include "ck_vm.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // node configuration living in device memory
@@ -60,8 +61,16 @@ __device__ __forceinline__ u32 ck_fnv1a(const u8* p, u32 n) {
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8)
+__constant__ uint32_t ck_vm_prog_dev[CK_VM_PROG_WORDS] = CK_VM_PROG_INIT;
+
+#define CK_WALK_THREADS 128
+__global__ void __launch_bounds__(CK_WALK_THREADS)
 ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride) {
+    // the schema bytecode and one 64-byte window per thread live in shared memory
+    __shared__ u32 s_prog[CK_VM_PROG_WORDS];
+    __shared__ u32 s_win[CK_WALK_THREADS * CK_WIN_WORDS];
+    for (u32 k = threadIdx.x; k < CK_VM_PROG_WORDS; k += CK_WALK_THREADS) s_prog[k] = ck_vm_prog_dev[k];
+    __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long a = off[i], b = off[i + 1];
@@ -70,10 +79,11 @@ ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
     else {
-        Rd r; r.init(in + a, len);
+        VRd r; r.init(in + a, len, s_win + threadIdx.x * CK_WIN_WORDS);
         AnyCtx cx;
         cx.kfill = 0;
-        status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_NOT_CANONICAL;
+        VmDicts dk;
+        status = ck_vm_walk(r, s_prog, o, cx, dk, stop) ? CK_OK : CK_NOT_CANONICAL;
     }
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);

@@ -27,6 +27,9 @@
 typedef uint8_t u8;
 typedef uint32_t u32;
 typedef uint64_t u64;
+#if !defined(__CUDACC__)
+struct uint4 { u32 x, y, z, w; };        // host test build of the device sources
+#endif
 
 struct Span { u32 off, len; };
 

@@ -12,7 +12,9 @@ _LIB = os.path.join(HERE, "libck_hostsim.so")
 def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, "hostsim.cpp"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_walk.cuh"),
-            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_common.h")]
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_common.h"),
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm.cuh"),
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm_prog.h")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-o", _LIB, srcs[0]])
@@ -29,6 +31,8 @@ def lib():
         _lib.ck_host_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_walk.restype = ctypes.c_int
         _lib.ck_host_num_cols.restype = ctypes.c_int
+        _lib.ck_host_vm_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
+        _lib.ck_host_vm_walk.restype = ctypes.c_int
     return _lib
 
 
@@ -37,4 +41,12 @@ def walk(payload: bytes):
     L = lib()
     cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
     ok = L.ck_host_walk(payload, len(payload), cols.ctypes.data)
+    return bool(ok), cols
+
+
+def vm_walk(payload: bytes):
+    """the table-driven walker (csrc/ck_vm.cuh): -> (accepted, cols)"""
+    L = lib()
+    cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
+    ok = L.ck_host_vm_walk(payload, len(payload), cols.ctypes.data)
     return bool(ok), cols

@@ -79,3 +79,45 @@ def test_mutation_fuzz_is_sound():
             accepted += 1
             assert _is_fixed(m), m[:2000]
     assert accepted > 1000
+
+
+def test_table_driven_walker_equals_recursive_walker():
+    """csrc/ck_vm.cuh (bytecode interpreter, the one the GPU runs) against csrc/ck_walk.cuh (recursive
+    descent, the one fuzzed against pydantic above): same verdict and same columns on every input."""
+    from calfkit import synth
+    from hostsim import vm_walk
+    rng = random.Random(11)
+    seeds = [as_bytes(c["input"]) for c in golden("codec.json")] + [as_bytes(c["input"]) for c in golden("tool_node.json")]
+    seeds += synth.tool_events(30, seed=1) + synth.tool_events(10, seed=2, size=None, full_history=True) + \
+        synth.fanout_events(2, seed=3, fanout=70) + synth.mixed_events(20, seed=4, hi=20000)
+    seeds = [s for s in seeds if s]
+
+    def same(b):
+        a1, c1 = walk(b)
+        a2, c2 = vm_walk(b)
+        assert a1 == a2, b[:300]
+        if a1:
+            assert (c1[2:50] == c2[2:50]).all(), b[:300]
+    for s in seeds:
+        same(s)
+    good = [s for s in seeds if walk(s)[0]]
+    tok = [b'"', b"{", b"}", b"[", b"]", b",", b":", b"\\", b" ", b"0", b"1", b"e", b".", b"-", b"null", b"true", b"false",
+           b"1.5", b'"a"', b"{}", b"[]", b"\xc3\xa9", b"\xff", b"\x01", b'"kind":"tool-return",', b'"a":1,', b"Z", b".5"]
+    for _ in range(60000):
+        b = bytearray(rng.choice(good))
+        for _ in range(rng.choice([1, 1, 2, 3])):
+            if not b:
+                break
+            op, i = rng.randrange(5), rng.randrange(len(b))
+            if op == 0:
+                b[i] = rng.randrange(256)
+            elif op == 1:
+                del b[i]
+            elif op == 2:
+                b[i:i] = rng.choice(tok)
+            elif op == 3:
+                j = min(len(b), i + rng.randrange(1, 40)); b[i:i] = b[i:j]
+            else:
+                j = min(len(b), i + rng.randrange(1, 40)); del b[i:j]
+        if b:
+            same(bytes(b))
