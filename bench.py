@@ -226,10 +226,76 @@ def main() -> None:
     batch = synth.pack(recs)
     del recs
     in_bytes = int(batch.data.nbytes)
-    eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096)
     topics = ["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"]
-    eng.register_topics(topics, num_partitions=NUM_PARTITIONS)
-    eng.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))
+    import ctypes as C
+    from calfkit.engine.exchange import exchange as run_exchange, plan_exchange
+    launches = [0]
+
+    class Lane:
+        """one BatchEngine (= one CUDA stream + its HBM buffers) with torch views of its result tables and
+        a pinned host landing buffer; two lanes ping-pong in the end-to-end loop (double buffering)"""
+        def __init__(self):
+            self.eng = eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096)
+            eng.register_topics(topics, num_partitions=NUM_PARTITIONS)
+            eng.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))
+            self.stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+            bufs = eng.device_buffers()
+            p_pubs, p_len, p_desc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            eng.lib.ck_device_buffers2(eng.h, C.byref(p_pubs), C.byref(p_len), C.byref(p_desc))
+            self.t_pubs = torch.as_tensor(CudaArray(p_pubs.value, (2 * n, 8), "<i4"), device=dev)
+            self.t_out_off = torch.as_tensor(CudaArray(bufs["out_off"], (n + 1,), "<i8"), device=dev)
+            self.t_out_len = torch.as_tensor(CudaArray(p_len.value, (n,), "<i4"), device=dev)
+            self.out_cap = eng.max_out
+            self.t_out = torch.as_tensor(CudaArray(bufs["out"], (self.out_cap,), "|u1"), device=dev)
+            if world > 1:
+                self.send_buf = torch.empty(int(self.out_cap * min(1.0, args.cross * 2 + 0.05)) + (1 << 20), dtype=torch.uint8, device=dev)
+                self.recv_buf = torch.empty_like(self.send_buf)
+            self.h_out = torch.empty(self.out_cap, dtype=torch.uint8).pin_memory()
+            self.h_out_np = self.h_out.numpy()
+            # pinned landing buffers for the offsets / lengths / publish table as well
+            self.h_off = torch.empty(n + 1, dtype=torch.int64).pin_memory().numpy()
+            self.h_len = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+            self.h_pubs = torch.empty(2 * n * PUB_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(PUB_DTYPE)
+            self.d2h = 0
+            self.rbytes = 0
+
+        def gather(self, plan, buf):
+            eng = self.eng
+            eng._check(eng.lib.ck_gather_spans(eng.h, self.t_out.data_ptr(), plan.src_off.data_ptr(), plan.lens.data_ptr(),
+                                               int(plan.sel.numel()), buf.data_ptr(), plan.dst_off.data_ptr()))
+            launches[0] += 1
+
+        def exchange(self):
+            """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
+            with torch.cuda.stream(self.stream):
+                nrecv, rbytes, _ = run_exchange(plan_exchange(self.t_pubs, self.t_out_off, self.t_out_len, rank, world),
+                                                self.gather, self.send_buf, self.recv_buf)
+            self.rbytes = rbytes
+            return nrecv, rbytes
+
+        def enqueue_device(self, d_in, d_off):
+            self.eng.submit_device(d_in, d_off, n)
+            self.eng.tool_plan()
+            launches[0] += 7            # walk, plan, 3 x scan, emit, route
+            if world > 1:
+                self.exchange()
+
+        def enqueue_host(self, h_in_np, h_off_np):
+            self.eng.submit(h_in_np, h_off_np)          # asynchronous H2D of the batch from pinned memory + decode
+            self.eng.tool_plan()
+            if world > 1:
+                self.exchange()
+                if self.rbytes:
+                    with torch.cuda.stream(self.stream):
+                        self.h_out[self.out_cap - self.rbytes:].copy_(self.recv_buf[:self.rbytes], non_blocking=True)
+
+        def fetch_host(self):
+            out, off, ln, pubs = self.eng._fetch(out_buf=self.h_out_np, off_buf=self.h_off, len_buf=self.h_len,
+                                                 pubs_buf=self.h_pubs)   # D2H: payloads, offsets, lengths, publishes (waits)
+            self.d2h = int(out.nbytes + off.nbytes + ln.nbytes + pubs.nbytes + self.rbytes)
+
+    lane = Lane()
+    eng = lane.eng
     if world > 1:
         eng.submit(batch.data, batch.offsets)
         corr_off = eng.columns()[COL["CORR_OFF"]]
@@ -239,57 +305,7 @@ def main() -> None:
     h_off = torch.from_numpy(batch.offsets.copy()).pin_memory()
     d_in = h_in.to(dev)
     d_off = h_off.to(dev)
-    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
-    bufs = eng.device_buffers()
-    import ctypes as C
-    p_pubs, p_len, p_desc = C.c_void_p(), C.c_void_p(), C.c_void_p()
-    eng.lib.ck_device_buffers2(eng.h, C.byref(p_pubs), C.byref(p_len), C.byref(p_desc))
-    t_pubs = torch.as_tensor(CudaArray(p_pubs.value, (2 * n, 8), "<i4"), device=dev)
-    t_out_off = torch.as_tensor(CudaArray(bufs["out_off"], (n + 1,), "<i8"), device=dev)
-    t_out_len = torch.as_tensor(CudaArray(p_len.value, (n,), "<i4"), device=dev)
-    out_cap = eng.max_out
-    t_out = torch.as_tensor(CudaArray(bufs["out"], (out_cap,), "|u1"), device=dev)
-    send_buf = torch.empty(int(out_cap * min(1.0, args.cross * 2 + 0.05)) + (1 << 20), dtype=torch.uint8, device=dev) if world > 1 else None
-    recv_buf = torch.empty_like(send_buf) if world > 1 else None
-    launches = [0]
-
-    from calfkit.engine.exchange import exchange as run_exchange, plan_exchange
-
-    def gather(plan, buf):
-        eng._check(eng.lib.ck_gather_spans(eng.h, t_out.data_ptr(), plan.src_off.data_ptr(), plan.lens.data_ptr(),
-                                           int(plan.sel.numel()), buf.data_ptr(), plan.dst_off.data_ptr()))
-        launches[0] += 1
-
-    def exchange():
-        """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
-        nrecv, rbytes, _rlens = run_exchange(plan_exchange(t_pubs, t_out_off, t_out_len, rank, world), gather, send_buf, recv_buf)
-        return nrecv, rbytes
-
-    def step_device():
-        eng.submit_device(d_in, d_off, n)
-        eng.tool_plan()
-        launches[0] += 7            # walk, plan, 3 x scan, emit, route
-        if world > 1:
-            with torch.cuda.stream(stream):
-                return exchange()
-        return 0, 0
-
-    h_out = torch.empty(out_cap, dtype=torch.uint8).pin_memory()
-    h_out_np = h_out.numpy()
-    d2h_bytes = [0]
-
-    def step_e2e():
-        eng.submit(h_in.numpy(), h_off.numpy())            # H2D of the batch + decode
-        eng.tool_plan()
-        extra = 0
-        if world > 1:
-            with torch.cuda.stream(stream):
-                _rc, rbytes = exchange()
-                extra = rbytes
-                if rbytes:
-                    h_out[out_cap - rbytes:].copy_(recv_buf[:rbytes], non_blocking=True)
-        out, off, ln, pubs = eng._fetch(out_buf=h_out_np)      # D2H of payload bytes, offsets, publish table (waits)
-        d2h_bytes[0] = int(out.nbytes + off.nbytes + ln.nbytes + pubs.nbytes + extra)
+    stream = lane.stream
 
     def barrier():
         if world > 1:
@@ -298,7 +314,7 @@ def main() -> None:
 
     # ---- device-resident timing ------------------------------------------------------------------
     for _ in range(args.warmup):
-        step_device()
+        lane.enqueue_device(d_in, d_off)
     eng.sync()
     eng.profile(True)
     sampler = ClockSampler(local_rank)
@@ -309,7 +325,7 @@ def main() -> None:
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
-            step_device()
+            lane.enqueue_device(d_in, d_off)
         ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -318,6 +334,7 @@ def main() -> None:
     eng.profile(False)
     gpu_launches = launches[0]
     out_bytes, npay, npub = eng.out_size()
+    out_payload_bytes = int(lane.t_out_len.to(torch.int64).sum().item())
     cols = eng.columns()
     ok_frac = float((cols[COL["STATUS"]] == 0).mean())
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -327,26 +344,34 @@ def main() -> None:
     ms_step = ms_total / args.steps
     value = world * n / (ms_step / 1e3)
 
-    # ---- end to end (host buffers) -----------------------------------------------------------------
-    for _ in range(2):
-        step_e2e()
+    # ---- end to end (host buffers), double buffered over two engines -------------------------------
+    # step k: lane k%2 takes the batch from pinned host memory (H2D + all kernels, asynchronous) while the
+    # previous step's results are copied back from the other lane (D2H + wait): the two PCIe directions
+    # and the kernels overlap, exactly as a worker consuming a stream of batches would run it.
+    lanes = [lane, Lane()]
+    h_in_np, h_off_np = h_in.numpy(), h_off.numpy()
+    e2e_steps = max(4, min(args.steps, 8))
+
+    def run_e2e(k_steps):
+        lanes[0].enqueue_host(h_in_np, h_off_np)
+        for k in range(1, k_steps):
+            lanes[k % 2].enqueue_host(h_in_np, h_off_np)
+            lanes[(k - 1) % 2].fetch_host()
+        lanes[(k_steps - 1) % 2].fetch_host()
+
+    run_e2e(3)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(3, min(args.steps, 5))
     t0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(e2e_steps):
-            step_e2e()
-        e1.record(stream)
-    barrier()
+    run_e2e(e2e_steps)
+    torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    t = torch.tensor([e2e_ms, wall_ms], dtype=torch.float64, device=dev)
+    barrier()
+    t = torch.tensor([wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0].item()) / e2e_steps
     e2e_value = world * n / (e2e_ms / 1e3)
+    d2h_bytes = [lanes[0].d2h]
 
     def shutdown():
         # orderly teardown, then leave without running interpreter finalisers (pinned tensors wrapping
@@ -375,7 +400,7 @@ def main() -> None:
         "walk": in_bytes + 8 * (n + 1) + 4 * ncols_walk * n,
         "plan": 4 * 24 * n + 160 * n + 2 * 32 * n + 4 * n,
         "scan": 3 * 4 * n + 8 * n,
-        "emit": 2 * out_bytes + 160 * n + 8 * n,
+        "emit": 2 * out_payload_bytes + 160 * n + 8 * n,
         "route": 2 * 2 * 32 * n,
     }
     kern = {}
@@ -395,8 +420,9 @@ def main() -> None:
     roofline = {"kernel": f"ck_{dom}_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": kern[dom]["ms_per_launch"] / ms_step,
-                "pipeline": {"algo_bytes_per_event": (in_bytes + out_bytes) / n,
-                             "achieved": (in_bytes + out_bytes) / ms_step / 1e6, "frac": (in_bytes + out_bytes) / ms_step / 1e6 / peak},
+                "pipeline": {"algo_bytes_per_event": (in_bytes + out_payload_bytes) / n,
+                             "achieved": (in_bytes + out_payload_bytes) / ms_step / 1e6,
+                             "frac": (in_bytes + out_payload_bytes) / ms_step / 1e6 / peak},
                 "kernels": kern, "sum_kernel_ms_per_step": kern_step_ms}
 
     # ---- CPU baseline: the oracle port on a bounded sample, all host cores ----------------------------
@@ -421,14 +447,16 @@ def main() -> None:
         "data": "synthetic",
         "config": {"workload": "tool_event_1k: tool-stage Envelope JSON (1152+-16 B), single @agent_tool node get_weather "
                                "(BASELINE.json configs[1])",
-                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "out_bytes_mean": out_bytes / max(npay, 1),
+                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "out_bytes_mean": out_payload_bytes / max(npay, 1),
                    "publishes_per_event": 2, "partitions": NUM_PARTITIONS, "cross_partition_fraction": args.cross if world > 1 else 0.0,
                    "sharding": "records by Kafka partition -> GPU" if world > 1 else "single GPU",
                    "l2": "inputs (%.2f GB) and outputs larger than the 126 MB L2: every step streams from HBM" % (in_bytes / 1e9),
                    "tool": "device template " + repr(TOOL_FMT), "accepted_fraction": ok_frac, "parity_spot_check_256": parity_ok},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h_bytes[0],
-                "ms_per_step": e2e_ms, "api": "BatchEngine.submit(host) + tool_plan + fetch(host)", "steps": e2e_steps},
+                "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "api": "BatchEngine.submit(pinned host) + tool_plan + fetch(pinned host), two engines double-buffered",
+                "timing": "host wall clock around the whole pipelined loop, synchronised on both sides (spans two streams), max over ranks"},
         "gpu_launches": gpu_launches,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",

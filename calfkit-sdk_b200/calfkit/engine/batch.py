@@ -245,14 +245,18 @@ class BatchEngine:
         self._check(self.lib.ck_out_size(self.h, C.byref(nb), C.byref(npay), C.byref(npub)))
         return nb.value, npay.value, npub.value
 
-    def _fetch(self, want_pubs: bool = True, out_buf: np.ndarray | None = None):
+    def _fetch(self, want_pubs: bool = True, out_buf: np.ndarray | None = None, off_buf: np.ndarray | None = None,
+               len_buf: np.ndarray | None = None, pubs_buf: np.ndarray | None = None):
+        """D2H of the results.  The optional *_buf arrays let a caller land everything in pinned memory it
+        owns (required for copies that overlap with the other PCIe direction)."""
         nb, npay, npub = self.out_size()
         out = out_buf if out_buf is not None else np.empty(max(nb, 1), dtype=np.uint8)
-        off = np.zeros(npay + 1, dtype=np.int64)
-        ln = np.zeros(npay, dtype=np.uint32)
-        pubs = np.zeros(npub if want_pubs else 0, dtype=PUB_DTYPE)
+        off = off_buf[:npay + 1] if off_buf is not None else np.zeros(npay + 1, dtype=np.int64)
+        ln = len_buf[:npay] if len_buf is not None else np.zeros(npay, dtype=np.uint32)
+        npub_eff = npub if want_pubs else 0
+        pubs = pubs_buf[:npub_eff] if pubs_buf is not None else np.zeros(npub_eff, dtype=PUB_DTYPE)
         self._check(self.lib.ck_fetch_output(self.h, ptr(out), out.nbytes, ptr(off) if npay else None,
-                                             ptr(ln) if npay else None, ptr(pubs) if (want_pubs and npub) else None))
+                                             ptr(ln) if npay else None, ptr(pubs) if npub_eff else None))
         return out[:nb], off, ln, pubs
 
     def fetch(self, out_buf: np.ndarray | None = None, with_columns: bool = True) -> BatchOutput:

@@ -207,7 +207,13 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
 
 static int launch_walk(ck_handle* h) {
     KTimer t(h, CK_K_WALK);
-    if (h->n) ck_walk_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n);
+    static int mode = -1, pf = 0;
+    if (mode < 0) {   // development switch for A/B measurements of the two walker implementations
+        const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "vm")) ? 1 : 0;
+        const char* q = getenv("CK_PREFETCH"); pf = q ? atoi(q) : 2048;
+    }
+    if (h->n && mode == 1) ck_walk_vm_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n);
+    else if (h->n) ck_walk_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n, (u32)pf);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }

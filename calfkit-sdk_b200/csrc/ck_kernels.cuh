@@ -65,7 +65,7 @@ __constant__ uint32_t ck_vm_prog_dev[CK_VM_PROG_WORDS] = CK_VM_PROG_INIT;
 
 #define CK_WALK_THREADS 128
 __global__ void __launch_bounds__(CK_WALK_THREADS)
-ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride) {
+ck_walk_vm_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride) {
     // the schema bytecode and one 64-byte window per thread live in shared memory
     __shared__ u32 s_prog[CK_VM_PROG_WORDS];
     __shared__ u32 s_win[CK_WALK_THREADS * CK_WIN_WORDS];
@@ -84,6 +84,32 @@ ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32
         cx.kfill = 0;
         VmDicts dk;
         status = ck_vm_walk(r, s_prog, o, cx, dk, stop) ? CK_OK : CK_NOT_CANONICAL;
+    }
+    o.set(CK_COL_STATUS, status);
+    o.set(CK_COL_ERR, stop);
+}
+
+// recursive-descent walker (csrc/ck_walk.cuh).  pf: software prefetch of the record towards L2 before the
+// (strictly sequential, latency-bound) walk starts
+__global__ void __launch_bounds__(128, 8)
+ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride, u32 pf) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long a = off[i], b = off[i + 1];
+    WalkOut o; o.base = cols + i; o.stride = stride;
+    u32 len = (u32)(b - a);
+    u32 status, stop = 0;
+    if (len == 0) status = CK_EMPTY;
+    else {
+        if (pf) {
+            const u8* p = in + a;
+            u32 lim = len < pf ? len : pf;
+            for (u32 k = 0; k < lim; k += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + k));
+        }
+        Rd r; r.init(in + a, len);
+        AnyCtx cx;
+        cx.kfill = 0;
+        status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_NOT_CANONICAL;
     }
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);
