@@ -219,6 +219,7 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("CK_NCCL_DEBUG", "WARN")   # no version banner on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.events
@@ -283,6 +284,10 @@ def main() -> None:
         def enqueue_host(self, h_in_np, h_off_np):
             self.eng.submit(h_in_np, h_off_np)          # asynchronous H2D of the batch from pinned memory + decode
             self.eng.tool_plan()
+
+        def exchange_host(self):
+            """N > 1: forward foreign-partition payloads and land what this rank received in pinned memory.
+            Called after the other lane's D2H so that its host-side wait does not stall the copy pipeline."""
             if world > 1:
                 self.exchange()
                 if self.rbytes:
@@ -354,9 +359,11 @@ def main() -> None:
 
     def run_e2e(k_steps):
         lanes[0].enqueue_host(h_in_np, h_off_np)
+        lanes[0].exchange_host()
         for k in range(1, k_steps):
             lanes[k % 2].enqueue_host(h_in_np, h_off_np)
             lanes[(k - 1) % 2].fetch_host()
+            lanes[k % 2].exchange_host()
         lanes[(k_steps - 1) % 2].fetch_host()
 
     run_e2e(3)

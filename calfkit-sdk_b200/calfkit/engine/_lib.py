@@ -12,7 +12,7 @@ import numpy as np
 from calfkit.exceptions import EngineError
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_PKG_ROOT, "libcalfkit_b200.so")
+LIB_PATH = os.environ.get("CK_LIB") or os.path.join(_PKG_ROOT, "libcalfkit_b200.so")   # CK_LIB: kernel A/B builds during development
 
 # ---- constants mirrored from csrc/ck_common.h (checked against the header in tests/test_abi.py) ----
 CK_OK, CK_NOT_CANONICAL, CK_JSON_INVALID, CK_SCHEMA_INVALID, CK_UNSUPPORTED, CK_EMPTY = range(6)

@@ -25,7 +25,7 @@ struct ck_handle {
     // device buffers
     u8* d_in = nullptr; long long* d_in_off = nullptr;
     u8* d_out = nullptr; long long* d_out_off = nullptr;
-    u8* d_aux = nullptr; long long* d_aux_off = nullptr;
+    u8* d_aux = nullptr; long long* d_aux_off = nullptr; u8* d_glue = nullptr;
     u32* d_cols = nullptr; ck_out_desc* d_descs = nullptr; u32* d_pay_len = nullptr; ck_pub* d_pubs = nullptr;
     unsigned long long* d_tile_sum = nullptr; unsigned long long* d_grand = nullptr;
     u8* d_lit = nullptr; ck_tool_cfg* d_tool_cfg = nullptr; ck_agent_cfg* d_agent_cfg = nullptr;
@@ -104,6 +104,7 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     ALLOC(h->d_out_off, sizeof(long long) * ((size_t)h->max_payloads + 1));
     ALLOC(h->d_aux, max_aux_bytes + CK_PAD);
     ALLOC(h->d_aux_off, sizeof(long long) * ((size_t)max_records + 1));
+    ALLOC(h->d_glue, (size_t)CK_GLUE_STRIDE * h->max_payloads + CK_PAD);
     ALLOC(h->d_cols, sizeof(u32) * (size_t)CK_NUM_COLS * max_records);
     ALLOC(h->d_descs, sizeof(ck_out_desc) * (size_t)h->max_payloads);
     ALLOC(h->d_pay_len, sizeof(u32) * (size_t)h->max_payloads);
@@ -130,7 +131,7 @@ extern "C" void ck_destroy(ck_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_cols, h->d_descs, h->d_pay_len,
+    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_cols, h->d_descs, h->d_pay_len,
                     h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_agent_cfg, h->d_counts, h->d_slot_base, h->d_agent_tables, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
                     h->d_tab_len, h->d_tab_id, h->d_tab_names};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -257,7 +258,7 @@ static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
         if (npay) {
             u32 warps_per_block = 256 / 32;
             ck_emit_kernel<<<(npay + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(
-                h->cur_in, h->cur_in_off, h->d_lit, aux, h->d_descs, h->d_out_off, npay, h->d_out, (long long)h->max_out);
+                h->cur_in, h->cur_in_off, h->d_lit, aux, h->d_glue, h->d_descs, h->d_out_off, npay, h->d_out, (long long)h->max_out);
         }
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -271,7 +272,7 @@ extern "C" int ck_tool_args(ck_handle* h) {
     {
         KTimer t(h, CK_K_PLAN);
         if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
-            h->d_tool_cfg, h->d_lit, nullptr, 0, h->d_descs, h->d_pay_len, h->d_pubs);
+            h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 0, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
     h->n_pubs = 0;
@@ -284,7 +285,7 @@ static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_of
     {
         KTimer t(h, CK_K_PLAN);
         if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
-            h->d_tool_cfg, h->d_lit, aux_off, 1, h->d_descs, h->d_pay_len, h->d_pubs);
+            h->d_tool_cfg, h->d_lit, aux_off, aux, h->d_glue, 1, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
     // NOTE: payload sizes are bounded by in + per-record constant; the caller sizes max_out accordingly
@@ -320,7 +321,7 @@ extern "C" int ck_return_plan(ck_handle* h) {
     {
         KTimer t(h, CK_K_PLAN);
         if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
-            h->d_tool_cfg, h->d_lit, nullptr, 2, h->d_descs, h->d_pay_len, h->d_pubs);
+            h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 2, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (scan_emit(h, h->n, nullptr)) return 1;
@@ -404,11 +405,10 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     unsigned long long slots = *h->h_grand;
     if (slots > h->max_payloads) return fail(h, "ck_fanout_plan: more payloads than max_payloads");
-    if (slots * 32 > h->max_aux) return fail(h, "ck_fanout_plan: max_aux_bytes too small for the frame ids (32 B per payload)");
     {
         KTimer t(h, CK_K_FANOUT);
         if (n) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
-            h->d_slot_base, unix_ms, seed, h->d_aux, h->d_descs, h->d_pay_len, h->d_pubs);
+            h->d_slot_base, unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (scan_emit(h, (u32)slots, h->d_aux)) return 1;

@@ -73,7 +73,8 @@ enum {
 // Output-record descriptor written by the plan kernels and consumed by emit/route.
 // An output payload is the concatenation of up to CK_MAX_SEGS segments.
 #define CK_MAX_SEGS 16
-enum { CK_SRC_INPUT = 0, CK_SRC_LIT = 1, CK_SRC_AUX = 2 };   // input record / literal pool / per-batch aux blob
+enum { CK_SRC_INPUT = 0, CK_SRC_LIT = 1, CK_SRC_AUX = 2, CK_SRC_GLUE = 3 };   // input record / literal pool / per-batch aux blob / per-payload glue slot
+#define CK_GLUE_STRIDE 512    // bytes of scratch per payload in which a plan thread assembles the new text of a splice
 typedef struct {
     uint32_t src_off[CK_MAX_SEGS];   // offset inside the source (INPUT: relative to the record start)
     uint32_t len_src[CK_MAX_SEGS];   // (len << 2) | src

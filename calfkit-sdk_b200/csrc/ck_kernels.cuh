@@ -140,22 +140,88 @@ __device__ __forceinline__ Span ck_dict_find(Rd& r, u32 obj, u32 key_off, u32 ke
     return none;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Output layout planner.  A payload is described as <= CK_MAX_SEGS segments such that EVERY segment
+// starts at a 16-byte aligned offset of the output payload and every segment but the last is a
+// multiple of 16 bytes long — so each 16-byte output vector the emit kernel writes comes from exactly
+// one segment (no straddling, no per-segment head/tail handling; the kernel is instruction bound).
+// Pieces arrive in output order.  Long input / aux pieces become DIRECT segments (copied from where
+// they lie); everything short — the literals and ids of the inserted entry, and the <= 15 bytes on
+// either side of a splice point that do not fill a vector — is packed by this thread, 8 aligned bytes
+// per store, into the payload's glue slot and becomes a GLUE segment.
+// ------------------------------------------------------------------------------------------------
+#define CK_DIRECT_MIN 48u
 struct SegWriter {
     ck_out_desc* d;
-    u32 n, total;
-    __device__ __forceinline__ void init(ck_out_desc* dd) { d = dd; n = 0; total = 0; }
-    __device__ __forceinline__ void add(u32 src, u32 off, u32 len) {
-        if (len == 0) return;
-        if (n > 0 && src == (d->len_src[n - 1] & 3u) && d->src_off[n - 1] + (d->len_src[n - 1] >> 2) == off) {
-            d->len_src[n - 1] += len << 2;        // contiguous with the previous segment: merge
-        } else if (n < CK_MAX_SEGS) {
-            d->src_off[n] = off; d->len_src[n] = (len << 2) | src; n++;
-        } else { n = CK_MAX_SEGS + 1; }
+    Rd* r; const u8* lit; const u8* aux; u8* slot;         // byte sources and this payload's glue slot
+    u32 n, total;                                          // segments so far, output offset
+    bool in_glue, overflow;
+    u32 gfill, grun;                                       // bytes of the slot used, start of the open run
+    unsigned long long acc; u32 cnt;
+
+    __device__ __forceinline__ void init(ck_out_desc* dd, Rd* rr, const u8* l, const u8* a, u8* s) {
+        d = dd; r = rr; lit = l; aux = a; slot = s; n = 0; total = 0; in_glue = false; overflow = false; gfill = 0; grun = 0; acc = 0; cnt = 0;
+    }
+    __device__ __forceinline__ void seg(u32 src, u32 off, u32 len) {
+        if (n < CK_MAX_SEGS) { d->src_off[n] = off; d->len_src[n] = (len << 2) | src; n++; } else overflow = true;
+    }
+    // append the low `nb` (1..8) bytes of `chunk` to the open run: 8 aligned bytes per store
+    __device__ __forceinline__ void put8(unsigned long long chunk, u32 nb) {
+        if (gfill + nb > CK_GLUE_STRIDE) { overflow = true; return; }
+        if (nb < 8) chunk &= (~0ull >> (8 * (8 - nb)));
+        acc |= chunk << (8 * cnt);
+        u32 c2 = cnt + nb;
+        gfill += nb;
+        if (c2 >= 8) {
+            *(unsigned long long*)(slot + ((gfill - (c2 - 8)) - 8)) = acc;
+            acc = cnt ? (chunk >> (8 * (8 - cnt))) : 0ull;
+            c2 -= 8;
+        }
+        cnt = c2;
+    }
+    __device__ __forceinline__ void put(u8 b) { put8((unsigned long long)b, 1); }
+    __device__ __forceinline__ static unsigned long long load8_g(const u8* p) {    // unaligned 8 bytes from global memory
+        u32 s = (u32)((uintptr_t)p & 7);
+        const unsigned long long* q = (const unsigned long long*)((uintptr_t)p - s);
+        unsigned long long lo = q[0];
+        if (s == 0) return lo;
+        unsigned long long hi = q[1];
+        return (lo >> (8 * s)) | (hi << (64 - 8 * s));
+    }
+    __device__ __forceinline__ unsigned long long fetch8(u32 src, u32 off) {
+        return src == CK_SRC_INPUT ? r->load8(off) : load8_g((src == CK_SRC_LIT ? lit : aux) + off);
+    }
+    __device__ __forceinline__ void close_run() {          // the open glue run becomes a segment
+        if (cnt) { *(unsigned long long*)(slot + (gfill & ~7u)) = acc; acc = 0; cnt = 0; }
+        seg(CK_SRC_GLUE, grun, gfill - grun);
+        gfill = (gfill + 15u) & ~15u;                      // next run starts 16-aligned inside the slot
+        in_glue = false;
+    }
+    __device__ __forceinline__ void glue_bytes(u32 src, u32 off, u32 len) {
+        if (!in_glue) { in_glue = true; grun = gfill; }
+        for (u32 k = 0; k < len; k += 8) put8(fetch8(src, off + k), len - k < 8 ? len - k : 8);
         total += len;
     }
+    __device__ __forceinline__ void add(u32 src, u32 off, u32 len) {
+        if (len == 0) return;
+        bool direct_ok = (src == CK_SRC_INPUT || src == CK_SRC_AUX) && len >= CK_DIRECT_MIN;
+        if (!direct_ok) { glue_bytes(src, off, len); return; }
+        if (in_glue || (total & 15u)) {                    // bring the output offset to a vector boundary first
+            u32 need = (16u - (total & 15u)) & 15u;
+            glue_bytes(src, off, need);
+            off += need; len -= need;
+            close_run();
+        }
+        u32 body = len & ~15u;
+        seg(src, off, body);
+        total += body;
+        if (len - body) glue_bytes(src, off + body, len - body);   // the ragged end opens the next glue run
+    }
+    __device__ __forceinline__ void hex_uuid7(unsigned long long unix_ms, unsigned long long seed, unsigned long long idx);
     __device__ __forceinline__ bool finish(u32 record) {
+        if (in_glue) close_run();
         d->nseg = n; d->record = record; d->total_len = total;
-        return n <= CK_MAX_SEGS;
+        return !overflow;
     }
 };
 
@@ -171,6 +237,7 @@ __global__ void __launch_bounds__(128)
 ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
                     const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
                     const long long* __restrict__ aux_off,    // per record [n+1] spans of the host results blob, or NULL
+                    const u8* __restrict__ aux, u8* __restrict__ glue,
                     int mode, ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -188,7 +255,7 @@ ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off
     if (status != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; COL(CK_COL_NOUT) = 0; return; }
 
     u32 nframes = COL(CK_COL_NFRAMES), nargs = COL(CK_COL_NARGS), kinds = COL(CK_COL_ARGKINDS);
-    SegWriter w; w.init(d);
+    SegWriter w; w.init(d, &r, lit, aux, glue + (size_t)i * CK_GLUE_STRIDE);
     Span call = {0, 0};
     if (mode == 2) {
         // plain ReturnCall(state) of a node whose run() left the state as it is on the wire
@@ -355,6 +422,15 @@ __device__ __forceinline__ void ck_uuid7_hex(unsigned long long unix_ms, unsigne
     for (int k = 0; k < 16; k++) { out32[k] = hx[(hi >> (60 - 4 * k)) & 15]; out32[16 + k] = hx[(lo >> (60 - 4 * k)) & 15]; }
 }
 
+__device__ __forceinline__ void SegWriter::hex_uuid7(unsigned long long unix_ms, unsigned long long seed, unsigned long long idx) {
+    u8 tmp[32];
+    ck_uuid7_hex(unix_ms, seed, idx, tmp);
+    if (!in_glue) { in_glue = true; grun = gfill; }
+#pragma unroll
+    for (int k = 0; k < 32; k++) put(tmp[k]);
+    total += 32;
+}
+
 // pass 1: how many payloads does each record produce (pending + 1 for the handler return)
 __global__ void __launch_bounds__(128)
 ck_fanout_count_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
@@ -389,7 +465,7 @@ ck_fanout_count_kernel(const u8* __restrict__ in, const long long* __restrict__ 
 __global__ void __launch_bounds__(128)
 ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
                       const ck_agent_cfg* __restrict__ cfgp, const u8* __restrict__ lit, const long long* __restrict__ slot_base,
-                      unsigned long long unix_ms, unsigned long long seed, u8* __restrict__ aux /* 32 B per payload slot */,
+                      unsigned long long unix_ms, unsigned long long seed, const u8* __restrict__ aux, u8* __restrict__ glue,
                       ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -425,10 +501,9 @@ ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ o
             }
             u32 s = slot + j;
             ck_out_desc* d = descs + s;
-            SegWriter w; w.init(d);
+            SegWriter w; w.init(d, &r, lit, aux, glue + (size_t)s * CK_GLUE_STRIDE);
             if (tool == 0xffffffffu) { bad = true; w.finish(i); pay_len[s] = 0; pubs[2 * s] = none; pubs[2 * s + 1] = none; j++; }
             else {
-                ck_uuid7_hex(unix_ms, seed, (unsigned long long)s, aux + (size_t)s * 32);
                 u32 cur = 0;
                 if (ov) { w.add(CK_SRC_INPUT, 0, sov_off); w.add(CK_SRC_INPUT, fov_off, fov_len); cur = sov_off + sov_len; }
                 w.add(CK_SRC_INPUT, cur, list_end - cur);
@@ -436,7 +511,7 @@ ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ o
                 w.add(CK_SRC_LIT, cfg.tool_lit_off[tool], cfg.tool_lit_len[tool]);
                 w.add(CK_SRC_INPUT, k.off, k.len);                       // tool_call_id (raw JSON string content)
                 w.add(CK_SRC_LIT, cfg.lit_mid[0], cfg.lit_mid[1]);
-                w.add(CK_SRC_AUX, s * 32, 32);
+                w.hex_uuid7(unix_ms, seed, (unsigned long long)s);
                 w.add(CK_SRC_LIT, cfg.lit_tail[0], cfg.lit_tail[1]);
                 w.add(CK_SRC_INPUT, list_end, r.n - list_end);
                 w.finish(i);
@@ -452,7 +527,7 @@ ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ o
     if (action == CK_ACT_FANOUT && cfg.publish_topic_id >= 0) {
         // handler return value of the list[Call] branch: the original envelope (nodes/base.py:88)
         u32 s = slot + j;
-        SegWriter w; w.init(descs + s);
+        SegWriter w; w.init(descs + s, &r, lit, aux, glue + (size_t)s * CK_GLUE_STRIDE);
         w.add(CK_SRC_INPUT, 0, r.n); w.finish(i);
         pay_len[s] = r.n;
         ck_pub q = none; q.payload = s; q.topic_id = cfg.publish_topic_id; pubs[2 * s] = q; pubs[2 * s + 1] = none;
@@ -588,34 +663,65 @@ ck_gather_spans_kernel(const u8* __restrict__ src, const long long* __restrict__
     ck_warp_copy(dst + dst_off[warp], src + src_off[warp], (u32)len, lane);
 }
 
+// ------------------------------------------------------------------------------------------------
+// encode: one warp per payload.  Thanks to the aligned layout (SegWriter) the payload is a sequence of
+// 16-byte vectors each of which lies inside one segment: lane l of iteration k produces vector
+// 32k + l = unaligned 16-byte gather from its segment's source + one aligned 16-byte store.  Which
+// segment a vector belongs to is found without a search: the lanes holding the segment table mark the
+// vectors where a segment starts, one warp-wide OR gives the mask and a popcount gives the index.
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ck_emit_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, const u8* __restrict__ lit,
-               const u8* __restrict__ aux, const ck_out_desc* __restrict__ descs, const long long* __restrict__ out_off,
-               u32 n, u8* __restrict__ out, long long out_cap) {
+               const u8* __restrict__ aux, const u8* __restrict__ glue, const ck_out_desc* __restrict__ descs,
+               const long long* __restrict__ out_off, u32 n, u8* __restrict__ out, long long out_cap) {
     u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
     long long o0 = out_off[warp], o1 = out_off[warp + 1];
     if (o1 == o0 || o1 > out_cap) return;    // overflow is reported by ck_fetch_output, never written
     const ck_out_desc* d = descs + warp;
     u32 nseg = d->nseg;
-    if (nseg > CK_MAX_SEGS) return;
-    // lanes 0..nseg-1 fetch one segment descriptor each, then broadcast
-    u32 my_off = lane < nseg ? d->src_off[lane] : 0, my_ls = lane < nseg ? d->len_src[lane] : 0;
+    if (nseg == 0 || nseg > CK_MAX_SEGS) return;
+    u32 total = d->total_len;
     const u8* rec = in + in_off[d->record];
-    u8* dst = out + o0;
-    // pull the whole source record towards L1 with one wave of independent requests, so that the
-    // segment copies below (a dependent load->store chain per segment) hit L1 instead of each exposing
-    // a full HBM latency
-    {
-        u32 rec_len = (u32)(in_off[d->record + 1] - in_off[d->record]);
-        for (u32 o = lane * 128; o < rec_len; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + o));
+    // segment table: lane s holds segment s (source address, start vector, length)
+    u32 my_len = 0;
+    const u8* my_ptr = rec;
+    if (lane < nseg) {
+        u32 so = d->src_off[lane], ls = d->len_src[lane];
+        u32 src = ls & 3u;
+        my_len = ls >> 2;
+        my_ptr = (src == CK_SRC_INPUT) ? rec + so : (src == CK_SRC_LIT ? lit + so : (src == CK_SRC_AUX ? aux + so
+                 : glue + (size_t)warp * CK_GLUE_STRIDE + so));
     }
-    for (u32 s = 0; s < nseg; s++) {
-        u32 so = __shfl_sync(0xffffffffu, my_off, s), ls = __shfl_sync(0xffffffffu, my_ls, s);
-        u32 len = ls >> 2, src = ls & 3u;
-        const u8* sp = (src == CK_SRC_INPUT) ? rec + so : (src == CK_SRC_LIT ? lit + so : aux + so);
-        ck_warp_copy(dst, sp, len, lane);
-        dst += len;
+    u32 start = my_len;                      // exclusive prefix sum of the segment lengths = output offset
+#pragma unroll
+    for (int k = 1; k < CK_MAX_SEGS; k <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, start, k); if (lane >= k) start += y; }
+    start -= my_len;
+    u32 start_vec = start >> 4;
+    unsigned long long pbits = (unsigned long long)(uintptr_t)my_ptr;
+    u32 plo = (u32)pbits, phi = (u32)(pbits >> 32);
+    uint4* dst = (uint4*)(out + o0);
+    u32 nvec = (total + 15u) >> 4;
+    u32 segs_before = 0;
+    for (u32 v0 = 0; v0 < nvec; v0 += 32) {
+        u32 bit = (lane < nseg && my_len && start_vec >= v0 && start_vec < v0 + 32) ? (1u << (start_vec - v0)) : 0u;
+        u32 mask = __reduce_or_sync(0xffffffffu, bit);
+        u32 seg = segs_before + __popc(mask & (0xffffffffu >> (31 - lane))) - 1;
+        segs_before += __popc(mask);
+        u32 s_start = __shfl_sync(0xffffffffu, start, seg & 31);
+        u32 s_lo = __shfl_sync(0xffffffffu, plo, seg & 31), s_hi = __shfl_sync(0xffffffffu, phi, seg & 31);
+        u32 v = v0 + lane;
+        if (v < nvec) {
+            const u8* src = (const u8*)(uintptr_t)(((unsigned long long)s_hi << 32) | s_lo) + ((v << 4) - s_start);
+            u32 sh = (u32)((uintptr_t)src & 3u) * 8u;
+            const u32* a = (const u32*)((uintptr_t)src & ~(uintptr_t)3);
+            // 5 aligned words cover the 16 unaligned bytes (may touch <= 19 bytes past the span: all sources are padded)
+            u32 w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = __ldg(a + 3), w4 = __ldg(a + 4);
+            uint4 o;
+            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+            dst[v] = o;
+        }
     }
 }
 
