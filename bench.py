@@ -219,7 +219,7 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("CK_NCCL_DEBUG", "WARN")   # no version banner on stdout: one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner / logs must not land on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.events
@@ -278,8 +278,6 @@ def main() -> None:
             self.eng.submit_device(d_in, d_off, n)
             self.eng.tool_plan()
             launches[0] += 7            # walk, plan, 3 x scan, emit, route
-            if world > 1:
-                self.exchange()
 
         def enqueue_host(self, h_in_np, h_off_np):
             self.eng.submit(h_in_np, h_off_np)          # asynchronous H2D of the batch from pinned memory + decode
@@ -318,22 +316,41 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    for _ in range(args.warmup):
-        lane.enqueue_device(d_in, d_off)
-    eng.sync()
+    # N == 1: one lane, back-to-back steps.  N > 1: two lanes alternate so that the (latency-bound: host-side
+    # split sizes + three small collectives) cross-partition exchange of step k overlaps the kernels of
+    # step k+1 on the other lane's stream.
+    lanes = [lane, Lane()] if world > 1 else [lane]
+
+    def run_device(k_steps):
+        if world == 1:
+            for _ in range(k_steps):
+                lane.enqueue_device(d_in, d_off)
+            return
+        lanes[0].enqueue_device(d_in, d_off)
+        for k in range(1, k_steps):
+            lanes[k % 2].enqueue_device(d_in, d_off)
+            lanes[(k - 1) % 2].exchange()
+        lanes[(k_steps - 1) % 2].exchange()
+
+    run_device(args.warmup)
+    torch.cuda.synchronize()
     eng.profile(True)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev_end = [torch.cuda.Event(enable_timing=True) for _ in lanes]
     launches[0] = 0
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(args.steps):
-            lane.enqueue_device(d_in, d_off)
-        ev1.record(stream)
+    for ln_ in lanes[1:]:
+        ln_.stream.wait_stream(lanes[0].stream)
+    ev0.record(lanes[0].stream)
+    for ln_ in lanes[1:]:
+        ln_.stream.wait_event(ev0)                       # no lane starts before the start event
+    run_device(args.steps)
+    for e_, ln_ in zip(ev_end, lanes):
+        e_.record(ln_.stream)
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = max(ev0.elapsed_time(e_) for e_ in ev_end)
     sampler.stop_flag = True
     prof = eng.profile_read()
     eng.profile(False)
@@ -353,7 +370,8 @@ def main() -> None:
     # step k: lane k%2 takes the batch from pinned host memory (H2D + all kernels, asynchronous) while the
     # previous step's results are copied back from the other lane (D2H + wait): the two PCIe directions
     # and the kernels overlap, exactly as a worker consuming a stream of batches would run it.
-    lanes = [lane, Lane()]
+    if len(lanes) < 2:
+        lanes = [lane, Lane()]
     h_in_np, h_off_np = h_in.numpy(), h_off.numpy()
     e2e_steps = max(4, min(args.steps, 8))
 
@@ -415,7 +433,7 @@ def main() -> None:
         if cnt and k in algo:
             kern[k] = {"ms_per_launch": ms / cnt, "launches": cnt, "algo_bytes": algo[k],
                        "gbs": algo[k] / (ms / cnt) / 1e6 if k != "scan" else None}
-    kern_step_ms = sum(v[0] for v in prof.values()) / args.steps
+    kern_step_ms = sum(v[0] / v[1] for v in prof.values() if v[1])        # one launch of each per step
     dom = max((k for k in kern if k != "scan"), key=lambda k: kern[k]["ms_per_launch"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -14,7 +14,8 @@ def build(force: bool = False) -> str:
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_walk.cuh"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_common.h"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm.cuh"),
-            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm_prog.h")]
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm_prog.h"),
+            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_canon.cuh")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-o", _LIB, srcs[0]])
@@ -33,6 +34,8 @@ def lib():
         _lib.ck_host_num_cols.restype = ctypes.c_int
         _lib.ck_host_vm_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_vm_walk.restype = ctypes.c_int
+        _lib.ck_host_canon.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+        _lib.ck_host_canon.restype = ctypes.c_int
     return _lib
 
 
@@ -50,3 +53,13 @@ def vm_walk(payload: bytes):
     cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
     ok = L.ck_host_vm_walk(payload, len(payload), cols.ctypes.data)
     return bool(ok), cols
+
+
+def canon(payload: bytes):
+    """the device canonicaliser (csrc/ck_canon.cuh): -> (status, canonical bytes or b"")"""
+    L = lib()
+    cap = 4 * len(payload) + 8192
+    out = np.zeros(cap, dtype=np.uint8)
+    n = ctypes.c_uint32(0)
+    st = L.ck_host_canon(payload, len(payload), out.ctypes.data, cap, ctypes.byref(n))
+    return st, out[:n.value].tobytes()

@@ -1,0 +1,104 @@
+"""CPU fuzz of the device canonicaliser source (csrc/ck_canon.cuh, g++ build): its verdicts against the
+reference codec (pydantic on the mirrored models, themselves pinned to the reference by the goldens).
+  CK_OK (0)             -> bytes identical to dump(validate(input)), and the fast walker accepts them
+  CK_JSON_INVALID (2)   -> pydantic raises exactly one json_invalid error
+  CK_SCHEMA_INVALID (3) -> pydantic raises, and not for JSON syntax
+  CK_UNSUPPORTED (4)    -> no claim (counted, must stay a minority on realistic inputs)"""
+import json
+import random
+
+from conftest import as_bytes, golden
+from hostsim import canon, walk
+from pydantic import ValidationError
+
+
+def _truth(b: bytes):
+    from calfkit import _ids
+    from calfkit.models import Envelope
+    _ids.set_id_source(lambda: "0" * 31 + "1")
+    try:
+        return 0, Envelope.model_validate_json(b).model_dump_json().encode()
+    except ValidationError as e:
+        errs = e.errors()
+        return (2 if errs[0]["type"] == "json_invalid" and len(errs) == 1 else 3), b""
+    finally:
+        _ids.set_id_source(None)
+
+
+def _check(b: bytes, stats: dict):
+    st, out = canon(b)
+    stats[st] = stats.get(st, 0) + 1
+    if st == 4:
+        return
+    tst, tout = _truth(b)
+    assert st == tst, (st, tst, b[:400])
+    if st == 0:
+        assert out == tout, (b[:400], out[:200], tout[:200])
+        assert walk(out)[0], out[:400]          # whatever the canonicaliser emits, the fast path must accept
+
+
+def test_goldens():
+    stats: dict = {}
+    for c in golden("codec.json") + golden("tool_node.json"):
+        _check(as_bytes(c["input"]), stats)
+    assert stats[0] > 100 and stats.get(4, 0) < 15
+
+
+def test_reformatted_records_are_recovered():
+    """pretty-printed, key-sorted and ASCII-escaped spellings of valid records canonicalise to the
+    reference bytes (none of them is UNSUPPORTED)"""
+    from calfkit import synth
+    recs = synth.tool_events(20, seed=31) + synth.tool_events(10, seed=32, size=None, full_history=True) + \
+        synth.fanout_events(2, seed=33, fanout=5) + synth.mixed_events(10, seed=34, hi=8000)
+    for r in recs:
+        obj = json.loads(r)
+        for variant in (json.dumps(obj, indent=2), json.dumps(obj, sort_keys=True),
+                        json.dumps(obj, ensure_ascii=True, separators=(" , ", " : "))):
+            st, out = canon(variant.encode())
+            assert st == 0 and out == r
+
+
+def test_mutation_fuzz():
+    from calfkit import synth
+    rng = random.Random(3)
+    seeds = [as_bytes(c["input"]) for c in golden("codec.json") + golden("tool_node.json") if 0 < len(as_bytes(c["input"])) < 5000]
+    seeds += synth.tool_events(6, seed=9) + synth.tool_events(4, seed=8, size=None, full_history=True)
+    for s in list(seeds):
+        try:
+            obj = json.loads(s)
+        except Exception:
+            continue
+        seeds.append(json.dumps(obj, indent=1).encode())
+        seeds.append(json.dumps(obj, sort_keys=True, ensure_ascii=True, separators=(", ", " : ")).encode())
+    tok = [b'"', b"{", b"}", b"[", b"]", b",", b":", b"\\", b" ", b"\n", b"0", b"1", b"9", b"e", b"E", b".", b"-", b"+", b"null", b"true",
+           b"false", b"1.5", b"1e5", b"-0", b"0.10", b'"a"', b"{}", b"[]", b"\\u0041", b"\\/", b"\xc3\xa9", b"\xff", b"\x01", b"\t",
+           b'"kind":"tool-return",', b'"a":1,', b"NaN", b"Infinity", b"Z", b"+00:00", b".000000", b".5", b"00", b'"zz":[1,{"q":2}],',
+           b'"part_kind":"text",', b'"kind":"request",', b"\\ud83d\\ude00", b"\\ud800", b"2.50", b"1E-7", b"12e3"]
+    stats: dict = {}
+    for _ in range(60000):
+        b = bytearray(rng.choice(seeds))
+        for _ in range(rng.choice([1, 1, 1, 2, 3])):
+            if not b:
+                break
+            op, i = rng.randrange(7), rng.randrange(len(b))
+            if op == 0:
+                b[i] = rng.randrange(256)
+            elif op == 1:
+                del b[i]
+            elif op == 2:
+                b[i:i] = rng.choice(tok)
+            elif op == 3:
+                j = min(len(b), i + rng.randrange(1, 40)); b[i:i] = b[i:j]
+            elif op == 4:
+                j = min(len(b), i + rng.randrange(1, 40)); del b[i:j]
+            elif op == 5:
+                k = bytes(b).find(b"null", i)
+                if k >= 0:
+                    b[k:k + 4] = rng.choice(tok)
+            else:
+                k = bytes(b).find(b'"', i)
+                if k >= 0:
+                    b[k + 1:k + 1] = rng.choice(tok)
+        if b:
+            _check(bytes(b), stats)
+    assert stats.get(0, 0) > 3000 and stats.get(3, 0) > 1000 and stats.get(2, 0) > 10000
