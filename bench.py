@@ -205,6 +205,9 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # stdout carries exactly ONE JSON line: anything a library prints to fd 1 (NCCL's version banner ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -487,7 +490,8 @@ def main() -> None:
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes (oracle/port.py)"},
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     shutdown()
 
 

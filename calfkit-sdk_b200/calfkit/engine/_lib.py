@@ -30,7 +30,7 @@ COLS = ["STATUS", "ACTION", "ERR", "CORR_OFF", "CORR_LEN", "NFRAMES", "FRAMES_OF
 COL = {name: i for i, name in enumerate(COLS)}
 NUM_COLS = len(COLS)
 
-KERNELS = ["walk", "plan", "scan", "emit", "route", "fanout"]
+KERNELS = ["walk", "plan", "scan", "emit", "route", "fanout", "canon"]
 NUM_KERNELS = len(KERNELS)
 
 PUB_DTYPE = np.dtype([("payload", "<u4"), ("topic_id", "<i4"), ("topic_off", "<u4"), ("topic_len", "<u4"),
@@ -38,7 +38,7 @@ PUB_DTYPE = np.dtype([("payload", "<u4"), ("topic_id", "<i4"), ("topic_off", "<u
 
 EXPORTS = ["ck_create", "ck_destroy", "ck_last_error", "ck_version", "ck_register_topics", "ck_set_tool_node", "ck_submit",
            "ck_submit_device", "ck_tool_args", "ck_tool_plan", "ck_tool_plan_device", "ck_return_plan", "ck_set_agent_node", "ck_set_agent_tool_topic_ids", "ck_fanout_plan",
-           "ck_sync", "ck_out_size", "ck_fetch_columns", "ck_fetch_output", "ck_fetch_topic_hist", "ck_stream",
+           "ck_sync", "ck_out_size", "ck_fetch_columns", "ck_fetch_output", "ck_fetch_overlay", "ck_fetch_topic_hist", "ck_stream",
            "ck_device_buffers", "ck_device_buffers2", "ck_gather_spans", "ck_profile", "ck_profile_read"]
 
 _lib = None
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
         "ck_out_size": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "ck_fetch_columns": (C.c_int, [vp, u32p]),
         "ck_fetch_output": (C.c_int, [vp, u8p, C.c_uint64, i64p, u32p, vp]),
+        "ck_fetch_overlay": (C.c_int, [vp, u8p, C.c_uint64, i64p, u32p, C.POINTER(C.c_uint64)]),
         "ck_fetch_topic_hist": (C.c_int, [vp, u32p, C.c_uint32]),
         "ck_stream": (vp, [vp]),
         "ck_device_buffers": (C.c_int, [vp] + [C.POINTER(vp)] * 5),

@@ -61,9 +61,17 @@ class BatchOutput:
     """Result of one plan+emit: unique payloads + the publish table that references them."""
 
     def __init__(self, engine: "BatchEngine", out: np.ndarray, out_off: np.ndarray, out_len: np.ndarray, pubs: np.ndarray,
-                 in_data: np.ndarray | None, in_off: np.ndarray | None, cols: np.ndarray | None):
+                 in_data: np.ndarray | None, in_off: np.ndarray | None, cols: np.ndarray | None, overlay=None):
         self.engine, self.out, self.out_off, self.out_len, self.pubs = engine, out, out_off, out_len, pubs
         self.in_data, self.in_off, self.cols = in_data, in_off, cols
+        self.overlay = overlay          # (bytes, off[n], len[n]): canonical re-emissions of non-canonical inputs
+
+    def record_bytes(self, r: int) -> np.ndarray:
+        """the bytes the column spans of record r refer to: its canonical re-emission if it has one"""
+        if self.overlay is not None and self.overlay[1][r] >= 0:
+            o = int(self.overlay[1][r])
+            return self.overlay[0][o:o + int(self.overlay[2][r])]
+        return self.in_data[self.in_off[r]:self.in_off[r + 1]]
 
     def payload(self, i: int) -> bytes:
         return self.out[self.out_off[i]:self.out_off[i] + self.out_len[i]].tobytes()
@@ -74,16 +82,16 @@ class BatchOutput:
     def topic_of(self, p) -> str:
         if p["topic_id"] >= 0:
             return self.engine.topic_names[int(p["topic_id"])]
-        base = int(self.in_off[p["record"]]) + int(p["topic_off"])
-        raw = self.in_data[base:base + int(p["topic_len"])].tobytes()
+        rec = self.record_bytes(int(p["record"]))
+        raw = rec[int(p["topic_off"]):int(p["topic_off"]) + int(p["topic_len"])].tobytes()
         return json.loads(b'"' + raw + b'"')
 
     def key_of(self, p) -> bytes | None:
         if not p["has_key"]:
             return None
         r = int(p["record"])
-        base = int(self.in_off[r]) + int(self.cols[COL["CORR_OFF"], r])
-        raw = self.in_data[base:base + int(self.cols[COL["CORR_LEN"], r])].tobytes()
+        o = int(self.cols[COL["CORR_OFF"], r])
+        raw = self.record_bytes(r)[o:o + int(self.cols[COL["CORR_LEN"], r])].tobytes()
         return json.loads(b'"' + raw + b'"').encode()
 
     def publishes(self) -> Iterator[Publish]:
@@ -262,7 +270,20 @@ class BatchEngine:
     def fetch(self, out_buf: np.ndarray | None = None, with_columns: bool = True) -> BatchOutput:
         out, off, ln, pubs = self._fetch(out_buf=out_buf)
         cols = self.columns() if with_columns else None
-        return BatchOutput(self, out, off, ln, pubs, self._in_data, self._in_off, cols)
+        return BatchOutput(self, out, off, ln, pubs, self._in_data, self._in_off, cols, self.overlay())
+
+    def overlay(self):
+        """(bytes, off[n], len[n]) of the canonicalised records of the current batch, or None if there are none"""
+        if not self.n:
+            return None
+        off = np.empty(self.n, dtype=np.int64)
+        ln = np.empty(self.n, dtype=np.uint32)
+        buf = np.empty(self.max_in + 256, dtype=np.uint8)
+        used = C.c_uint64(0)
+        self._check(self.lib.ck_fetch_overlay(self.h, ptr(buf), buf.nbytes, ptr(off), ptr(ln), C.byref(used)))
+        if not (off >= 0).any():
+            return None
+        return buf[:used.value], off, ln
 
     # ------------------------------------------------------------------------------------------
     def stream_ptr(self) -> int:

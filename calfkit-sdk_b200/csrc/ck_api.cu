@@ -26,6 +26,8 @@ struct ck_handle {
     u8* d_in = nullptr; long long* d_in_off = nullptr;
     u8* d_out = nullptr; long long* d_out_off = nullptr;
     u8* d_aux = nullptr; long long* d_aux_off = nullptr; u8* d_glue = nullptr;
+    u8* d_ovl = nullptr; long long* d_ovl_off = nullptr; u32* d_ovl_len = nullptr; u32* d_clen = nullptr; long long* d_coff = nullptr;
+    uint64_t max_ovl = 0;
     u32* d_cols = nullptr; ck_out_desc* d_descs = nullptr; u32* d_pay_len = nullptr; ck_pub* d_pubs = nullptr;
     unsigned long long* d_tile_sum = nullptr; unsigned long long* d_grand = nullptr;
     u8* d_lit = nullptr; ck_tool_cfg* d_tool_cfg = nullptr; ck_agent_cfg* d_agent_cfg = nullptr;
@@ -95,6 +97,10 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     if (prop.major != 10) { g_create_error = "ck_create: this library is built for sm_100a (B200) only"; ck_destroy(h); return 1; }
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    {   // the canonicaliser is (boundedly) recursive: give device threads room for its frames
+        size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+        if (cur < 12 * 1024 && (e = cudaDeviceSetLimit(cudaLimitStackSize, 12 * 1024)) != cudaSuccess) return bail("cudaDeviceSetLimit(stack)", e);
+    }
     h->max_in = max_in_bytes; h->max_out = max_out_bytes; h->max_aux = max_aux_bytes; h->max_records = max_records;
     h->max_payloads = max_payloads > max_records ? max_payloads : max_records; h->max_pubs = 2 * h->max_payloads;
 #define ALLOC(p, bytes) if ((e = cudaMalloc((void**)&(p), (bytes))) != cudaSuccess) return bail("cudaMalloc " #p, e)
@@ -105,6 +111,12 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     ALLOC(h->d_aux, max_aux_bytes + CK_PAD);
     ALLOC(h->d_aux_off, sizeof(long long) * ((size_t)max_records + 1));
     ALLOC(h->d_glue, (size_t)CK_GLUE_STRIDE * h->max_payloads + CK_PAD);
+    h->max_ovl = max_in_bytes;
+    ALLOC(h->d_ovl, h->max_ovl + CK_PAD);
+    ALLOC(h->d_ovl_off, sizeof(long long) * ((size_t)max_records + 1));
+    ALLOC(h->d_ovl_len, sizeof(u32) * (size_t)max_records);
+    ALLOC(h->d_clen, sizeof(u32) * (size_t)max_records);
+    ALLOC(h->d_coff, sizeof(long long) * ((size_t)max_records + 1));
     ALLOC(h->d_cols, sizeof(u32) * (size_t)CK_NUM_COLS * max_records);
     ALLOC(h->d_descs, sizeof(ck_out_desc) * (size_t)h->max_payloads);
     ALLOC(h->d_pay_len, sizeof(u32) * (size_t)h->max_payloads);
@@ -131,7 +143,7 @@ extern "C" void ck_destroy(ck_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_cols, h->d_descs, h->d_pay_len,
+    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_ovl, h->d_ovl_off, h->d_ovl_len, h->d_clen, h->d_coff, h->d_cols, h->d_descs, h->d_pay_len,
                     h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_agent_cfg, h->d_counts, h->d_slot_base, h->d_agent_tables, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
                     h->d_tab_len, h->d_tab_id, h->d_tab_names};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -206,16 +218,42 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
     return 0;
 }
 
-static int launch_walk(ck_handle* h) {
-    KTimer t(h, CK_K_WALK);
-    static int mode = -1, pf = 0;
-    if (mode < 0) {   // development switch for A/B measurements of the two walker implementations
-        const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "vm")) ? 1 : 0;
-        const char* q = getenv("CK_PREFETCH"); pf = q ? atoi(q) : 2048;
+static ck_view view_of(ck_handle* h) {
+    ck_view v; v.in = h->cur_in; v.off = h->cur_in_off; v.ovl = h->d_ovl; v.ovl_off = h->d_ovl_off; v.ovl_len = h->d_ovl_len;
+    return v;
+}
+
+static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad);
+
+// decode = walk every submitted record; re-emit the ones that are valid but not canonical into the overlay
+// (count -> scan -> write) and walk those again in their canonical spelling
+static int launch_decode(ck_handle* h) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "vm")) ? 1 : 0; }   // development A/B switch
+    u32 n = h->n;
+    if (!n) return 0;
+    ck_view v = view_of(h);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_ovl_off, 0xff, sizeof(long long) * (size_t)n, h->stream));      // no overlays yet
+    {
+        KTimer t(h, CK_K_WALK);
+        if (mode == 1) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        else ck_walk_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        CUDA_TRY(h, cudaGetLastError());
     }
-    if (h->n && mode == 1) ck_walk_vm_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n);
-    else if (h->n) ck_walk_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n, (u32)pf);
-    CUDA_TRY(h, cudaGetLastError());
+    {
+        KTimer t(h, CK_K_CANON);
+        ck_canon_count_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_clen, n, h->d_coff, 0)) return 1;
+    {
+        KTimer t(h, CK_K_CANON);
+        ck_canon_write_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen, h->d_coff, h->d_ovl, (long long)h->max_ovl,
+                                                                 h->d_ovl_off, h->d_ovl_len);
+        if (mode == 1) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        else ck_walk_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        CUDA_TRY(h, cudaGetLastError());
+    }
     return 0;
 }
 
@@ -229,14 +267,14 @@ extern "C" int ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* ho
     CUDA_TRY(h, cudaMemcpyAsync(h->d_in_off, host_off, sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->d_in + nbytes, 0, 16, h->stream));
     h->cur_in = h->d_in; h->cur_in_off = h->d_in_off; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
-    return launch_walk(h);
+    return launch_decode(h);
 }
 
 extern "C" int ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n) {
     cudaSetDevice(h->device);
     if (n > h->max_records) return fail(h, "ck_submit_device: batch has more records than max_records");
     h->cur_in = dev_in; h->cur_in_off = (const long long*)dev_off; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
-    return launch_walk(h);
+    return launch_decode(h);
 }
 
 static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad) {
@@ -258,7 +296,7 @@ static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
         if (npay) {
             u32 warps_per_block = 256 / 32;
             ck_emit_kernel<<<(npay + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(
-                h->cur_in, h->cur_in_off, h->d_lit, aux, h->d_glue, h->d_descs, h->d_out_off, npay, h->d_out, (long long)h->max_out);
+                view_of(h), h->d_lit, aux, h->d_glue, h->d_descs, h->d_out_off, npay, h->d_out, (long long)h->max_out);
         }
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -271,7 +309,7 @@ extern "C" int ck_tool_args(ck_handle* h) {
     if (!h->tool_set) return fail(h, "ck_tool_args: call ck_set_tool_node first");
     {
         KTimer t(h, CK_K_PLAN);
-        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
+        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
             h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 0, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -284,7 +322,7 @@ static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_of
     if (h->h_tool_cfg.tpl_nparts == 0 && aux_off == nullptr) return fail(h, "ck_tool_plan: node has no device template, host results required");
     {
         KTimer t(h, CK_K_PLAN);
-        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
+        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
             h->d_tool_cfg, h->d_lit, aux_off, aux, h->d_glue, 1, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -293,7 +331,7 @@ static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_of
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * h->n;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->d_cols, h->n, h->d_pubs, npubs,
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -320,7 +358,7 @@ extern "C" int ck_return_plan(ck_handle* h) {
     if (!h->tool_set) return fail(h, "ck_return_plan: call ck_set_tool_node (publish topic) first");
     {
         KTimer t(h, CK_K_PLAN);
-        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->n, h->d_cols, h->n,
+        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
             h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 2, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -328,7 +366,7 @@ extern "C" int ck_return_plan(ck_handle* h) {
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * h->n;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->d_cols, h->n, h->d_pubs, npubs,
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -396,7 +434,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     u32 n = h->n;
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, n, h->d_cols, n, h->d_agent_cfg, max_fanout, h->d_counts);
+        if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, max_fanout, h->d_counts);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (run_scan(h, h->d_counts, n, h->d_slot_base, 0)) return 1;
@@ -407,7 +445,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     if (slots > h->max_payloads) return fail(h, "ck_fanout_plan: more payloads than max_payloads");
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cur_in, h->cur_in_off, n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
+        if (n) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
             h->d_slot_base, unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -415,7 +453,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * (u32)slots;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(h->cur_in, h->cur_in_off, h->d_cols, n, h->d_pubs, npubs,
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -471,6 +509,22 @@ extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, in
     if (host_out_len && h->n_payloads) CUDA_TRY(h, cudaMemcpyAsync(host_out_len, h->d_pay_len, sizeof(u32) * (size_t)h->n_payloads, cudaMemcpyDeviceToHost, h->stream));
     if (host_pubs && h->n_pubs) CUDA_TRY(h, cudaMemcpyAsync(host_pubs, h->d_pubs, sizeof(ck_pub) * (size_t)h->n_pubs, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int ck_fetch_overlay(ck_handle* h, uint8_t* host_ovl, uint64_t cap, int64_t* host_off, uint32_t* host_len, uint64_t* used) {
+    cudaSetDevice(h->device);
+    if (!h->n) { if (used) *used = 0; return 0; }
+    long long total = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&total, h->d_coff + h->n, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(host_off, h->d_ovl_off, sizeof(long long) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(host_len, h->d_ovl_len, sizeof(u32) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if ((uint64_t)total > h->max_ovl) total = (long long)h->max_ovl;
+    if ((uint64_t)total > cap) return fail(h, "ck_fetch_overlay: host buffer too small");
+    if (total) CUDA_TRY(h, cudaMemcpyAsync(host_ovl, h->d_ovl, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (used) *used = (uint64_t)total;
     return 0;
 }
 

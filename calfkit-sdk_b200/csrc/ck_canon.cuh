@@ -25,7 +25,7 @@
 #else
 #define CK_HDR
 #endif
-#define CJ_MAX_DEPTH 200                 // jiter's recursion limit (probe: 200 nested containers parse, 201 do not)
+#define CJ_MAX_DEPTH 200                 // jiter: a value enclosed by more than 200 containers is rejected (probes in DESIGN.md)
 
 struct CIn { const u8* p; u32 n; };
 struct COut {
@@ -126,17 +126,17 @@ CK_HD u32 cj_scalar_end(const CIn& in, u32 pos) {
 }
 
 CK_HD bool cj_validate(const CIn& in) {
-    u32 kind[(CJ_MAX_DEPTH + 31) / 32];
-    u32 depth = 0;
+    u32 kind[(CJ_MAX_DEPTH + 2 + 31) / 32];
+    u32 depth = 0;                                  // number of containers enclosing the value at pos
     u32 pos = cj_skip_ws(in, 0);
     if (pos >= in.n) return false;
     for (;;) {
         // ---- a value starts at pos
         if (pos >= in.n) return false;
+        if (depth > CJ_MAX_DEPTH) return false;
         u8 c = in.p[pos];
         bool opened = false;
         if (c == '{' || c == '[') {
-            if (depth >= CJ_MAX_DEPTH) return false;
             if (c == '{') kind[depth >> 5] |= 1u << (depth & 31); else kind[depth >> 5] &= ~(1u << (depth & 31));
             depth++;
             pos = cj_skip_ws(in, pos + 1);
@@ -325,10 +325,18 @@ CK_HD int cj_emit_number(const CIn& in, u32 a, u32 b, COut& o, bool as_float) {
     return CE_OK;
 }
 
+#define CJ_HS 256
+struct CJ {                                   // one canonicalisation in flight
+    CIn in; COut o;
+    u32 depth;
+    u32 hs[CJ_HS]; u32 hsp;                   // key hashes of the dict scopes being checked for duplicates (LIFO)
+};
+
 // generic value ("Any"): whitespace stripped, strings / numbers canonical, NaN / +-Infinity -> null.
 // Objects with duplicate keys (decoded) are UNSUPPORTED (the reference keeps the first position with the
 // last value).
-CK_HDR int cj_emit_any(const CIn& in, u32 pos, COut& o) {
+CK_HDR int cj_emit_any(CJ& cj, u32 pos) {
+    const CIn& in = cj.in; COut& o = cj.o;
     // iterative: the text is valid JSON, so emitting tokens in order minus whitespace reproduces the structure
     u32 end = cj_skip_value(in, pos);
     // duplicate-key check per object: O(k^2) on hashes of decoded keys, objects visited with a small stack
@@ -341,12 +349,12 @@ CK_HDR int cj_emit_any(const CIn& in, u32 pos, COut& o) {
             if (c == '{') {
                 // collect this object's keys
                 u32 q = cj_skip_ws(in, p + 1);
-                u32 hs[64]; u32 nh = 0;
+                u32 base = cj.hsp, nh = 0;
                 while (in.p[q] != '}') {
                     u32 h = cj_str_hash(in, q);
-                    for (u32 k = 0; k < nh; k++) if (hs[k] == h) return CE_UNSUP;
-                    if (nh >= 64) return CE_UNSUP;
-                    hs[nh++] = h;
+                    for (u32 k = 0; k < nh; k++) if (cj.hs[base + k] == h) return CE_UNSUP;
+                    if (base + nh >= CJ_HS) return CE_UNSUP;
+                    cj.hs[base + nh++] = h;
                     q = cj_skip_value(in, q);                 // key
                     q = cj_skip_ws(in, q); q++;                // ':'
                     q = cj_skip_ws(in, q);
@@ -528,11 +536,6 @@ CJ_TABLE CConst cj_enum_finish[] = {{"stop", 4}, {"length", 6}, {"content_filter
 
 #define CJ_MAXF 13
 
-struct CJ {                                   // one canonicalisation in flight
-    CIn in; COut o;
-    u32 depth;
-};
-
 CK_HDR int cj_emit_model(CJ& c, u32 pos, u32 model);
 
 CK_HD void cj_emit_const(COut& o, u32 k) { o.put('"'); o.puts(cj_consts[k].s, cj_consts[k].len); o.put('"'); }
@@ -572,9 +575,9 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
     switch (type) {
     case T_STRN: if (is_null) { CPUTS(o, "null"); return CE_OK; } /* fall through */
     case T_STR: if (ch != '"') return CE_SCHEMA; cj_emit_string(in, pos, o); return CE_OK;
-    case T_ANY: return cj_emit_any(in, pos, o);
+    case T_ANY: return cj_emit_any(c, pos);
     case T_OBJN: if (is_null) { CPUTS(o, "null"); return CE_OK; } /* fall through */
-    case T_OBJ: if (ch != '{') return CE_SCHEMA; return cj_emit_any(in, pos, o);
+    case T_OBJ: if (ch != '{') return CE_SCHEMA; return cj_emit_any(c, pos);
     case T_INT: {
         if (ch == '"' || ch == 't' || ch == 'f') return CE_UNSUP;              // lax coercions of str / bool
         if (!(ch == '-' || cj_isdigit(ch))) return CE_SCHEMA;
@@ -617,12 +620,12 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
     case T_ARGS: {                                  // Sequence[Any] | None
         if (is_null) { CPUTS(o, "null"); return CE_OK; }
         if (ch != '[') return CE_SCHEMA;
-        return cj_emit_any(in, pos, o);
+        return cj_emit_any(c, pos);
     }
     case T_ARGSUNION:                               // str | dict[str, Any] | None
         if (is_null) { CPUTS(o, "null"); return CE_OK; }
         if (ch == '"') { cj_emit_string(in, pos, o); return CE_OK; }
-        if (ch == '{') return cj_emit_any(in, pos, o);
+        if (ch == '{') return cj_emit_any(c, pos);
         return CE_SCHEMA;
     case T_STR_OR_LISTSTR:
         if (ch == '"') { cj_emit_string(in, pos, o); return CE_OK; }
@@ -639,13 +642,14 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
         if (ch != '{') return CE_SCHEMA;
         o.put('{');
         u32 q = cj_skip_ws(in, pos + 1);
-        u32 hs[CK_DICT_KEYS]; u32 nh = 0;
+        u32 base = c.hsp, nh = 0;
         bool first = true;
         while (in.p[q] != '}') {
             u32 h = cj_str_hash(in, q);
-            for (u32 k = 0; k < nh; k++) if (hs[k] == h) return CE_UNSUP;       // duplicate keys: first position, last value
-            if (nh >= CK_DICT_KEYS) return CE_UNSUP;
-            hs[nh++] = h;
+            for (u32 k = 0; k < nh; k++) if (c.hs[base + k] == h) return CE_UNSUP;   // duplicate keys: first position, last value
+            if (base + nh >= CJ_HS) return CE_UNSUP;
+            c.hs[base + nh++] = h;
+            c.hsp = base + nh;                                                    // nested scopes stack above this one
             if (!first) o.put(',');
             first = false;
             cj_emit_string(in, q, o);
@@ -670,16 +674,19 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
                     if (m >= 0) {
                         u32 save = o.len, sd = c.depth;
                         rc = cj_emit_model(c, q, (u32)m);
-                        if (rc == CE_SCHEMA) { o.len = save; c.depth = sd; rc = -1; }   // not a valid instance: it is just data
+                        // tagged but not a valid instance: the reference keeps it as plain data (smart union).  That text
+                        // is not a fixed point the fast path can recognise, so it is left undecided here.
+                        if (rc == CE_SCHEMA) { (void)save; (void)sd; return CE_UNSUP; }
                     }
                 }
-                if (rc < 0) rc = cj_emit_any(in, q, o);
+                if (rc < 0) rc = cj_emit_any(c, q);
             }
             if (rc) return rc;
             q = cj_skip_value(in, q); q = cj_skip_ws(in, q);
             if (in.p[q] == ',') q = cj_skip_ws(in, q + 1);
         }
         o.put('}');
+        c.hsp = base;
         return CE_OK;
     }
     }
@@ -746,7 +753,12 @@ CK_HDR int cj_emit_model(CJ& c, u32 pos, u32 model) {
         const CField& f = cj_fields[M.first + k];
         if (k) o.put(',');
         o.put('"'); o.puts(f.name, f.nlen); o.put('"'); o.put(':');
-        if (fpos[k]) { int rc = cj_emit_value(c, fpos[k], f.type, f.arg); if (rc) return rc; continue; }
+        if (fpos[k]) {
+            // DataPart.schema_ given through its alias survives one dump but not the next (the emitted key
+            // `schema_` is ignored on validation): such a record has no stable canonical form
+            if (f.no_primary && in.p[fpos[k]] != 'n') return CE_UNSUP;
+            int rc = cj_emit_value(c, fpos[k], f.type, f.arg); if (rc) return rc; continue;
+        }
         switch (f.dflt) {
         case D_REQ: return CE_SCHEMA;                                           // missing
         case D_NULL: CPUTS(o, "null"); break;
@@ -769,15 +781,15 @@ CK_HDR int cj_emit_model(CJ& c, u32 pos, u32 model) {
 
 // entry point: -> CK_OK / CK_JSON_INVALID / CK_SCHEMA_INVALID / CK_UNSUPPORTED; out_len = canonical length
 CK_HD_NOINLINE u32 ck_canonicalise(const u8* rec, u32 len, u8* out, u32 cap, u32& out_len) {
-    CJ c; c.in.p = rec; c.in.n = len; c.o.p = out; c.o.cap = cap; c.o.len = 0; c.o.ovf = false; c.depth = 0;
+    CJ c; c.in.p = rec; c.in.n = len; c.o.p = out; c.o.cap = cap; c.o.len = 0; c.o.ovf = false; c.depth = 0; c.hsp = 0;
     out_len = 0;
     if (!cj_validate(c.in)) return CK_JSON_INVALID;
     u32 pos = cj_skip_ws(c.in, 0);
     if (c.in.p[pos] != '{') return CK_SCHEMA_INVALID;                           // model_type
     int rc = cj_emit_model(c, pos, M_ENVELOPE);
     if (rc == CE_SCHEMA) return CK_SCHEMA_INVALID;
-    if (rc == CE_UNSUP || c.o.ovf) return CK_UNSUPPORTED;
     out_len = c.o.len;
+    if (rc == CE_UNSUP || (cap != 0 && c.o.ovf)) return CK_UNSUPPORTED;      // cap == 0: counting run, nothing is stored
     return CK_OK;
 }
 

@@ -13,6 +13,24 @@
 #include <cuda_runtime.h>
 #include "ck_walk.cuh"
 #include "ck_vm.cuh"
+#include "ck_canon.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// A batch as the kernels see it: the submitted records (concatenated bytes + offsets) plus an overlay —
+// the canonical re-emission of the records that arrived in a non-canonical spelling (ck_canon.cuh).
+// Every stage after decode reads a record through ck_rec(), i.e. its canonical bytes.
+// ------------------------------------------------------------------------------------------------
+struct ck_view {
+    const u8* in; const long long* off;
+    const u8* ovl; const long long* ovl_off; const u32* ovl_len;     // ovl_off[i] < 0: record i has no overlay
+};
+__device__ __forceinline__ const u8* ck_rec(const ck_view& v, u32 i, u32& len) {
+    long long o = v.ovl_off[i];
+    if (o >= 0) { len = v.ovl_len[i]; return v.ovl + o; }
+    long long a = v.off[i];
+    len = (u32)(v.off[i + 1] - a);
+    return v.in + a;
+}
 
 // ------------------------------------------------------------------------------------------------
 // node configuration living in device memory
@@ -65,7 +83,7 @@ __constant__ uint32_t ck_vm_prog_dev[CK_VM_PROG_WORDS] = CK_VM_PROG_INIT;
 
 #define CK_WALK_THREADS 128
 __global__ void __launch_bounds__(CK_WALK_THREADS)
-ck_walk_vm_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride) {
+ck_walk_vm_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     // the schema bytecode and one 64-byte window per thread live in shared memory
     __shared__ u32 s_prog[CK_VM_PROG_WORDS];
     __shared__ u32 s_win[CK_WALK_THREADS * CK_WIN_WORDS];
@@ -73,17 +91,18 @@ ck_walk_vm_kernel(const u8* __restrict__ in, const long long* __restrict__ off, 
     __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    long long a = off[i], b = off[i + 1];
+    u32 len; const u8* rec;
+    if (mode == 0) { long long a = v.off[i]; len = (u32)(v.off[i + 1] - a); rec = v.in + a; }
+    else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }
     WalkOut o; o.base = cols + i; o.stride = stride;
-    u32 len = (u32)(b - a);
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
     else {
-        VRd r; r.init(in + a, len, s_win + threadIdx.x * CK_WIN_WORDS);
+        VRd r; r.init(rec, len, s_win + threadIdx.x * CK_WIN_WORDS);
         AnyCtx cx;
         cx.kfill = 0;
         VmDicts dk;
-        status = ck_vm_walk(r, s_prog, o, cx, dk, stop) ? CK_OK : CK_NOT_CANONICAL;
+        status = ck_vm_walk(r, s_prog, o, cx, dk, stop) ? CK_OK : (mode ? CK_UNSUPPORTED : CK_NOT_CANONICAL);
     }
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);
@@ -92,27 +111,63 @@ ck_walk_vm_kernel(const u8* __restrict__ in, const long long* __restrict__ off, 
 // recursive-descent walker (csrc/ck_walk.cuh).  pf: software prefetch of the record towards L2 before the
 // (strictly sequential, latency-bound) walk starts
 __global__ void __launch_bounds__(128, 8)
-ck_walk_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride, u32 pf) {
+ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    long long a = off[i], b = off[i + 1];
+    u32 len; const u8* rec;
+    if (mode == 0) { long long a = v.off[i]; len = (u32)(v.off[i + 1] - a); rec = v.in + a; }      // the submitted spelling
+    else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }                                  // re-walk of canonicalised records
     WalkOut o; o.base = cols + i; o.stride = stride;
-    u32 len = (u32)(b - a);
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
     else {
-        if (pf) {
-            const u8* p = in + a;
-            u32 lim = len < pf ? len : pf;
-            for (u32 k = 0; k < lim; k += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + k));
-        }
-        Rd r; r.init(in + a, len);
+        Rd r; r.init(rec, len);
         AnyCtx cx;
         cx.kfill = 0;
-        status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_NOT_CANONICAL;
+        // a canonicalised record the walker cannot prove stays loud (never happens by construction: hostsim fuzz)
+        status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : (mode ? CK_UNSUPPORTED : CK_NOT_CANONICAL);
     }
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);
+}
+
+// ------------------------------------------------------------------------------------------------
+// canonicaliser kernels (ck_canon.cuh): one thread per record that the walker left as CK_NOT_CANONICAL.
+//   count: verdict + canonical length (the emitter runs with a zero-capacity sink)
+//   write: after the exclusive scan of the lengths, emit into the overlay buffer
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+ck_canon_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32* __restrict__ clen) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 need = 0;
+    if (cols[(size_t)CK_COL_STATUS * stride + i] == CK_NOT_CANONICAL) {
+        long long a = v.off[i];
+        u32 len = (u32)(v.off[i + 1] - a), out_len = 0;
+        u32 st = ck_canonicalise(v.in + a, len, nullptr, 0, out_len);
+        if (st == CK_OK) need = (out_len + 15u) & ~15u;
+        else cols[(size_t)CK_COL_STATUS * stride + i] = st;
+    }
+    clen[i] = need;
+}
+
+__global__ void __launch_bounds__(64)
+ck_canon_write_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, const u32* __restrict__ clen,
+                      const long long* __restrict__ coff, u8* __restrict__ ovl, long long ovl_cap,
+                      long long* __restrict__ ovl_off, u32* __restrict__ ovl_len) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 need = clen[i];
+    if (!need) return;
+    long long o0 = coff[i];
+    if (o0 + need > ovl_cap) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; return; }   // overlay buffer full
+    long long a = v.off[i];
+    u32 out_len = 0;
+    u32 st = ck_canonicalise(v.in + a, (u32)(v.off[i + 1] - a), ovl + o0, need, out_len);
+    if (st != CK_OK) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; return; }
+    for (u32 k = out_len; k < need; k++) ovl[o0 + k] = 0;
+    ovl_len[i] = out_len;
+    ovl_off[i] = o0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,7 +289,7 @@ struct SegWriter {
 //   mode 1: classify + build the final payload from the device template or the host's results (aux)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
+ck_plan_tool_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
                     const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
                     const long long* __restrict__ aux_off,    // per record [n+1] spans of the host results blob, or NULL
                     const u8* __restrict__ aux, u8* __restrict__ glue,
@@ -248,8 +303,8 @@ ck_plan_tool_kernel(const u8* __restrict__ in, const long long* __restrict__ off
     ck_out_desc* d = descs + i;
     u32 status = COL(CK_COL_STATUS);
     u32 action = CK_ACT_NONE;
-    long long a = off[i];
-    Rd r; r.init(in + a, (u32)(off[i + 1] - a));
+    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
+    Rd r; r.init(rec, rlen);
     pubs[2 * i] = none; pubs[2 * i + 1] = none;
     pay_len[i] = 0; d->nseg = 0; d->total_len = 0; d->record = i;
     if (status != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; COL(CK_COL_NOUT) = 0; return; }
@@ -433,7 +488,7 @@ __device__ __forceinline__ void SegWriter::hex_uuid7(unsigned long long unix_ms,
 
 // pass 1: how many payloads does each record produce (pending + 1 for the handler return)
 __global__ void __launch_bounds__(128)
-ck_fanout_count_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
+ck_fanout_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
                        const ck_agent_cfg* __restrict__ cfgp, u32 max_fanout, u32* __restrict__ counts) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -441,8 +496,8 @@ ck_fanout_count_kernel(const u8* __restrict__ in, const long long* __restrict__ 
     counts[i] = 0;
     COL(CK_COL_NOUT) = 0;
     if (COL(CK_COL_STATUS) != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; return; }
-    long long a = off[i];
-    Rd r; r.init(in + a, (u32)(off[i + 1] - a));
+    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
+    Rd r; r.init(rec, rlen);
     if (COL(CK_COL_NFRAMES) == 0) { COL(CK_COL_ACTION) = CK_ACT_RAISES; return; }
     u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF);
     u32 pos = tc + 1, pending = 0;
@@ -463,7 +518,7 @@ ck_fanout_count_kernel(const u8* __restrict__ in, const long long* __restrict__ 
 // pass 2: descriptors.  slot_base = exclusive scan of counts (payload slots), one publish per payload
 // except a single Call whose payload is published twice (target + publish_topic): pubs are sized 2/slot.
 __global__ void __launch_bounds__(128)
-ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ off, u32 n, u32* __restrict__ cols, u32 stride,
+ck_fanout_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
                       const ck_agent_cfg* __restrict__ cfgp, const u8* __restrict__ lit, const long long* __restrict__ slot_base,
                       unsigned long long unix_ms, unsigned long long seed, const u8* __restrict__ aux, u8* __restrict__ glue,
                       ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
@@ -473,8 +528,8 @@ ck_fanout_plan_kernel(const u8* __restrict__ in, const long long* __restrict__ o
     u32 action = COL(CK_COL_ACTION);
     if (COL(CK_COL_STATUS) != CK_OK || (action != CK_ACT_CALL && action != CK_ACT_FANOUT)) return;
     const ck_agent_cfg& cfg = *cfgp;
-    long long a = off[i];
-    Rd r; r.init(in + a, (u32)(off[i + 1] - a));
+    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
+    Rd r; r.init(rec, rlen);
     u32 slot = (u32)slot_base[i];
     u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF);
     u32 frames_off = COL(CK_COL_FRAMES_OFF), frames_len = COL(CK_COL_FRAMES_LEN), nframes = COL(CK_COL_NFRAMES);
@@ -671,7 +726,7 @@ ck_gather_spans_kernel(const u8* __restrict__ src, const long long* __restrict__
 // vectors where a segment starts, one warp-wide OR gives the mask and a popcount gives the index.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ck_emit_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, const u8* __restrict__ lit,
+ck_emit_kernel(ck_view vw, const u8* __restrict__ lit,
                const u8* __restrict__ aux, const u8* __restrict__ glue, const ck_out_desc* __restrict__ descs,
                const long long* __restrict__ out_off, u32 n, u8* __restrict__ out, long long out_cap) {
     u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -682,7 +737,7 @@ ck_emit_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, 
     u32 nseg = d->nseg;
     if (nseg == 0 || nseg > CK_MAX_SEGS) return;
     u32 total = d->total_len;
-    const u8* rec = in + in_off[d->record];
+    u32 rec_len; const u8* rec = ck_rec(vw, d->record, rec_len);
     // segment table: lane s holds segment s (source address, start vector, length)
     u32 my_len = 0;
     const u8* my_ptr = rec;
@@ -747,7 +802,7 @@ __device__ __forceinline__ u32 ck_murmur2(const u8* data, u32 len) {
 }
 
 __global__ void __launch_bounds__(256)
-ck_route_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off, const u32* __restrict__ cols, u32 stride,
+ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
                 ck_pub* __restrict__ pubs, u32 npubs, ck_topic_table tab, u32 num_partitions, u32* __restrict__ topic_hist, u32 hist_cap) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = j < npubs;
@@ -755,7 +810,7 @@ ck_route_kernel(const u8* __restrict__ in, const long long* __restrict__ in_off,
     if (live) { p = pubs[j]; live = (p.payload != 0xffffffffu); }
     int tid = -1;
     if (live) {
-        const u8* rec = in + in_off[p.record];
+        u32 rec_len; const u8* rec = ck_rec(vw, p.record, rec_len);
         tid = p.topic_id;
         if (tid < 0 && p.topic_len && tab.cap) {
             u32 h = ck_fnv1a(rec + p.topic_off, p.topic_len);

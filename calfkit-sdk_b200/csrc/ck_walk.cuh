@@ -241,7 +241,27 @@ CK_HD_NOINLINE u32 ck_number_core(const u8* g, u32 n, u32 pos, bool allow_int, b
         frac_len = p - frac_start;
         if (frac_len == 0) return false;
     }
-    if (p < r.n) { u8 e = r.at(p); if (e == 'e' || e == 'E') return false; }   // exponent spelling: not proven here
+    if (p < r.n && r.at(p) == 'e') {
+        // canonical scientific spelling d[.ddd]e[+-]X: what the reference prints outside [1e-5, 1e16).  A fixed
+        // point when it has <= 15 significant digits, no trailing fractional zero, the exponent is in the range
+        // that is printed this way, and the value is far from overflow / subnormals (DBL_DIG argument).
+        if (!allow_float || int_zero || int_len != 1) return false;
+        if (is_float && r.at(frac_start + frac_len - 1) == '0') return false;
+        if (1 + frac_len > 15) return false;
+        p++;
+        if (p >= r.n) return false;
+        u8 sg = r.at(p);
+        if (sg != '+' && sg != '-') return false;
+        p++;
+        if (p >= r.n) return false;
+        u8 d0 = r.at(p);
+        if (d0 < '1' || d0 > '9') return false;
+        u32 x = 0, xl = 0;
+        while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; x = x * 10 + (u32)(d - '0'); p++; if (++xl > 3) return false; }
+        if (x > 290 || (sg == '-' ? x < 6 : x < 16)) return false;
+        return p;
+    }
+    if (p < r.n && r.at(p) == 'E') return false;
     if (!is_float) {
         if (!allow_int) return false;
         if (neg && int_zero) return false;          // "-0" re-emits as "0"
@@ -283,12 +303,12 @@ CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
 // Iterative (explicit container bit-stack); duplicate keys make a value non-canonical because the
 // reference re-emits a Python dict, so each open object keeps 32-bit key hashes in a small stack.
 // -------------------------------------------------------------------------------------------------
-#define CK_MAX_DEPTH 96          // fast-path bound; jiter's own limit (~200) is handled by the canonicaliser
+#define CK_MAX_DEPTH 208         // array sizes; the rule itself: a value enclosed by more than 200 containers is json_invalid
 #define CK_KEYSTACK 64
 #define CK_DICT_KEYS 128     // tool_calls / tool_results entries handled on the fast path
 
 struct AnyCtx {
-    u32 kind[CK_MAX_DEPTH / 32];        // bit = 1: object, 0: array
+    u32 kind[(CK_MAX_DEPTH + 31) / 32]; // bit = 1: object, 0: array
     u32 khash[CK_KEYSTACK];
     u8  kbase[CK_MAX_DEPTH];            // khash fill level when the object at this depth was opened
     u32 kfill;
@@ -308,12 +328,12 @@ CK_HD_NOINLINE u32 ck_any_core(const u8* g, u32 n, u32 pos, u32 base_depth, AnyC
     cx.kfill = 0;
     Span s;
     for (;;) {
-        // ---- parse a value
+        // ---- parse a value (nesting index = base_depth - 1 + depth must not exceed jiter's 200)
         if (pos >= r.n) return false;
+        if (base_depth + depth > 201) return false;
         u8 c = r.at(pos);
         bool opened = false;
         if (c == '{' || c == '[') {
-            if (depth + base_depth >= CK_MAX_DEPTH) return false;
             bool is_obj = (c == '{');
             if (is_obj) cx.kind[depth >> 5] |= (1u << (depth & 31)); else cx.kind[depth >> 5] &= ~(1u << (depth & 31));
             cx.kbase[depth] = (u8)cx.kfill;

@@ -101,6 +101,10 @@ int  ck_fetch_columns(ck_handle* h, uint32_t* host_cols /* CK_NUM_COLS * n, colu
  * the padded total */
 int  ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off /* n_payloads+1 */,
                      uint32_t* host_out_len /* n_payloads */, ck_publish* host_pubs /* n_publishes */);
+/* canonical re-emissions of the records that were submitted in a non-canonical spelling: record i has one iff
+ * host_off[i] >= 0 (then host_ovl[host_off[i] .. + host_len[i]) are its canonical bytes; column spans of that
+ * record refer to them) */
+int  ck_fetch_overlay(ck_handle* h, uint8_t* host_ovl, uint64_t cap, int64_t* host_off, uint32_t* host_len, uint64_t* used);
 int  ck_fetch_topic_hist(ck_handle* h, uint32_t* host_hist, uint32_t n);
 
 /* introspection for benchmarks / tests ------------------------------------------------------------ */
@@ -110,7 +114,7 @@ int  ck_device_buffers2(ck_handle* h, void** pubs, void** pay_len, void** descs)
 int  ck_profile(ck_handle* h, int enable);         /* record (asynchronous) CUDA events around every kernel */
 int  ck_profile_read(ck_handle* h, float* ms /* CK_NUM_KERNELS */, uint32_t* launches /* CK_NUM_KERNELS */, int reset);
 
-enum { CK_K_WALK = 0, CK_K_PLAN, CK_K_SCAN, CK_K_EMIT, CK_K_ROUTE, CK_K_FANOUT, CK_NUM_KERNELS };
+enum { CK_K_WALK = 0, CK_K_PLAN, CK_K_SCAN, CK_K_EMIT, CK_K_ROUTE, CK_K_FANOUT, CK_K_CANON, CK_NUM_KERNELS };
 
 #ifdef __cplusplus
 }
