@@ -189,6 +189,123 @@ def place_on_partitions(batch, corr_off, rank: int, world: int, cross: float, se
     return batch
 
 
+
+def _cpu_fanout_worker(chunk):
+    from oracle import port
+    registry = {f"tool_{j:02d}": f"tool.tool_{j:02d}.input" for j in range(256)}
+    nb = 0
+    for rec in chunk:
+        for (_t, _k, _c, payload) in port.agent_fanout("planner", "planner.input", "planner.output", registry, rec):
+            nb += len(payload)
+    return len(chunk), nb
+
+
+def run_fanout(args, rank, world, local_rank, dev, real_stdout) -> None:
+    """BASELINE.json configs[2]: one Agent node fans every event out to F @agent_tool nodes (reference
+    nodes/agent.py:177-211 + nodes/base.py:73-88): per event F envelopes, each the full state + one pushed frame,
+    plus the handler-return publish of the original envelope.  Write-bandwidth bound."""
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from calfkit import synth
+    from calfkit.engine import BatchEngine
+    F = args.fanout
+    n = args.events if args.events != 1_000_000 else 4096
+    recs = synth.fanout_events(n, seed=3000 + rank, fanout=F)
+    batch = synth.pack(recs)
+    in_bytes = int(batch.data.nbytes)
+    per_out = int(in_bytes / n) + 260
+    out_cap = n * ((F + 1) * (per_out + 16)) + (1 << 20)
+    eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096, max_out_bytes=out_cap, max_payloads=n * (F + 1))
+    registry = {f"tool_{j:02d}": f"tool.tool_{j:02d}.input" for j in range(F)}
+    eng.register_topics(list(registry.values()) + ["planner.input", "planner.output"], num_partitions=NUM_PARTITIONS)
+    eng.set_agent_node("planner", "planner.input", "planner.output", registry)
+    d_in = torch.from_numpy(batch.data.copy()).to(dev)
+    d_off = torch.from_numpy(batch.offsets.copy()).to(dev)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    ms0 = 1767225600000
+
+    def step(k):
+        eng.submit_device(d_in, d_off, n)
+        eng.fanout_plan(ms0 + k, 1234 + k, max_fanout=256)
+
+    for k in range(args.warmup):
+        step(k)
+    eng.sync()
+    eng.profile(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    prof = eng.profile_read()
+    eng.profile(False)
+    out_bytes, npay, npub = eng.out_size()
+    value = world * n / (ms_step / 1e3)
+    # end to end: pinned host in -> device -> pinned host out
+    h_in = torch.from_numpy(batch.data.copy()).pin_memory()
+    h_off = torch.from_numpy(batch.offsets.copy()).pin_memory()
+    h_out = torch.empty(out_bytes + (1 << 20), dtype=torch.uint8).pin_memory()
+    h_o = torch.empty(npay + 1, dtype=torch.int64).pin_memory().numpy()
+    h_l = torch.empty(npay, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    from calfkit.engine._lib import PUB_DTYPE
+    h_p = torch.empty(npub * PUB_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(PUB_DTYPE)
+    d2h = 0
+    for k in range(2):
+        eng.submit(h_in.numpy(), h_off.numpy()); eng.fanout_plan(ms0, 1, max_fanout=256)
+        o, of, ln, pb = eng._fetch(out_buf=h_out.numpy(), off_buf=h_o, len_buf=h_l, pubs_buf=h_p)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = 3
+    for k in range(e2e_steps):
+        eng.submit(h_in.numpy(), h_off.numpy()); eng.fanout_plan(ms0, 1, max_fanout=256)
+        o, of, ln, pb = eng._fetch(out_buf=h_out.numpy(), off_buf=h_o, len_buf=h_l, pubs_buf=h_p)
+        d2h = int(o.nbytes + of.nbytes + ln.nbytes + pb.nbytes)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    payload_bytes = int(ln.astype(np.int64).sum())
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    kern = {k: {"ms_per_launch": ms / c, "launches": c} for k, (ms, c) in prof.items() if c}
+    emit_ms = kern["emit"]["ms_per_launch"]
+    algo_emit = in_bytes + payload_bytes            # every input byte read at least once + every payload byte written
+    cores = os.cpu_count() or 1
+    sample = recs[: max(cores * 2, 64)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(min(cores, len(sample))) as pool:
+        chunks = [sample[i::cores] for i in range(cores) if sample[i::cores]]
+        pool.map(_cpu_fanout_worker, [c[:1] for c in chunks])
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_fanout_worker, chunks)
+        cpu_dt = time.perf_counter() - t0
+    cpu_n = sum(r[0] for r in res)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"fanout: 1 Agent node -> {F} @agent_tool nodes (BASELINE.json configs[2]), post-LLM agent-stage envelopes",
+                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "payloads_per_event": npay / n,
+                   "out_bytes_per_event": payload_bytes / n, "l2": "outputs (%.1f GB/step) far larger than L2" % (payload_bytes / 1e9)},
+        "clocks": sampler.summary(),
+        "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "BatchEngine.submit(pinned host) + fanout_plan + fetch(pinned host)"},
+        "gpu_launches": args.steps * 14,
+        "roofline": {"kernel": "ck_emit_kernel", "bound": "hbm", "achieved": algo_emit / emit_ms / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": algo_emit / emit_ms / 1e6 / peak, "traffic": None, "share_of_step": emit_ms / ms_step, "kernels": kern},
+        "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cpu_n} events in {cpu_dt:.1f} s over {min(cores, len(sample))} processes (oracle/port.py agent_fanout)"},
+    }
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -199,6 +316,9 @@ def main() -> None:
     ap.add_argument("--events", type=int, default=1_000_000, help="events per GPU per step (config 2: 1M)")
     ap.add_argument("--cross", type=float, default=0.125, help="fraction of records on a foreign partition (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="events for the cpu_baseline leg (0 = auto)")
+    ap.add_argument("--workload", default="tool_event_1k", choices=["tool_event_1k", "fanout"],
+                    help="tool_event_1k = BASELINE.json configs[1] (the headline); fanout = configs[2]: 1 Agent -> 64 tools")
+    ap.add_argument("--fanout", type=int, default=64)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -225,6 +345,9 @@ def main() -> None:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner / logs must not land on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.workload == "fanout":
+        run_fanout(args, rank, world, local_rank, dev, real_stdout)
+        return
     n = args.events
     recs = synth.tool_events(n, seed=1000 + rank)
     batch = synth.pack(recs)
