@@ -201,11 +201,16 @@ class BatchEngine:
         pid = self.topic_ids[publish_topic] if publish_topic else -1
         self._check(self.lib.ck_set_agent_node(self.h, pid, ptr(anb), len(an), ptr(cbb), len(cb), ptr(nb), ptr(no),
                                                ptr(tb), ptr(to), len(names)))
-        ids = np.asarray([self.topic_ids[v] for v in registry.values()], dtype=np.uint32)
-        self._check(self.lib.ck_set_agent_tool_topic_ids(self.h, ptr(ids), len(ids)))
+        ids = np.asarray([self.topic_ids[v] for v in registry.values()] or [0], dtype=np.uint32)
+        self._check(self.lib.ck_set_agent_tool_topic_ids(self.h, self.topic_ids.get(callback_topic, -1), ptr(ids), len(registry)))
 
-    def fanout_plan(self, unix_ms: int, seed: int, max_fanout: int = 128) -> None:
-        self._check(self.lib.ck_fanout_plan(self.h, unix_ms, seed, max_fanout))
+    def fanout_plan(self, unix_ms: int, seed: int, max_fanout: int = 128, sequential: bool = False) -> None:
+        """list[Call] / Call of the pending tool calls; sequential: first pending only (agent.py:94-108)."""
+        self._check(self.lib.ck_fanout_plan(self.h, unix_ms, seed, max_fanout, 1 if sequential else 0))
+
+    def tailcall_plan(self, unix_ms: int, seed: int) -> None:
+        """TailCall to the agent's own subscribe topic (agent.py:171-175)."""
+        self._check(self.lib.ck_tailcall_plan(self.h, unix_ms, seed))
 
     # ------------------------------------------------------------------------------------------
     def submit(self, data: np.ndarray, offsets: np.ndarray) -> None:

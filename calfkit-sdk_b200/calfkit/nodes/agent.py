@@ -182,10 +182,7 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
             if action == "silent":
                 continue
             new_bytes = bytes(rec[:s0]) + new_state.model_dump_json().encode() + bytes(rec[s1:])
-            if action == "tailcall":
-                # all requested tools were invalid: go round again through our own topic (agent.py:171-175)
-                action = "return_self"
-            post.setdefault(action, []).append((i, new_bytes))
+            post.setdefault(action, []).append((i, new_bytes))   # "tailcall": all requested tools invalid (agent.py:171-175)
         produced: list[Record] = []
         now_ms = time.time_ns() // 1_000_000
         for kind, items in post.items():
@@ -194,12 +191,13 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
             recs2 = [Record(records[i].topic, b, records[i].key, records[i].correlation_id) for i, b in items]
             d2, o2 = pack_records(recs2)
             engine.submit(d2, o2)                                                            # re-validated on the device
+            seed = int(np.random.SeedSequence().entropy) & ((1 << 63) - 1)
             if kind == "fanout":
-                engine.fanout_plan(now_ms, int(np.random.SeedSequence().entropy) & ((1 << 63) - 1), max_fanout=1 if self.sequential_only_mode else 256)
+                engine.fanout_plan(now_ms, seed, max_fanout=256, sequential=self.sequential_only_mode)
             elif kind == "return":
                 engine.return_plan()
             else:
-                raise NotImplementedError("TailCall retry of an agent with only invalid tool calls")
+                engine.tailcall_plan(now_ms, seed)
             out = engine.fetch()
             for p in out.publishes():
                 src = recs2[p.record]

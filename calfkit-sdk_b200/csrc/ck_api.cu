@@ -395,6 +395,9 @@ extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const u
     puts(",", c.lit_comma);
     puts("\",\"" + an + "\"],\"frame_id\":\"", c.lit_mid);
     puts("\",\"overrides\":null}", c.lit_tail);
+    puts("{\"target_topic\":\"" + cb + "\",\"callback_topic\":\"", c.lit_tc_head);
+    puts("\",\"input_args\":null,\"frame_id\":\"", c.lit_tc_mid);
+    c.self_topic_id = -1;
     std::vector<u32> tab(5 * (size_t)ntools);
     for (u32 k = 0; k < ntools; k++) {
         std::string nm((const char*)tool_names + tool_name_off[k], tool_name_off[k + 1] - tool_name_off[k]);
@@ -421,20 +424,47 @@ extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const u
     return 0;
 }
 
-extern "C" int ck_set_agent_tool_topic_ids(ck_handle* h, const uint32_t* ids, uint32_t ntools) {
+extern "C" int ck_set_agent_tool_topic_ids(ck_handle* h, int32_t self_topic_id, const uint32_t* ids, uint32_t ntools) {
     cudaSetDevice(h->device);
     if (!h->agent_set || ntools != h->h_agent_cfg.ntools) return fail(h, "ck_set_agent_tool_topic_ids: agent node not set / size mismatch");
-    CUDA_TRY(h, cudaMemcpy(h->d_agent_tables + 4 * (size_t)ntools, ids, sizeof(u32) * ntools, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (ntools) CUDA_TRY(h, cudaMemcpy(h->d_agent_tables + 4 * (size_t)ntools, ids, sizeof(u32) * ntools, cudaMemcpyHostToDevice));
+    h->h_agent_cfg.self_topic_id = self_topic_id;
+    CUDA_TRY(h, cudaMemcpy(h->d_agent_cfg, &h->h_agent_cfg, sizeof h->h_agent_cfg, cudaMemcpyHostToDevice));
     return 0;
 }
 
-extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout) {
+extern "C" int ck_tailcall_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed) {
+    cudaSetDevice(h->device);
+    if (!h->agent_set) return fail(h, "ck_tailcall_plan: call ck_set_agent_node first");
+    if (h->h_agent_cfg.self_topic_id < 0) return fail(h, "ck_tailcall_plan: the agent's own topic is not registered");
+    u32 n = h->n;
+    if (n > h->max_payloads) return fail(h, "ck_tailcall_plan: more payloads than max_payloads");
+    {
+        KTimer t(h, CK_K_FANOUT);
+        if (n) ck_tailcall_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
+            unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (scan_emit(h, n, h->d_aux)) return 1;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        u32 npubs = 2 * n;
+        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, n, h->d_pubs, npubs,
+            h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
+        CUDA_TRY(h, cudaGetLastError());
+        h->n_pubs = npubs;
+    }
+    return 0;
+}
+
+extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout, uint32_t sequential) {
     cudaSetDevice(h->device);
     if (!h->agent_set) return fail(h, "ck_fanout_plan: call ck_set_agent_node first");
     u32 n = h->n;
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, max_fanout, h->d_counts);
+        if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, max_fanout, sequential, h->d_counts);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (run_scan(h, h->d_counts, n, h->d_slot_base, 0)) return 1;

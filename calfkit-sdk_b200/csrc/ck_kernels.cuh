@@ -452,6 +452,9 @@ struct ck_agent_cfg {
     uint32_t lit_comma[2];             // ,
     uint32_t lit_mid[2];               // ","<agent_name>"],"frame_id":"
     uint32_t lit_tail[2];              // ","overrides":null}
+    uint32_t lit_tc_head[2];           // {"target_topic":"<self topic>","callback_topic":"      (TailCall to self)
+    uint32_t lit_tc_mid[2];            // ","input_args":null,"frame_id":"
+    int32_t  self_topic_id;            // registered id of subscribe_topics[0] (or -1)
     uint32_t ntools;
     // per tool k (device arrays): name span + frame-prefix literal span in the pool:
     //   {"target_topic":"<topic_k>","callback_topic":"<callback>","input_args":["
@@ -489,7 +492,7 @@ __device__ __forceinline__ void SegWriter::hex_uuid7(unsigned long long unix_ms,
 // pass 1: how many payloads does each record produce (pending + 1 for the handler return)
 __global__ void __launch_bounds__(128)
 ck_fanout_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
-                       const ck_agent_cfg* __restrict__ cfgp, u32 max_fanout, u32* __restrict__ counts) {
+                       const ck_agent_cfg* __restrict__ cfgp, u32 max_fanout, u32 sequential, u32* __restrict__ counts) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
 #define COL(k) cols[(size_t)(k) * stride + i]
@@ -507,6 +510,8 @@ ck_fanout_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
         if (ck_dict_find(r, tr, k.off, k.len).len == 0) pending++;
         if (pos < r.n && r.at(pos) == ',') pos++;
     }
+    // sequential_only_mode (agent.py:94-108,179-192): only the first pending call goes out, as a single Call
+    if (sequential && pending > 1) pending = 1;
     if (pending == 0 || pending > max_fanout) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_STATUS) = CK_UNSUPPORTED; return; }
     u32 extra = (cfgp->publish_topic_id >= 0 && pending > 1) ? 1u : 0u;   // list[Call]: the input envelope is the return value
     counts[i] = pending + extra;
@@ -577,6 +582,7 @@ ck_fanout_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
                 j++;
             }
         }
+        if (action == CK_ACT_CALL && j) break;                           // single Call: first pending only
         if (pos < r.n && r.at(pos) == ',') pos++;
     }
     if (action == CK_ACT_FANOUT && cfg.publish_topic_id >= 0) {
@@ -588,6 +594,53 @@ ck_fanout_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
         ck_pub q = none; q.payload = s; q.topic_id = cfg.publish_topic_id; pubs[2 * s] = q; pubs[2 * s + 1] = none;
     }
     if (bad) { COL(CK_COL_STATUS) = CK_UNSUPPORTED; }
+#undef COL
+}
+
+
+// TailCall to self (reference nodes/agent.py:171-175 -> nodes/base.py:120-136): the current frame is
+// replaced by {target_topic: self.subscribe_topics[0], callback_topic: <popped frame's callback>,
+// input_args: null, frame_id: fresh uuid7, overrides: null}; one payload, published keyed to the
+// target and, as the handler's return value, unkeyed to publish_topic.
+__global__ void __launch_bounds__(128)
+ck_tailcall_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, const ck_agent_cfg* __restrict__ cfgp,
+                        const u8* __restrict__ lit, unsigned long long unix_ms, unsigned long long seed,
+                        const u8* __restrict__ aux, u8* __restrict__ glue,
+                        ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#define COL(k) cols[(size_t)(k) * stride + i]
+    const ck_agent_cfg& cfg = *cfgp;
+    ck_pub none; none.payload = 0xffffffffu; none.topic_id = -1; none.topic_off = none.topic_len = 0; none.record = i;
+    none.has_key = 0; none.partition = -1; none.pad = 0;
+    pubs[2 * i] = none; pubs[2 * i + 1] = none;
+    pay_len[i] = 0;
+    COL(CK_COL_NOUT) = 0;
+    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
+    Rd r; r.init(rec, rlen);
+    SegWriter w; w.init(descs + i, &r, lit, aux, glue + (size_t)i * CK_GLUE_STRIDE);
+    if (COL(CK_COL_STATUS) != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; w.finish(i); return; }
+    if (COL(CK_COL_NFRAMES) == 0) { COL(CK_COL_ACTION) = CK_ACT_RAISES; w.finish(i); return; }   // unwind_frame on an empty stack
+    u32 top_off = COL(CK_COL_TOP_OFF), top_len = COL(CK_COL_TOP_LEN);
+    u32 cur = 0, fo = COL(CK_COL_FOV_OFF);
+    if (r.at(fo) != 'n') {                                   // overrides rule (nodes/base.py:66-67)
+        u32 so = COL(CK_COL_SOV_OFF);
+        w.add(CK_SRC_INPUT, 0, so); w.add(CK_SRC_INPUT, fo, COL(CK_COL_FOV_LEN)); cur = so + COL(CK_COL_SOV_LEN);
+    }
+    w.add(CK_SRC_INPUT, cur, top_off - cur);
+    w.add(CK_SRC_LIT, cfg.lit_tc_head[0], cfg.lit_tc_head[1]);
+    w.add(CK_SRC_INPUT, COL(CK_COL_CB_OFF), COL(CK_COL_CB_LEN));
+    w.add(CK_SRC_LIT, cfg.lit_tc_mid[0], cfg.lit_tc_mid[1]);
+    w.hex_uuid7(unix_ms, seed, (unsigned long long)i);
+    w.add(CK_SRC_LIT, cfg.lit_tail[0], cfg.lit_tail[1]);
+    w.add(CK_SRC_INPUT, top_off + top_len, r.n - (top_off + top_len));
+    w.finish(i);
+    pay_len[i] = w.total;
+    COL(CK_COL_ACTION) = CK_ACT_TAILCALL;
+    ck_pub p = none; p.payload = i; p.topic_id = cfg.self_topic_id; p.has_key = 1; pubs[2 * i] = p;
+    u32 nout = 1;
+    if (cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = i; q.topic_id = cfg.publish_topic_id; pubs[2 * i + 1] = q; nout = 2; }
+    COL(CK_COL_NOUT) = nout;
 #undef COL
 }
 

@@ -85,8 +85,14 @@ int  ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const uint8_t* ag
                        const uint8_t* callback_topic, uint32_t callback_len,
                        const uint8_t* tool_names, const uint32_t* tool_name_off,
                        const uint8_t* tool_topics, const uint32_t* tool_topic_off, uint32_t ntools);
-int  ck_set_agent_tool_topic_ids(ck_handle* h, const uint32_t* ids /* 0xffffffff = unregistered */, uint32_t ntools);
-int  ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout);
+int  ck_set_agent_tool_topic_ids(ck_handle* h, int32_t self_topic_id /* id of the agent's subscribe_topics[0], -1 = unregistered */,
+                                 const uint32_t* ids /* 0xffffffff = unregistered */, uint32_t ntools);
+/* sequential != 0: Agent(sequential_only_mode=True) — only the first pending call goes out, as a single
+ * Call (agent.py:94-108,179-192). */
+int  ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_fanout, uint32_t sequential);
+/* TailCall to the agent's own topic (all requested tools invalid -> retry, agent.py:171-175;
+ * nodes/base.py:120-136): the current frame is replaced by a fresh one inheriting its callback_topic. */
+int  ck_tailcall_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed);
 /* copy n spans src[src_off[i] .. +src_len[i]) -> dst[dst_off[i] ..) on the handle's stream (device pointers);
  * used to pack cross-partition payloads before the NCCL all-to-all */
 int  ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64_t* dev_src_off, const int64_t* dev_src_len,

@@ -227,6 +227,62 @@ def test_fanout_matches_oracle(engine):
         e.close()
 
 
+def test_sequential_call_and_tailcall_match_oracle(engine):
+    """Agent(sequential_only_mode=True): first pending call only, as a single Call; no pending call at
+    all -> TailCall to the agent's own topic (reference nodes/agent.py:94-108,171-175; nodes/base.py:90-136)."""
+    from oracle import port
+    from calfkit import _ids, synth
+    from calfkit.engine.batch import device_uuid7_hex
+    from calfkit.engine import BatchEngine
+    recs = synth.fanout_events(12, seed=3, fanout=5) + synth.fanout_events(3, seed=4, fanout=1)
+    registry = {f"tool_{j:02d}": f"tool.tool_{j:02d}.input" for j in range(64)}
+    e = BatchEngine(0, max_records=64, max_in_bytes=8 << 20, max_out_bytes=64 << 20, max_payloads=256)
+    try:
+        e.register_topics(list(registry.values()) + ["planner.input", "planner.output"], num_partitions=8)
+        e.set_agent_node("planner", "planner.input", "planner.output", registry)
+        b = synth.pack(recs)
+        ms, seed = 1767225600000, 77
+        e.submit(b.data, b.offsets)
+        e.fanout_plan(ms, seed, max_fanout=64, sequential=True)
+        out = e.fetch()
+        assert (out.cols[0] == 0).all()
+        pubs = list(out.publishes())
+        assert len(pubs) == 2 * len(recs)
+        for i, rec in enumerate(recs):
+            _ids.set_id_source(lambda: device_uuid7_hex(ms, seed, i))
+            try:
+                want = port.agent_fanout("planner", "planner.input", "planner.output", registry, rec, sequential=True)
+            finally:
+                _ids.set_id_source(None)
+            assert [(p.topic, p.key, p.payload) for p in pubs[2 * i:2 * i + 2]] == [(t, k, pl) for (t, k, c, pl) in want], i
+        # TailCall: tool-stage events (a frame with input_args, overrides on some) + the golden TailCall input
+        recs2 = synth.tool_events(40, seed=5) + synth.mixed_events(20, seed=6)
+        b2 = synth.pack(recs2)
+        e.submit(b2.data, b2.offsets)
+        e.tailcall_plan(ms, seed)
+        out = e.fetch()
+        pubs = list(out.publishes())
+        k = 0
+        for i, rec in enumerate(recs2):
+            env = port.decode(rec)
+            if not env.internal_workflow_state.call_stack._internal_list:
+                assert out.cols[1][i] == 3            # CK_ACT_RAISES: unwind_frame on an empty stack
+                continue
+            _ids.set_id_source(lambda: device_uuid7_hex(ms, seed, i))
+            try:
+                corr = env.context.deps.correlation_id
+                ctx_state = port.prepare_context(env).state
+                got_pubs, returned = port.publish_action("planner.input", port.TailCall("planner.input", ctx_state), env, corr)
+            finally:
+                _ids.set_id_source(None)
+            want = [(t, kk, port.encode(en)) for (t, kk, c, en) in got_pubs] + [("planner.output", None, port.encode(returned))]
+            assert [(p.topic, p.key, p.payload) for p in pubs[k:k + 2]] == want, i
+            k += 2
+        assert k == len(pubs)
+    finally:
+        e.close()
+
+
 def test_mixed_sizes_and_edge_batches(engine):
     """config 5 shapes (128 B .. 64 KB, 256 topics' worth of tools, UTF-8 + escapes) and degenerate
     batches: empty batch, zero-length record, a batch of one."""

@@ -71,3 +71,84 @@ def test_parallel_fanout_three_tools_and_aggregation():
         assert r.output == f"A<v> | B<v> | C<v:t{i}>"
         calls = [m for m in r.message_history if getattr(m, "kind", "") == "response" and m.tool_calls]
         assert len(calls[-1].tool_calls) == 3
+
+
+def _three_tools():
+    from calfkit import agent_tool
+
+    @agent_tool
+    def tool_a(x: str) -> str:
+        """a"""
+        return f"A<{x}>"
+
+    @agent_tool(device_template="B<{x}>")
+    def tool_b(x: str) -> str:
+        """b"""
+        return f"B<{x}>"
+
+    return tool_a, tool_b
+
+
+def test_sequential_only_mode_routes_one_call_at_a_time():
+    """Agent(sequential_only_mode=True) (reference nodes/agent.py:94-108,179-192): the pending calls of one
+    model turn go out one by one as single Calls; no aggregation batch exists; same final answer."""
+    _skip_without_cuda()
+    from calfkit import Agent, Client, Worker
+    from calfkit.models.messages import ModelResponse, TextPart, ToolCallPart, ToolReturnPart
+    from calfkit.nodes import FunctionModelClient
+    tool_a, tool_b = _three_tools()
+    turns = []
+
+    def llm(messages, tools):
+        rets = [p for p in getattr(messages[-1], "parts", []) if isinstance(p, ToolReturnPart)]
+        turns.append(len(rets))
+        if rets:
+            return ModelResponse(parts=[TextPart(content=" | ".join(str(r.content) for r in rets))])
+        return ModelResponse(parts=[ToolCallPart(tool_name=t.name, args={"x": "v"}) for t in tools])
+
+    async def go():
+        client = Client.connect()
+        agent = Agent("planner", subscribe_topics="planner.input", publish_topic="planner.output",
+                      model_client=FunctionModelClient(llm), tools=[tool_a, tool_b], sequential_only_mode=True)
+        worker = Worker(client, nodes=[agent, tool_a, tool_b])
+        hs = [await client.invoke_node("go", "planner.input") for i in range(8)]
+        await worker.run(until_idle=True)
+        res = [await h.result(timeout=5) for h in hs]
+        assert not agent._pending_batches
+        await client.close()
+        return res
+
+    res = asyncio.run(go())
+    for r in res:
+        assert r.output == "A<v> | B<v>"
+    assert turns.count(0) == 8 and turns.count(2) == 8          # the model ran twice per event, never on a partial batch
+
+
+def test_all_tools_invalid_tailcall_retry():
+    """The model asks only for tools that do not exist -> every call gets a RetryPromptPart and the agent
+    TailCalls itself (reference nodes/agent.py:140-175); the next turn sees the retry prompts."""
+    _skip_without_cuda()
+    from calfkit import Agent, Client, Worker
+    from calfkit.models.messages import ModelResponse, RetryPromptPart, TextPart, ToolCallPart
+    from calfkit.nodes import FunctionModelClient
+    tool_a, tool_b = _three_tools()
+
+    def llm(messages, tools):
+        retries = [p for p in getattr(messages[-1], "parts", []) if isinstance(p, RetryPromptPart)]
+        if retries:
+            return ModelResponse(parts=[TextPart(content=f"gave up after {len(retries)} retry prompts: {retries[0].tool_name}")])
+        return ModelResponse(parts=[ToolCallPart(tool_name="nope", args={}), ToolCallPart(tool_name="nada", args={})])
+
+    async def go():
+        client = Client.connect()
+        agent = Agent("planner", subscribe_topics="planner.input", publish_topic="planner.output",
+                      model_client=FunctionModelClient(llm), tools=[tool_a, tool_b])
+        worker = Worker(client, nodes=[agent, tool_a, tool_b])
+        hs = [await client.invoke_node("go", "planner.input") for i in range(5)]
+        await worker.run(until_idle=True)
+        res = [await h.result(timeout=5) for h in hs]
+        await client.close()
+        return res
+
+    for r in asyncio.run(go()):
+        assert r.output == "gave up after 2 retry prompts: nope"
