@@ -200,7 +200,7 @@ def _cpu_fanout_worker(chunk):
     return len(chunk), nb
 
 
-def run_fanout(args, rank, world, local_rank, dev, real_stdout) -> None:
+def run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -> None:
     """BASELINE.json configs[2]: one Agent node fans every event out to F @agent_tool nodes (reference
     nodes/agent.py:177-211 + nodes/base.py:73-88): per event F envelopes, each the full state + one pushed frame,
     plus the handler-return publish of the original envelope.  Write-bandwidth bound."""
@@ -277,6 +277,8 @@ def run_fanout(args, rank, world, local_rank, dev, real_stdout) -> None:
     algo_emit = in_bytes + payload_bytes            # every input byte read at least once + every payload byte written
     cores = os.cpu_count() or 1
     sample = recs[: max(cores * 2, 64)]
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)
     ctx = mp.get_context("spawn")
     with ctx.Pool(min(cores, len(sample))) as pool:
         chunks = [sample[i::cores] for i in range(cores) if sample[i::cores]]
@@ -340,13 +342,17 @@ def main() -> None:
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host threads + pinned staging buffers next to this GPU's PCIe root (one process per GPU; restored for the CPU leg)
+    from calfkit.engine.batch import bind_host_to_gpu
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_host_to_gpu(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner / logs must not land on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     if args.workload == "fanout":
-        run_fanout(args, rank, world, local_rank, dev, real_stdout)
+        run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus)
         return
     n = args.events
     recs = synth.tool_events(n, seed=1000 + rank)
@@ -355,7 +361,7 @@ def main() -> None:
     in_bytes = int(batch.data.nbytes)
     topics = ["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"]
     import ctypes as C
-    from calfkit.engine.exchange import exchange as run_exchange, plan_exchange
+    from calfkit.engine.exchange import exchange as run_exchange, plan_exchange_device
     launches = [0]
 
     class Lane:
@@ -395,8 +401,8 @@ def main() -> None:
         def exchange(self):
             """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
             with torch.cuda.stream(self.stream):
-                nrecv, rbytes, _ = run_exchange(plan_exchange(self.t_pubs, self.t_out_off, self.t_out_len, rank, world),
-                                                self.gather, self.send_buf, self.recv_buf)
+                nrecv, rbytes, _ = run_exchange(plan_exchange_device(self.eng, rank, world, dev), self.gather, self.send_buf, self.recv_buf)
+            launches[0] += 8            # exchange plan: count, 3 x scan, scatter, 3 x scan
             self.rbytes = rbytes
             return nrecv, rbytes
 
@@ -577,6 +583,7 @@ def main() -> None:
                 "kernels": kern, "sum_kernel_ms_per_step": kern_step_ms}
 
     # ---- CPU baseline: the oracle port on a bounded sample, all host cores ----------------------------
+    os.sched_setaffinity(0, all_cpus)
     cores = os.cpu_count() or 1
     sample_n = args.cpu_sample or max(cores * 8000, 20000)       # ~10-20 s of CPU work on all cores
     sample = [batch.record(i) for i in range(min(sample_n, n))]

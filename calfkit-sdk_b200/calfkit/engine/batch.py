@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 import string
 from dataclasses import dataclass
 from typing import Iterator, Sequence
@@ -117,6 +118,28 @@ def device_uuid7_hex(unix_ms: int, seed: int, index: int) -> str:
     hi = ((unix_ms & 0xFFFFFFFFFFFF) << 16) | 0x7000 | (r0 & 0xFFF)
     lo = (0x2 << 62) | (r1 & 0x3FFFFFFFFFFFFFFF)
     return f"{hi:016x}{lo:016x}"
+
+
+def bind_host_to_gpu(device: int) -> list[int] | None:
+    """Pin the calling process to the CPUs NVML reports as local to `device` (same socket / NUMA node), so
+    that pinned staging buffers allocated afterwards are first-touched next to the GPU's PCIe root.  With
+    one worker process per GPU this keeps eight concurrent H2D/D2H streams off the inter-socket link.
+    Returns the CPU list, or None when NVML is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
 
 
 class BatchEngine:

@@ -45,15 +45,40 @@ def plan_exchange(pubs: torch.Tensor, out_off: torch.Tensor, out_len: torch.Tens
     return ExchangePlan(sel, src_off, lens, dst_off, counts, nbytes)
 
 
+class _DevArray:
+    """raw device pointer -> torch.as_tensor via __cuda_array_interface__ (no copy)"""
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": (n,), "typestr": typestr, "version": 3}
+
+
+def plan_exchange_device(engine, rank: int, world: int, device) -> ExchangePlan:
+    """The same plan as plan_exchange(), computed by the library's own kernels (ck_exchange_plan: histogram ->
+    scan -> stable scatter -> scan) instead of a dozen tensor ops over the whole publish table; one host
+    synchronisation instead of three.  `counts` / `nbytes` are host tensors (the all-to-all split sizes)."""
+    import ctypes as C
+    src, ln, dst, pub = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    counts = torch.zeros(world, dtype=torch.int64)
+    nbytes = torch.zeros(world, dtype=torch.int64)
+    nsel = C.c_uint32(0)
+    engine._check(engine.lib.ck_exchange_plan(engine.h, rank, world, C.byref(src), C.byref(ln), C.byref(dst), C.byref(pub),
+                                              counts.data_ptr(), nbytes.data_ptr(), C.byref(nsel)))
+    n = nsel.value
+    if n == 0:
+        z = torch.zeros(0, dtype=torch.int64, device=device)
+        return ExchangePlan(z, z, z, z, counts, nbytes)
+    as_t = lambda p, ts: torch.as_tensor(_DevArray(p.value, n, ts), device=device)   # noqa: E731
+    return ExchangePlan(as_t(pub, "<u4"), as_t(src, "<i8"), as_t(ln, "<i8"), as_t(dst, "<i8"), counts, nbytes)
+
+
 def exchange(plan: ExchangePlan, gather: Callable[[ExchangePlan, torch.Tensor], None], send_buf: torch.Tensor,
              recv_buf: torch.Tensor) -> tuple[int, int, torch.Tensor]:
     """gather(plan, send_buf) packs the selected payloads; returns (n received payloads, received bytes,
     their lengths)."""
     gather(plan, send_buf)
-    meta_out = torch.stack([plan.counts, plan.nbytes], 1).contiguous()
+    meta_out = torch.stack([plan.counts, plan.nbytes], 1).contiguous().to(plan.lens.device)
     meta_in = torch.empty_like(meta_out)
     dist.all_to_all_single(meta_in, meta_out)
-    mo, mi = meta_out.tolist(), meta_in.tolist()
+    mo, mi = torch.stack([plan.counts, plan.nbytes], 1).tolist(), meta_in.tolist()
     sc, sb = [x[0] for x in mo], [x[1] for x in mo]
     rc, rb = [x[0] for x in mi], [x[1] for x in mi]
     if sum(rb) > recv_buf.numel() or sum(sb) > send_buf.numel():

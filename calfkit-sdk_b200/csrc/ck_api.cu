@@ -34,6 +34,10 @@ struct ck_handle {
     u32* d_counts = nullptr; long long* d_slot_base = nullptr; u32* d_agent_tables = nullptr;
     bool agent_set = false; ck_agent_cfg h_agent_cfg{};
     u32* d_topic_hist = nullptr;
+    // exchange planning (allocated on first use)
+    u32* d_x_hist = nullptr; long long* d_x_base = nullptr; unsigned long long* d_x_nbytes = nullptr;
+    long long *d_x_src_off = nullptr, *d_x_len = nullptr, *d_x_dst_off = nullptr; u32 *d_x_len32 = nullptr, *d_x_pub = nullptr;
+    unsigned long long *d_x_tile = nullptr, *d_x_grand = nullptr; long long* h_x = nullptr;   // h_x: pinned
     // topic table
     ck_topic_table tab{}; u32 *d_tab_hash = nullptr, *d_tab_off = nullptr, *d_tab_len = nullptr; int32_t* d_tab_id = nullptr; u8* d_tab_names = nullptr;
     uint32_t num_partitions = 0, hist_cap = 0;
@@ -145,9 +149,11 @@ extern "C" void ck_destroy(ck_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_ovl, h->d_ovl_off, h->d_ovl_len, h->d_clen, h->d_coff, h->d_cols, h->d_descs, h->d_pay_len,
                     h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_agent_cfg, h->d_counts, h->d_slot_base, h->d_agent_tables, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
-                    h->d_tab_len, h->d_tab_id, h->d_tab_names};
+                    h->d_tab_len, h->d_tab_id, h->d_tab_names, h->d_x_hist, h->d_x_base, h->d_x_nbytes, h->d_x_src_off, h->d_x_len, h->d_x_dst_off,
+                    h->d_x_len32, h->d_x_pub, h->d_x_tile, h->d_x_grand};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_grand) cudaFreeHost(h->h_grand);
+    if (h->h_x) cudaFreeHost(h->h_x);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -223,13 +229,14 @@ static ck_view view_of(ck_handle* h) {
     return v;
 }
 
-static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad);
+static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad,
+                    unsigned long long* tile_sum = nullptr, unsigned long long* grand = nullptr);
 
 // decode = walk every submitted record; re-emit the ones that are valid but not canonical into the overlay
 // (count -> scan -> write) and walk those again in their canonical spelling
 static int launch_decode(ck_handle* h) {
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "vm")) ? 1 : 0; }   // development A/B switch
+    if (mode < 0) { const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "vm")) ? 1 : (e && !strcmp(e, "global")) ? 2 : 0; }   // development A/B switch
     u32 n = h->n;
     if (!n) return 0;
     ck_view v = view_of(h);
@@ -237,7 +244,8 @@ static int launch_decode(ck_handle* h) {
     {
         KTimer t(h, CK_K_WALK);
         if (mode == 1) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
-        else ck_walk_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        else if (mode == 2) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        else ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 0);
         CUDA_TRY(h, cudaGetLastError());
     }
     {
@@ -251,7 +259,8 @@ static int launch_decode(ck_handle* h) {
         ck_canon_write_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen, h->d_coff, h->d_ovl, (long long)h->max_ovl,
                                                                  h->d_ovl_off, h->d_ovl_len);
         if (mode == 1) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else ck_walk_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        else if (mode == 2) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        else ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 1);
         CUDA_TRY(h, cudaGetLastError());
     }
     return 0;
@@ -277,13 +286,15 @@ extern "C" int ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64
     return launch_decode(h);
 }
 
-static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad) {
+static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad,
+                    unsigned long long* tile_sum, unsigned long long* grand) {
     KTimer t(h, CK_K_SCAN);
+    if (!tile_sum) { tile_sum = h->d_tile_sum; grand = h->d_grand; }
     u32 ntiles = (n + CK_SCAN_TILE - 1) / CK_SCAN_TILE;
     if (n) {
-        ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum, pad);
-        ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(h->d_tile_sum, ntiles, h->d_grand);
-        ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, h->d_tile_sum, out_off, pad);
+        ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, tile_sum, pad);
+        ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(tile_sum, ntiles, grand);
+        ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, tile_sum, out_off, pad);
     }
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -488,6 +499,69 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
     }
+    return 0;
+}
+
+// multi-GPU exchange planning: see ck_xplan_*_kernel.  One host synchronisation (the all-to-all needs the split
+// sizes on the host); the scatter and the offset scan are queued behind it.
+extern "C" int ck_exchange_plan(ck_handle* h, uint32_t rank, uint32_t world, const int64_t** dev_src_off, const int64_t** dev_len,
+                                const int64_t** dev_dst_off, const uint32_t** dev_pub, int64_t* host_counts, int64_t* host_nbytes,
+                                uint32_t* n_sel) {
+    cudaSetDevice(h->device);
+    if (world < 1 || world > CK_X_MAXWORLD || rank >= world) return fail(h, "ck_exchange_plan: world must be 1..16 and rank < world");
+    u32 nb_max = (h->max_pubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
+    if (!h->d_x_hist) {
+        size_t nh = (size_t)CK_X_MAXWORLD * nb_max;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_hist, sizeof(u32) * nh));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_base, sizeof(long long) * (nh + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_nbytes, sizeof(unsigned long long) * CK_X_MAXWORLD));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_src_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_len, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_dst_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_len32, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_pub, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+        size_t nt = (nh > h->max_pubs ? nh : h->max_pubs) / CK_SCAN_TILE + 2;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_tile, sizeof(unsigned long long) * nt));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_grand, sizeof(unsigned long long)));
+        CUDA_TRY(h, cudaMallocHost((void**)&h->h_x, sizeof(long long) * (2 * CK_X_MAXWORLD + 2)));
+    }
+    u32 npubs = h->n_pubs;
+    u32 nb = (npubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
+    for (u32 d = 0; d < world; d++) { host_counts[d] = 0; host_nbytes[d] = 0; }
+    *n_sel = 0;
+    if (dev_src_off) *dev_src_off = (const int64_t*)h->d_x_src_off;
+    if (dev_len) *dev_len = (const int64_t*)h->d_x_len;
+    if (dev_dst_off) *dev_dst_off = (const int64_t*)h->d_x_dst_off;
+    if (dev_pub) *dev_pub = h->d_x_pub;
+    if (!nb) return 0;
+    u32 nh = world * nb;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_x_nbytes, 0, sizeof(unsigned long long) * CK_X_MAXWORLD, h->stream));
+        ck_xplan_count_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, rank, world, h->d_x_hist, h->d_x_nbytes);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_x_hist, nh, h->d_x_base, 0, h->d_x_tile, h->d_x_grand)) return 1;
+    // first slot of every destination (= base[d * nb]), the total, and the bytes per destination
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->h_x, sizeof(long long), h->d_x_base, sizeof(long long) * nb, sizeof(long long), world,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_x + CK_X_MAXWORLD, h->d_x_nbytes, sizeof(long long) * world, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_x + 2 * CK_X_MAXWORLD, h->d_x_grand, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    long long total = h->h_x[2 * CK_X_MAXWORLD];
+    for (u32 d = 0; d < world; d++) {
+        long long next = d + 1 < world ? h->h_x[d + 1] : total;
+        host_counts[d] = next - h->h_x[d];
+        host_nbytes[d] = h->h_x[CK_X_MAXWORLD + d];
+    }
+    *n_sel = (u32)total;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        ck_xplan_scatter_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, h->d_out_off, rank, world, h->d_x_base,
+                                                                  h->d_x_src_off, h->d_x_len, h->d_x_len32, h->d_x_pub);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (total && run_scan(h, h->d_x_len32, (u32)total, h->d_x_dst_off, 0, h->d_x_tile, h->d_x_grand)) return 1;
     return 0;
 }
 

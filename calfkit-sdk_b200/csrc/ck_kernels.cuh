@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(CK_WALK_THREADS)
 ck_walk_vm_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     // the schema bytecode and one 64-byte window per thread live in shared memory
     __shared__ u32 s_prog[CK_VM_PROG_WORDS];
-    __shared__ u32 s_win[CK_WALK_THREADS * CK_WIN_WORDS];
+    __shared__ u32 s_win[CK_WALK_THREADS * CK_VMWIN_WORDS];
     for (u32 k = threadIdx.x; k < CK_VM_PROG_WORDS; k += CK_WALK_THREADS) s_prog[k] = ck_vm_prog_dev[k];
     __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,7 +98,7 @@ ck_walk_vm_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
     else {
-        VRd r; r.init(rec, len, s_win + threadIdx.x * CK_WIN_WORDS);
+        VRd r; r.init(rec, len, s_win + threadIdx.x * CK_VMWIN_WORDS);
         AnyCtx cx;
         cx.kfill = 0;
         VmDicts dk;
@@ -108,10 +108,11 @@ ck_walk_vm_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode
     o.set(CK_COL_ERR, stop);
 }
 
-// recursive-descent walker (csrc/ck_walk.cuh).  pf: software prefetch of the record towards L2 before the
-// (strictly sequential, latency-bound) walk starts
-__global__ void __launch_bounds__(128, 8)
-ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
+// recursive-descent walker (csrc/ck_walk.cuh), one thread per record.  R = WRd: the record is staged through a
+// per-thread shared-memory window (dynamic shared memory: blockDim.x * CK_WIN_STRIDE bytes); R = GRd: plain
+// global loads (kept for A/B, CK_WALKER=global).
+template <class R>
+__device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 len; const u8* rec;
@@ -121,7 +122,7 @@ ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
     else {
-        Rd r; r.init(rec, len);
+        R r; r.init(rec, len);
         AnyCtx cx;
         cx.kfill = 0;
         // a canonicalised record the walker cannot prove stays loud (never happens by construction: hostsim fuzz)
@@ -130,6 +131,10 @@ ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);
 }
+__global__ void __launch_bounds__(CK_WALK_THREADS, 8)
+ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRd>(v, n, cols, stride, mode); }
+__global__ void __launch_bounds__(CK_WALK_THREADS, 8)
+ck_walk_global_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<GRd>(v, n, cols, stride, mode); }
 
 // ------------------------------------------------------------------------------------------------
 // canonicaliser kernels (ck_canon.cuh): one thread per record that the walker left as CK_NOT_CANONICAL.
@@ -642,6 +647,73 @@ ck_tailcall_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, co
     if (cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = i; q.topic_id = cfg.publish_topic_id; pubs[2 * i + 1] = q; nout = 2; }
     COL(CK_COL_NOUT) = nout;
 #undef COL
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU exchange planning: the keyed publishes whose partition is owned by another
+// rank (partition % world != rank) are selected and ordered by destination rank, stably, so that one
+// variable-size all-to-all can forward them.  Two passes over the publish table around one scan:
+//   count   : per block, a histogram of destinations (shared-memory atomics) -> hist[dest][block],
+//             and the bytes per destination (one global atomic per destination per block)
+//   (scan)  : exclusive scan of hist[] flattened destination-major = first output slot of every (dest, block)
+//   scatter : every selected publish finds its rank among the block's publishes for the same destination
+//             (__match_any_sync inside the warp + warp totals in shared memory) and writes its span
+// ------------------------------------------------------------------------------------------------
+#define CK_X_MAXWORLD 16
+#define CK_X_BLOCK 256
+__device__ __forceinline__ bool ck_x_foreign(const ck_pub& p, u32 rank, u32 world, u32& dest) {
+    if (p.payload == 0xffffffffu || p.has_key != 1 || p.partition < 0) return false;
+    dest = (u32)p.partition % world;
+    return dest != rank;
+}
+
+__global__ void __launch_bounds__(CK_X_BLOCK)
+ck_xplan_count_kernel(const ck_pub* __restrict__ pubs, u32 npubs, const u32* __restrict__ pay_len, u32 rank, u32 world,
+                      u32* __restrict__ hist /* [world][gridDim.x] */, unsigned long long* __restrict__ nbytes /* [world] */) {
+    __shared__ u32 s_cnt[CK_X_MAXWORLD];
+    __shared__ unsigned long long s_bytes[CK_X_MAXWORLD];
+    if (threadIdx.x < CK_X_MAXWORLD) { s_cnt[threadIdx.x] = 0; s_bytes[threadIdx.x] = 0; }
+    __syncthreads();
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 dest = 0;
+    if (i < npubs) {
+        ck_pub p = pubs[i];
+        if (ck_x_foreign(p, rank, world, dest)) { atomicAdd(&s_cnt[dest], 1u); atomicAdd(&s_bytes[dest], (unsigned long long)pay_len[p.payload]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+        hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
+        if (s_bytes[threadIdx.x]) atomicAdd(&nbytes[threadIdx.x], s_bytes[threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(CK_X_BLOCK)
+ck_xplan_scatter_kernel(const ck_pub* __restrict__ pubs, u32 npubs, const u32* __restrict__ pay_len, const long long* __restrict__ out_off,
+                        u32 rank, u32 world, const long long* __restrict__ base /* scan of hist */,
+                        long long* __restrict__ x_src_off, long long* __restrict__ x_len, u32* __restrict__ x_len32, u32* __restrict__ x_pub) {
+    __shared__ u32 s_w[CK_X_BLOCK / 32][CK_X_MAXWORLD];
+    u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < (CK_X_BLOCK / 32) * CK_X_MAXWORLD) (&s_w[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 dest = 0, rank_in_warp = 0;
+    bool sel = false;
+    ck_pub p;
+    if (i < npubs) { p = pubs[i]; sel = ck_x_foreign(p, rank, world, dest); }
+    u32 act = __ballot_sync(0xffffffffu, sel);
+    if (sel) {
+        u32 same = __match_any_sync(act, dest);
+        rank_in_warp = __popc(same & ((1u << lane) - 1u));
+        if (rank_in_warp == 0) s_w[warp][dest] = __popc(same);
+    }
+    __syncthreads();
+    if (sel) {
+        u32 before = 0;
+        for (u32 w = 0; w < warp; w++) before += s_w[w][dest];
+        long long slot = base[(size_t)dest * gridDim.x + blockIdx.x] + before + rank_in_warp;
+        u32 len = pay_len[p.payload];
+        x_src_off[slot] = out_off[p.payload]; x_len[slot] = (long long)len; x_len32[slot] = len; x_pub[slot] = i;
+    }
 }
 
 // generic span gather (used to pack cross-partition payloads for the NCCL all-to-all): one warp per span

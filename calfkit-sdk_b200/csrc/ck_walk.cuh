@@ -39,7 +39,8 @@ struct Span { u32 off, len; };
 // allocated with >= 16 bytes of tail padding and a 256 B aligned base, so aligned-down / +8 loads
 // around a record never leave the allocation.
 // -------------------------------------------------------------------------------------------------
-struct Rd {
+struct GRd {
+    static const bool kWindow = false;
     const u8* g;     // record start
     u32 n;           // record length
     const u64* wp;   // address of the cached aligned word
@@ -52,7 +53,10 @@ struct Rd {
         return *p;
 #endif
     }
-    CK_HD void init(const u8* base, u32 len) { g = base; n = len; wp = nullptr; w = 0; }
+    CK_HD void init(const u8* base, u32 len, u32 st = 0) { (void)st; g = base; n = len; wp = nullptr; w = 0; }
+    CK_HD u32 st() const { return 0; }           // reader state carried through out-of-line calls (none here)
+    CK_HD void set_st(u32) {}
+    CK_HD void invalidate() {}
 
     CK_HD u8 at(u32 pos) {           // caller guarantees pos < n
         const u8* a = g + pos;
@@ -71,7 +75,147 @@ struct Rd {
         wp = q + 1; w = hi;
         return (lo >> (8 * s)) | (hi << (64 - 8 * s));
     }
+    CK_HD void load16(u32 pos, u64& x0, u64& x1) {
+        const u8* a = g + pos;
+        u32 s = (u32)((uintptr_t)a & 7);
+        const u64* q = (const u64*)((uintptr_t)a - s);
+        u64 w0 = ld64(q), w1 = ld64(q + 1);
+        x0 = w0; x1 = w1;
+        if (s) {
+            u64 w2 = ld64(q + 2);
+            x0 = (w0 >> (8 * s)) | (w1 << (64 - 8 * s));
+            x1 = (w1 >> (8 * s)) | (w2 << (64 - 8 * s));
+        }
+    }
 };
+
+typedef GRd Rd;        // the plan / fan-out kernels read a few scattered spots of a record: plain global loads
+
+// -------------------------------------------------------------------------------------------------
+// Window reader (the walker's): each thread stages CK_WIN_BYTES of its record in shared memory with
+// 16-byte asynchronous copies (cp.async, no data registers, all chunks of a refill in flight at once)
+// and reads bytes / unaligned words from there.  Thirty-two lanes walking thirty-two different records
+// cost one L1 tag lookup per lane per *load instruction* through global memory (the measured bound of the
+// GRd walker); through shared memory a warp-wide access is one wavefront unless banks
+// collide, and the global side shrinks to len/16 chunk copies per record.  Every access checks the
+// window and refills on demand (re-centred CK_WIN_BACK bytes behind the position), so correctness does not
+// depend on access order.  The window base is the reader's state; it travels through out-of-line
+// calls by value (cores return it next to their result).
+// -------------------------------------------------------------------------------------------------
+#ifndef CK_WIN_BYTES
+#define CK_WIN_BYTES 128
+#endif
+#define CK_WIN_BACK 16
+#define CK_WIN_STRIDE (CK_WIN_BYTES + 16)     // per-thread slot; the pad spreads the slots over the banks
+#define CK_WIN_NONE 0x80000000u     // o = ap - wbase is then >= 2^31 for every position: always refills
+#if defined(__CUDA_ARCH__)
+extern __shared__ uint4 ck_win_smem[];       // blockDim.x * CK_WIN_STRIDE bytes (dynamic shared memory of the walk kernel)
+#else
+static thread_local uint8_t ck_win_host[CK_WIN_STRIDE];
+#endif
+
+// (re)load the window so that it holds [wb, wb + CK_WIN_BYTES) of the 16-byte aligned stream gb[]; chunks at or
+// beyond `lim` (the record end rounded up to 16) are not touched.  Returns wb.
+CK_HD_NOINLINE u32 ck_win_refill(const u8* gb, u32 ap, u32 lim) {
+    u32 wb = ap & ~15u;
+    wb = wb >= CK_WIN_BACK ? wb - CK_WIN_BACK : 0u;
+#if defined(__CUDA_ARCH__)
+    u32 dst = (u32)__cvta_generic_to_shared((const u8*)ck_win_smem + threadIdx.x * CK_WIN_STRIDE);
+    const u8* src = gb + wb;
+#pragma unroll
+    for (u32 k = 0; k < CK_WIN_BYTES; k += 16)
+        if (wb + k < lim) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + k), "l"(src + k) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#else
+    for (u32 k = 0; k < CK_WIN_BYTES; k += 16) if (wb + k < lim) for (u32 j = 0; j < 16; j++) ck_win_host[k + j] = gb[wb + k + j];
+#endif
+    return wb;
+}
+
+struct WRd {
+    static const bool kWindow = true;
+    const u8* g;     // record start
+    u32 n;           // record length
+    u32 wbase;       // window base in the aligned stream (multiple of 16), CK_WIN_NONE = nothing staged
+    u32 m;           // g & 15: position p of the record is byte p + m of the 16-byte aligned stream
+    const u8* wp;    // this thread's window slot
+
+    CK_HD void init(const u8* base, u32 len, u32 st = CK_WIN_NONE) {
+        g = base; n = len; wbase = st; m = (u32)((uintptr_t)base & 15);
+#if defined(__CUDA_ARCH__)
+        wp = (const u8*)ck_win_smem + threadIdx.x * CK_WIN_STRIDE;
+#else
+        wp = ck_win_host;
+#endif
+    }
+    CK_HD u32 st() const { return wbase; }
+    CK_HD void set_st(u32 s) { wbase = s; }
+    CK_HD void invalidate() { wbase = CK_WIN_NONE; }
+    CK_HD u32 mis() const { return m; }
+    CK_HD const u8* win() const { return wp; }
+    CK_HD void refill(u32 ap) { wbase = ck_win_refill(g - m, ap, (m + n + 15u) & ~15u); }
+    CK_HD u8 at(u32 pos) {           // caller guarantees pos < n
+        u32 ap = pos + mis();
+        u32 o = ap - wbase;
+        if (o >= (u32)CK_WIN_BYTES) { refill(ap); o = ap - wbase; }
+        return win()[o];
+    }
+    // 8 bytes starting at pos, little endian; bytes at/after n are unspecified
+    CK_HD u64 load8(u32 pos) {
+        u32 ap = pos + mis();
+        u32 o = ap - wbase;
+        if (o > (u32)(CK_WIN_BYTES - 12)) { refill(ap); o = ap - wbase; }
+        const u32* w = (const u32*)(win() + (o & ~3u));
+        u32 a = w[0], b = w[1], c = w[2], sh = (o & 3u) * 8u;
+#if defined(__CUDA_ARCH__)
+        u32 lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+#else
+        u32 lo = sh ? (u32)((((u64)b << 32) | a) >> sh) : a, hi = sh ? (u32)((((u64)c << 32) | b) >> sh) : b;
+#endif
+        return ((u64)hi << 32) | lo;
+    }
+    // 16 bytes starting at pos (literal compare): two words of 8
+    CK_HD void load16(u32 pos, u64& x0, u64& x1) {
+        u32 ap = pos + mis();
+        u32 o = ap - wbase;
+        if (o > (u32)(CK_WIN_BYTES - 20)) { refill(ap); o = ap - wbase; }
+        const u32* w = (const u32*)(win() + (o & ~3u));
+        u32 a = w[0], b = w[1], c = w[2], d = w[3], e = w[4], sh = (o & 3u) * 8u;
+#if defined(__CUDA_ARCH__)
+        u32 q0 = __funnelshift_r(a, b, sh), q1 = __funnelshift_r(b, c, sh), q2 = __funnelshift_r(c, d, sh), q3 = __funnelshift_r(d, e, sh);
+#else
+        u32 q0 = sh ? (u32)((((u64)b << 32) | a) >> sh) : a, q1 = sh ? (u32)((((u64)c << 32) | b) >> sh) : b;
+        u32 q2 = sh ? (u32)((((u64)d << 32) | c) >> sh) : c, q3 = sh ? (u32)((((u64)e << 32) | d) >> sh) : d;
+#endif
+        x0 = ((u64)q1 << 32) | q0; x1 = ((u64)q3 << 32) | q2;
+    }
+};
+
+// Look-ahead prefetch of the record stream into L1 (experiment knob): every lane walks its
+// own record, so almost every warp-level load has some lane missing L1; pulling the line CK_PF_DIST
+// bytes ahead turns those into hits.  CK_PF: 0 off, 1 once per 128 B line (entry lands in its first
+// 32 B), 2 unconditional, 4 = 1 with a dummy load instead of prefetch.global.L1.
+#ifndef CK_PF
+#define CK_PF 0
+#endif
+#ifndef CK_PF_DIST
+#define CK_PF_DIST 256
+#endif
+CK_HD void ck_pf(const u8* a) {
+#if defined(__CUDA_ARCH__) && CK_PF
+#if CK_PF == 2
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(a + CK_PF_DIST));
+#elif CK_PF == 4
+    if (((uintptr_t)a & 127) < 32) { unsigned d; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(d) : "l"((const void*)((uintptr_t)(a + CK_PF_DIST) & ~(uintptr_t)3))); }
+#elif CK_PF == 3
+    if (((uintptr_t)a & 31) < 16) asm volatile("prefetch.global.L1 [%0];" :: "l"(a + CK_PF_DIST));
+#else
+    if (((uintptr_t)a & 127) < 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(a + CK_PF_DIST));
+#endif
+#else
+    (void)a;
+#endif
+}
 
 #define CK_REP8(b) ((u64)(b) * 0x0101010101010101ull)
 
@@ -92,26 +236,28 @@ CK_HD u32 ck_ctz64(u64 x) {
 // fetch + compare lives in two small out-of-line functions (8 and 16 bytes per call) so that the
 // ~150 literal sites of the schema cost a handful of instructions each instead of an inlined
 // unaligned-load sequence (instruction-cache footprint).
-CK_HD_NOINLINE bool ck_match8_core(const u8* g, u32 pos, u64 want, u64 mask) {
-    const u8* a = g + pos;
-    u32 s = (u32)((uintptr_t)a & 7);
-    const u64* q = (const u64*)((uintptr_t)a - s);
-    u64 got = Rd::ld64(q);
-    if (s) got = (got >> (8 * s)) | (Rd::ld64(q + 1) << (64 - 8 * s));
-    return ((got ^ want) & mask) == 0;
+// Out-of-line cores return the reader state next to their result (see WRd): match cores as
+// (state & ~1) | ok, the others as state << 32 | result with result 0 = failure (state then unspecified:
+// the caller invalidates its reader).
+#define CK_RET(res) (((u64)r.st() << 32) | (u64)(u32)(res))
+#define CK_CALL(e, call) u64 e##64 = (call); u32 e = (u32)e##64; if (!e) { r.invalidate(); return false; } r.set_st((u32)(e##64 >> 32))
+
+template <class R>
+CK_HD_NOINLINE u32 ck_match8_core(const u8* g, u32 n, u32 pos, u32 st, u64 want, u32 nb) {
+    R r; r.init(g, n, st);
+    ck_pf(g + pos);
+    u64 got = r.load8(pos);
+    u64 mask = ~0ull >> (8 * (8 - nb));
+    return (r.st() & ~1u) | (u32)(((got ^ want) & mask) == 0);
 }
-CK_HD_NOINLINE bool ck_match16_core(const u8* g, u32 pos, u64 want0, u64 want1, u64 mask1) {
-    const u8* a = g + pos;
-    u32 s = (u32)((uintptr_t)a & 7);
-    const u64* q = (const u64*)((uintptr_t)a - s);
-    u64 w0 = Rd::ld64(q), w1 = Rd::ld64(q + 1);
-    u64 g0 = w0, g1 = w1;
-    if (s) {
-        u64 w2 = Rd::ld64(q + 2);
-        g0 = (w0 >> (8 * s)) | (w1 << (64 - 8 * s));
-        g1 = (w1 >> (8 * s)) | (w2 << (64 - 8 * s));
-    }
-    return (g0 == want0) & (((g1 ^ want1) & mask1) == 0);
+template <class R>
+CK_HD_NOINLINE u32 ck_match16_core(const u8* g, u32 n, u32 pos, u32 st, u64 want0, u64 want1, u32 nb1) {
+    R r; r.init(g, n, st);
+    ck_pf(g + pos);
+    u64 g0, g1;
+    r.load16(pos, g0, g1);
+    u64 mask1 = ~0ull >> (8 * (8 - nb1));
+    return (r.st() & ~1u) | (u32)((g0 == want0) & (((g1 ^ want1) & mask1) == 0));
 }
 CK_HD u64 ck_lit_word(const char* lit, u32 L, u32 k) {      // bytes [k, k+8) of the literal, zero padded
     u64 w = 0;
@@ -119,15 +265,38 @@ CK_HD u64 ck_lit_word(const char* lit, u32 L, u32 k) {      // bytes [k, k+8) of
     for (u32 j = 0; j < 8; j++) if (k + j < L) w |= (u64)(u8)lit[k + j] << (8 * j);
     return w;
 }
-CK_HD u64 ck_lit_mask(u32 L, u32 k) { return (L - k >= 8) ? ~0ull : (~0ull >> (8 * (8 - (L - k)))); }
-CK_HD bool ck_match(Rd& r, u32& pos, const char* lit, u32 L) {
+CK_HD u32 ck_lit_nb(u32 L, u32 k) { return (L - k >= 8) ? 8u : (L - k); }      // valid bytes of the word at k
+#ifndef CK_MATCH_INLINE
+#define CK_MATCH_INLINE 1
+#endif
+template <class R>
+CK_HD bool ck_match(R& r, u32& pos, const char* lit, u32 L) {
     if (pos + L > r.n) return false;
     u32 k = 0;
+#if CK_MATCH_INLINE
+    if (R::kWindow) {          // shared-memory reads are short enough to inline: no call, no parameter traffic
+#pragma unroll
+        for (; k + 8 < L; k += 16) {
+            u64 g0, g1;
+            r.load16(pos + k, g0, g1);
+            if (!((g0 == ck_lit_word(lit, L, k)) & (((g1 ^ ck_lit_word(lit, L, k + 8)) & (~0ull >> (8 * (8 - ck_lit_nb(L, k + 8))))) == 0))) return false;
+        }
+        if (k < L) { if (((r.load8(pos + k) ^ ck_lit_word(lit, L, k)) & (~0ull >> (8 * (8 - ck_lit_nb(L, k))))) != 0) return false; }
+        pos += L;
+        return true;
+    }
+#endif
 #pragma unroll
     for (; k + 8 < L; k += 16) {
-        if (!ck_match16_core(r.g, pos + k, ck_lit_word(lit, L, k), ck_lit_word(lit, L, k + 8), ck_lit_mask(L, k + 8))) return false;
+        u32 s = ck_match16_core<R>(r.g, r.n, pos + k, r.st(), ck_lit_word(lit, L, k), ck_lit_word(lit, L, k + 8), ck_lit_nb(L, k + 8));
+        r.set_st(s & ~1u);
+        if (!(s & 1u)) return false;
     }
-    if (k < L) { if (!ck_match8_core(r.g, pos + k, ck_lit_word(lit, L, k), ck_lit_mask(L, k))) return false; }
+    if (k < L) {
+        u32 s = ck_match8_core<R>(r.g, r.n, pos + k, r.st(), ck_lit_word(lit, L, k), ck_lit_nb(L, k));
+        r.set_st(s & ~1u);
+        if (!(s & 1u)) return false;
+    }
     pos += L;
     return true;
 }
@@ -140,7 +309,8 @@ CK_HD bool ck_match(Rd& r, u32& pos, const char* lit, u32 L) {
 // raw bytes >= 0x20 except " and \, valid UTF-8 (no surrogates / overlongs / > U+10FFFF),
 // escapes \" \\ \n \t \r \b \f, and \u00XX (lower-case hex) only for the other controls.
 // -------------------------------------------------------------------------------------------------
-CK_HD bool ck_utf8_seq(Rd& r, u32& pos) {       // pos at a byte >= 0x80
+template <class R>
+CK_HD bool ck_utf8_seq(R& r, u32& pos) {       // pos at a byte >= 0x80
     u8 c = r.at(pos);
     u32 need; u8 lo = 0x80, hi = 0xBF;
     if (c >= 0xC2 && c <= 0xDF) need = 1;
@@ -162,19 +332,26 @@ CK_HD bool ck_utf8_seq(Rd& r, u32& pos) {       // pos at a byte >= 0x80
 
 // returns the position just after the closing quote, 0 on failure.  One out-of-line copy: the
 // walker calls it ~100 times per record and the code must stay inside the instruction cache.
-CK_HD_NOINLINE u32 ck_string_core(const u8* g, u32 n, u32 pos) {
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_string_core(const u8* g, u32 n, u32 pos, u32 st) {
+    R r; r.init(g, n, st);
     if (!(pos < r.n) || r.at(pos) != '"') return 0;
+    ck_pf(g + pos);
     pos++;
     for (;;) {
         if (pos >= r.n) return false;
         u64 x = r.load8(pos);
+#if CK_PF == 2 || CK_PF == 3
+        if (((uintptr_t)(g + pos) & 31) < 8) ck_pf((const u8*)((uintptr_t)(g + pos) & ~(uintptr_t)31));
+#elif CK_PF
+        if (((uintptr_t)(g + pos) & 127) < 8) ck_pf((const u8*)((uintptr_t)(g + pos) & ~(uintptr_t)127));
+#endif
         u64 special = (x & CK_REP8(0x80)) | ck_haszero(x ^ CK_REP8('"')) | ck_haszero(x ^ CK_REP8('\\')) | ck_lt20(x);
         if (special == 0) { pos += 8; continue; }
         pos += ck_ctz64(special) >> 3;
         if (pos >= r.n) return false;
         u8 c = r.at(pos);
-        if (c == '"') return pos + 1;
+        if (c == '"') return CK_RET(pos + 1);
         if (c == '\\') {
             if (pos + 1 >= r.n) return false;
             u8 e = r.at(pos + 1);
@@ -197,16 +374,18 @@ CK_HD_NOINLINE u32 ck_string_core(const u8* g, u32 n, u32 pos) {
     }
 }
 
-CK_HD bool ck_string(Rd& r, u32& pos, Span& out) {
-    u32 e = ck_string_core(r.g, r.n, pos);
-    if (!e) return false;
+template <class R>
+CK_HD bool ck_string(R& r, u32& pos, Span& out) {
+    CK_CALL(e, ck_string_core<R>(r.g, r.n, pos, r.st()));
     out.off = pos + 1; out.len = e - pos - 2; pos = e;
     return true;
 }
 
-CK_HD bool ck_null(Rd& r, u32& pos) { return M("null"); }
+template <class R>
+CK_HD bool ck_null(R& r, u32& pos) { return M("null"); }
 
-CK_HD bool ck_string_or_null(Rd& r, u32& pos, Span& out) {
+template <class R>
+CK_HD bool ck_string_or_null(R& r, u32& pos, Span& out) {
     if (PEEK('n')) { out.off = pos; out.len = 0; return ck_null(r, pos); }
     return ck_string(r, pos, out);
 }
@@ -217,8 +396,9 @@ CK_HD bool ck_string_or_null(Rd& r, u32& pos, Span& out) {
 // -?INT.FRAC with <= 15 significant digits, no trailing fractional zero (except the single ".0"),
 // magnitude in [1e-5, 1e16)  (DBL_DIG argument, DESIGN.md §canonical numbers).
 // -------------------------------------------------------------------------------------------------
-CK_HD_NOINLINE u32 ck_number_core(const u8* g, u32 n, u32 pos, bool allow_int, bool allow_float) {
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allow_int, bool allow_float) {
+    R r; r.init(g, n, st);
     u32 p = pos;
     bool neg = false;
     if (p < r.n && r.at(p) == '-') { neg = true; p++; }
@@ -259,14 +439,14 @@ CK_HD_NOINLINE u32 ck_number_core(const u8* g, u32 n, u32 pos, bool allow_int, b
         u32 x = 0, xl = 0;
         while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; x = x * 10 + (u32)(d - '0'); p++; if (++xl > 3) return false; }
         if (x > 290 || (sg == '-' ? x < 6 : x < 16)) return false;
-        return p;
+        return CK_RET(p);
     }
     if (p < r.n && r.at(p) == 'E') return false;
     if (!is_float) {
         if (!allow_int) return false;
         if (neg && int_zero) return false;          // "-0" re-emits as "0"
         if (int_len > 4000) return false;           // CPython int<->str digit limit is 4300
-        return p;
+        return CK_RET(p);
     }
     if (!allow_float) return false;
     if (int_len > 16) return false;
@@ -288,11 +468,11 @@ CK_HD_NOINLINE u32 ck_number_core(const u8* g, u32 n, u32 pos, bool allow_int, b
         else { if (lz > 4) return false; sig = frac_len - lz; }             // < 1e-5 prints as 1e-6 ...
     }
     if (sig > 15) return false;
-    return p;
+    return CK_RET(p);
 }
-CK_HD bool ck_number(Rd& r, u32& pos, bool allow_int, bool allow_float) {
-    u32 e = ck_number_core(r.g, r.n, pos, allow_int, allow_float);
-    if (!e) return false;
+template <class R>
+CK_HD bool ck_number(R& r, u32& pos, bool allow_int, bool allow_float) {
+    CK_CALL(e, ck_number_core<R>(r.g, r.n, pos, r.st(), allow_int, allow_float));
     pos = e;
     return true;
 }
@@ -314,15 +494,17 @@ struct AnyCtx {
     u32 kfill;
 };
 
-CK_HD u32 ck_hash_span(Rd& r, u32 off, u32 len) {
+template <class R>
+CK_HD u32 ck_hash_span(R& r, u32 off, u32 len) {
     u32 h = 2166136261u ^ len;
     for (u32 i = 0; i < len; i++) h = (h ^ r.at(off + i)) * 16777619u;
     return h;
 }
 
 // base_depth: nesting level of the value inside the document (root object = depth 1)
-CK_HD_NOINLINE u32 ck_any_core(const u8* g, u32 n, u32 pos, u32 base_depth, AnyCtx* cxp) {
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_any_core(const u8* g, u32 n, u32 pos, u32 st, u32 base_depth, AnyCtx* cxp) {
+    R r; r.init(g, n, st);
     AnyCtx& cx = *cxp;
     u32 depth = 0;
     cx.kfill = 0;
@@ -354,7 +536,7 @@ CK_HD_NOINLINE u32 ck_any_core(const u8* g, u32 n, u32 pos, u32 base_depth, AnyC
             if (opened) { in_obj = (cx.kind[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1; opened = false;
                           if (!in_obj) break; /* array: first element */ }
             else {
-                if (depth == 0) return pos;
+                if (depth == 0) return CK_RET(pos);
                 in_obj = (cx.kind[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1;
                 if (pos >= r.n) return false;
                 u8 d = r.at(pos);
@@ -376,28 +558,32 @@ CK_HD_NOINLINE u32 ck_any_core(const u8* g, u32 n, u32 pos, u32 base_depth, AnyC
     }
 }
 
-CK_HD bool ck_any(Rd& r, u32& pos, u32 base_depth, AnyCtx& cx) {
-    u32 e = ck_any_core(r.g, r.n, pos, base_depth, &cx);
-    if (!e) return false;
+template <class R>
+CK_HD bool ck_any(R& r, u32& pos, u32 base_depth, AnyCtx& cx) {
+    CK_CALL(e, ck_any_core<R>(r.g, r.n, pos, r.st(), base_depth, &cx));
     pos = e;
     return true;
 }
-CK_HD bool ck_any_obj(Rd& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('{') && ck_any(r, pos, d, cx); }
-CK_HD bool ck_any_obj_or_null(Rd& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('n') ? ck_null(r, pos) : ck_any_obj(r, pos, d, cx); }
+template <class R>
+CK_HD bool ck_any_obj(R& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('{') && ck_any(r, pos, d, cx); }
+template <class R>
+CK_HD bool ck_any_obj_or_null(R& r, u32& pos, u32 d, AnyCtx& cx) { return PEEK('n') ? ck_null(r, pos) : ck_any_obj(r, pos, d, cx); }
 
 // -------------------------------------------------------------------------------------------------
 // datetime: the spellings pydantic re-emits unchanged:
 //   YYYY-MM-DDTHH:MM:SS[.ffffff](Z | +HH:MM | -HH:MM | <naive>)   fraction: 6 digits, not 000000;
 //   offset != 00:00 (that prints as Z); calendar-valid date; year >= 1.
 // -------------------------------------------------------------------------------------------------
-CK_HD bool ck_2d(Rd& r, u32 p, u32& v) {
+template <class R>
+CK_HD bool ck_2d(R& r, u32 p, u32& v) {
     u8 a = r.at(p), b = r.at(p + 1);
     if (a < '0' || a > '9' || b < '0' || b > '9') return false;
     v = (u32)(a - '0') * 10 + (u32)(b - '0');
     return true;
 }
-CK_HD_NOINLINE u32 ck_datetime_core(const u8* g, u32 n, u32 pos) {
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_datetime_core(const u8* g, u32 n, u32 pos, u32 st) {
+    R r; r.init(g, n, st);
     u32 p = pos;
     if (p + 21 > r.n) return false;                 // "YYYY-MM-DDTHH:MM:SS" + quotes
     if (r.at(p) != '"') return false;
@@ -432,17 +618,19 @@ CK_HD_NOINLINE u32 ck_datetime_core(const u8* g, u32 n, u32 pos) {
         c = r.at(p);
     }
     if (c != '"') return false;
-    return p + 1;
+    return CK_RET(p + 1);
 }
-CK_HD bool ck_datetime(Rd& r, u32& pos) {
-    u32 e = ck_datetime_core(r.g, r.n, pos);
-    if (!e) return false;
+template <class R>
+CK_HD bool ck_datetime(R& r, u32& pos) {
+    CK_CALL(e, ck_datetime_core<R>(r.g, r.n, pos, r.st()));
     pos = e;
     return true;
 }
-CK_HD bool ck_datetime_or_null(Rd& r, u32& pos) { return PEEK('n') ? ck_null(r, pos) : ck_datetime(r, pos); }
+template <class R>
+CK_HD bool ck_datetime_or_null(R& r, u32& pos) { return PEEK('n') ? ck_null(r, pos) : ck_datetime(r, pos); }
 
-CK_HD bool ck_bool(Rd& r, u32& pos) { return PEEK('t') ? M("true") : M("false"); }
+template <class R>
+CK_HD bool ck_bool(R& r, u32& pos) { return PEEK('t') ? M("true") : M("false"); }
 
 // -------------------------------------------------------------------------------------------------
 // Typed pieces of the Envelope schema, in canonical key order.
@@ -452,7 +640,8 @@ struct ToolCallSpans { Span tool_name, args, tool_call_id; };
 
 // ToolCallPart / BuiltinToolCallPart (reference _vendor/pydantic_ai/messages.py:1187-1283)
 // returns 1 = tool-call, 2 = builtin-tool-call, 0 = no match
-CK_HD u32 ck_tool_call_part(Rd& r, u32& pos, u32 d, AnyCtx& cx, ToolCallSpans& o) {
+template <class R>
+CK_HD u32 ck_tool_call_part(R& r, u32& pos, u32 d, AnyCtx& cx, ToolCallSpans& o) {
     Span t;
     if (!M("{\"tool_name\":") || !ck_string(r, pos, o.tool_name) || !M(",\"args\":")) return 0;
     o.args.off = pos;
@@ -470,7 +659,8 @@ CK_HD u32 ck_tool_call_part(Rd& r, u32& pos, u32 d, AnyCtx& cx, ToolCallSpans& o
 // message parts.  Returns 1 for a request-side part, 2 for a response-side part, 0 = no match.
 // (request: system-prompt / user-prompt / tool-return / retry-prompt, messages.py:112,739,883,918;
 //  response: text / tool-call / builtin-tool-call / builtin-tool-return / thinking, :1059-1283)
-CK_HD u32 ck_message_part(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+template <class R>
+CK_HD u32 ck_message_part(R& r, u32& pos, u32 d, AnyCtx& cx) {
     Span t;
     if (M("{\"content\":")) {
         // content-first parts: system-prompt, user-prompt, retry-prompt (request) | text, thinking (response)
@@ -525,7 +715,8 @@ CK_HD u32 ck_message_part(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
 }
 
 // RequestUsage (reference _vendor/pydantic_ai/usage.py)
-CK_HD bool ck_usage(Rd& r, u32& pos, AnyCtx& cx) {
+template <class R>
+CK_HD bool ck_usage(R& r, u32& pos, AnyCtx& cx) {
     Span t;
     if (!M("{\"input_tokens\":") || !ck_number(r, pos, true, false) || !M(",\"cache_write_tokens\":") || !ck_number(r, pos, true, false) ||
         !M(",\"cache_read_tokens\":") || !ck_number(r, pos, true, false) || !M(",\"output_tokens\":") || !ck_number(r, pos, true, false) ||
@@ -549,8 +740,9 @@ CK_HD bool ck_usage(Rd& r, u32& pos, AnyCtx& cx) {
 
 // ModelMessage = ModelRequest | ModelResponse (messages.py:1014-1041, :1292-1345, :1554).
 // returns 1 = request, 2 = response, 0 = no match
-CK_HD_NOINLINE u32 ck_message_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* cxp) {   // -> end | kind << 30
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_message_core(const u8* g, u32 n, u32 pos, u32 st, u32 d, AnyCtx* cxp) {   // -> end | kind << 30
+    R r; r.init(g, n, st);
     AnyCtx& cx = *cxp;
     Span t;
     if (!M("{\"parts\":[")) return 0;
@@ -586,17 +778,18 @@ CK_HD_NOINLINE u32 ck_message_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* c
             !ck_any_obj_or_null(r, pos, d + 1, cx) || !M("}")) return 0;
         kind = 2;
     }
-    return pos | (kind << 30);
+    return CK_RET(pos | (kind << 30));
 }
-CK_HD u32 ck_message(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
-    u32 e = ck_message_core(r.g, r.n, pos, d, &cx);
-    if (!e) return 0;
+template <class R>
+CK_HD u32 ck_message(R& r, u32& pos, u32 d, AnyCtx& cx) {
+    CK_CALL(e, ck_message_core<R>(r.g, r.n, pos, r.st(), d, &cx));
     pos = e & 0x3fffffffu;
     return e >> 30;
 }
 
 // ToolDefinition (reference _vendor/pydantic_ai/tools.py:474-540)
-CK_HD bool ck_tool_definition(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+template <class R>
+CK_HD bool ck_tool_definition(R& r, u32& pos, u32 d, AnyCtx& cx) {
     Span t;
     if (!M("{\"name\":") || !ck_string(r, pos, t) || !M(",\"parameters_json_schema\":") || !ck_any_obj(r, pos, d + 1, cx) ||
         !M(",\"description\":") || !ck_string_or_null(r, pos, t) || !M(",\"outer_typed_dict_key\":") || !ck_string_or_null(r, pos, t) ||
@@ -610,11 +803,12 @@ CK_HD bool ck_tool_definition(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
 }
 
 // OverridesState | null (reference calfkit/models/state.py:22-26, node_schema.py:6-21)
-CK_HD_NOINLINE u32 ck_overrides_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* cxp) {
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_overrides_core(const u8* g, u32 n, u32 pos, u32 st, u32 d, AnyCtx* cxp) {
+    R r; r.init(g, n, st);
     AnyCtx& cx = *cxp;
     Span t;
-    if (PEEK('n')) { if (!ck_null(r, pos)) return 0; return pos; }
+    if (PEEK('n')) { if (!ck_null(r, pos)) return 0; return CK_RET(pos); }
     if (!M("{\"override_agent_tools\":")) return false;
     if (PEEK('n')) { if (!ck_null(r, pos)) return false; }
     else {
@@ -632,17 +826,18 @@ CK_HD_NOINLINE u32 ck_overrides_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx*
         if (!M("]")) return false;
     }
     if (!M("}")) return 0;
-    return pos;
+    return CK_RET(pos);
 }
-CK_HD bool ck_overrides_or_null(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
-    u32 e = ck_overrides_core(r.g, r.n, pos, d, &cx);
-    if (!e) return false;
+template <class R>
+CK_HD bool ck_overrides_or_null(R& r, u32& pos, u32 d, AnyCtx& cx) {
+    CK_CALL(e, ck_overrides_core<R>(r.g, r.n, pos, r.st(), d, &cx));
     pos = e;
     return true;
 }
 
 // final_output_parts element (reference calfkit/models/payload.py:6-35): `kind` comes first
-CK_HD bool ck_content_part(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
+template <class R>
+CK_HD bool ck_content_part(R& r, u32& pos, u32 d, AnyCtx& cx) {
     Span t;
     if (!M("{\"kind\":\"")) return false;
     if (M("text\",\"text\":")) {
@@ -665,7 +860,8 @@ CK_HD bool ck_content_part(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
 }
 
 // skip one already-validated canonical value (used for second looks at spans proven canonical)
-CK_HD void ck_skip_value(Rd& r, u32& pos) {
+template <class R>
+CK_HD void ck_skip_value(R& r, u32& pos) {
     u32 depth = 0;
     for (;;) {
         if (pos >= r.n) return;
@@ -691,21 +887,22 @@ CK_HD void ck_skip_value(Rd& r, u32& pos) {
 // `kind`, then `part_kind`) with an `| Any` fallback (reference models/state.py:70,
 // _vendor/pydantic_ai/tools.py:189-210).  A value is a fixed point if it is the canonical form of
 // its tagged model, or if it carries no such tag and is generically canonical.
-CK_HD_NOINLINE u32 ck_tool_result_core(const u8* g, u32 n, u32 pos, u32 d, AnyCtx* cxp) {
-    Rd r; r.init(g, n);
+template <class R>
+CK_HD_NOINLINE u64 ck_tool_result_core(const u8* g, u32 n, u32 pos, u32 st, u32 d, AnyCtx* cxp) {
+    R r; r.init(g, n, st);
     AnyCtx& cx = *cxp;
     Span t;
     u32 start = pos;
     if (PEEK('{')) {
         if (M("{\"return_value\":")) {
             if (ck_any(r, pos, d + 1, cx) && M(",\"content\":") && ck_string_or_null(r, pos, t) && M(",\"metadata\":") &&
-                ck_any(r, pos, d + 1, cx) && M(",\"kind\":\"tool-return\"}")) return pos;
+                ck_any(r, pos, d + 1, cx) && M(",\"kind\":\"tool-return\"}")) return CK_RET(pos);
         } else if (M("{\"message\":")) {
-            if (ck_string(r, pos, t) && M(",\"kind\":\"model-retry\"}")) return pos;
+            if (ck_string(r, pos, t) && M(",\"kind\":\"model-retry\"}")) return CK_RET(pos);
         } else if (M("{\"content\":")) {
             if (ck_string(r, pos, t) && M(",\"tool_name\":") && ck_string_or_null(r, pos, t) && M(",\"tool_call_id\":") &&
                 ck_string(r, pos, t) && M(",\"timestamp\":") && ck_datetime(r, pos) && M(",\"part_kind\":\"retry-prompt\"}")) {
-                return pos;
+                return CK_RET(pos);
             }
         }
         // not the canonical form of a tagged model: generic value, provided it carries no tag
@@ -733,14 +930,14 @@ CK_HD_NOINLINE u32 ck_tool_result_core(const u8* g, u32 n, u32 pos, u32 d, AnyCt
             if (p < end && r.at(p) == ',') p++;
         }
         if (have_kind ? tagged : part_tagged) return false;   // would be validated as the model: not proven here
-        return end;
+        return CK_RET(end);
     }
     if (!ck_any(r, pos, d, cx)) return 0;
-    return pos;
+    return CK_RET(pos);
 }
-CK_HD bool ck_tool_result_value(Rd& r, u32& pos, u32 d, AnyCtx& cx) {
-    u32 e = ck_tool_result_core(r.g, r.n, pos, d, &cx);
-    if (!e) return false;
+template <class R>
+CK_HD bool ck_tool_result_value(R& r, u32& pos, u32 d, AnyCtx& cx) {
+    CK_CALL(e, ck_tool_result_core<R>(r.g, r.n, pos, r.st(), d, &cx));
     pos = e;
     return true;
 }
@@ -757,7 +954,8 @@ struct WalkOut {
 
 #define SETSPAN(COL, a, b) do { o.set(COL, (a)); o.set(COL + 1, (b) - (a)); } while (0)
 
-CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
+template <class R>
+CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     u32 pos = 0;
     Span t;
     stop = 0;
@@ -766,6 +964,8 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     // walk without scanning the dicts again
     u32 tc_kh[CK_DICT_KEYS], tc_koff[CK_DICT_KEYS], tc_n = 0;     // key length is re-derived from the closing quote
     u32 tr_kh[CK_DICT_KEYS], tr_koff[CK_DICT_KEYS], tr_n = 0;
+    ToolCallSpans first_tc = {{0, 0}, {0, 0}, {0, 0}};
+    u32 first_tc0 = 0, first_tc1 = 0, first_tr0 = 0, first_tr1 = 0;
 #define FAIL do { stop = pos; return false; } while (0)
     // ---- context.state ---------------------------------------------------------------------
     if (!M("{\"context\":{\"state\":{\"tool_calls\":{")) FAIL;
@@ -780,7 +980,10 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             if (tc_n >= CK_DICT_KEYS) FAIL;
             tc_kh[tc_n] = h; tc_koff[tc_n] = t.off; tc_n++;
             ToolCallSpans tc;
-            if (!M(":") || ck_tool_call_part(r, pos, 5, cx, tc) != 1) FAIL;
+            if (!M(":")) FAIL;
+            u32 v0 = pos;
+            if (ck_tool_call_part(r, pos, 5, cx, tc) != 1) FAIL;
+            if (tc_n == 1) { first_tc = tc; first_tc0 = v0; first_tc1 = pos; }      // the common single-call case needs no second look
             if (PEEK(',')) { pos++; continue; }
             break;
         }
@@ -797,7 +1000,10 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             for (u32 k = 0; k < tr_n; k++) if (tr_kh[k] == h) FAIL;
             if (tr_n >= CK_DICT_KEYS) FAIL;
             tr_kh[tr_n] = h; tr_koff[tr_n] = t.off; tr_n++;
-            if (!M(":") || !ck_tool_result_value(r, pos, 5, cx)) FAIL;
+            if (!M(":")) FAIL;
+            u32 v0 = pos;
+            if (!ck_tool_result_value(r, pos, 5, cx)) FAIL;
+            if (tr_n == 1) { first_tr0 = v0; first_tr1 = pos; }
             if (PEEK(',')) { pos++; continue; }
             break;
         }
@@ -927,14 +1133,16 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     Span tn = {0, 0}, ar = {0, 0};
     if (nframes > 0 && top_nargs == 2 && (top_kinds & 1u)) {
         u32 h = ck_hash_span(r, top_a0.off, top_a0.len);
+        GRd gr; gr.init(r.g, r.n);          // byte compares of two far-apart spans: plain global loads
         // the hash covers the length, so a hit is (almost surely) the key: verify bytes + closing quote
         for (u32 k = 0; k < tc_n; k++) {
             if (tc_kh[k] != h) continue;
             u32 ko = tc_koff[k];
-            if (ko + top_a0.len >= r.n || r.at(ko + top_a0.len) != '"') continue;
+            if (ko + top_a0.len >= r.n || gr.at(ko + top_a0.len) != '"') continue;
             bool eq = true;
-            for (u32 b = 0; b < top_a0.len; b++) if (r.at(ko + b) != r.at(top_a0.off + b)) { eq = false; break; }
+            for (u32 b = 0; b < top_a0.len; b++) if (gr.at(ko + b) != gr.at(top_a0.off + b)) { eq = false; break; }
             if (!eq) continue;
+            if (k == 0) { call0 = first_tc0; call1 = first_tc1; tn = first_tc.tool_name; ar = first_tc.args; break; }
             u32 p2 = ko + top_a0.len + 2;
             call0 = p2;
             ToolCallSpans tcs;
@@ -945,10 +1153,11 @@ CK_HD bool ck_walk_envelope(Rd& r, WalkOut& o, AnyCtx& cx, u32& stop) {
         for (u32 k = 0; k < tr_n; k++) {
             if (tr_kh[k] != h) continue;
             u32 ko = tr_koff[k];
-            if (ko + top_a0.len >= r.n || r.at(ko + top_a0.len) != '"') continue;
+            if (ko + top_a0.len >= r.n || gr.at(ko + top_a0.len) != '"') continue;
             bool eq = true;
-            for (u32 b = 0; b < top_a0.len; b++) if (r.at(ko + b) != r.at(top_a0.off + b)) { eq = false; break; }
+            for (u32 b = 0; b < top_a0.len; b++) if (gr.at(ko + b) != gr.at(top_a0.off + b)) { eq = false; break; }
             if (!eq) continue;
+            if (k == 0) { res0 = first_tr0; res1 = first_tr1; break; }
             u32 p2 = ko + top_a0.len + 2;
             res0 = p2;
             ck_tool_result_value(r, p2, 5, cx);

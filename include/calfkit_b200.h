@@ -93,6 +93,15 @@ int  ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uint32_t max_
 /* TailCall to the agent's own topic (all requested tools invalid -> retry, agent.py:171-175;
  * nodes/base.py:120-136): the current frame is replaced by a fresh one inheriting its callback_topic. */
 int  ck_tailcall_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed);
+/* multi-GPU exchange planning (records shard by Kafka partition across the GPUs of a box; reference analogue:
+ * producing to a topic-partition another worker process consumes, nodes/base.py:82-87 key=correlation_id).  Selects the
+ * keyed publishes whose partition % world != rank, ordered by destination rank (stable), into library-owned device
+ * arrays: payload span in the output buffer (src_off, len), offset in the packed send buffer (dst_off, exclusive
+ * scan of len) and the index of the publish (pub).  host_counts / host_nbytes [world]: payloads and bytes per
+ * destination (the all-to-all split sizes).  Waits for the stream once. */
+int  ck_exchange_plan(ck_handle* h, uint32_t rank, uint32_t world, const int64_t** dev_src_off, const int64_t** dev_len,
+                      const int64_t** dev_dst_off, const uint32_t** dev_pub, int64_t* host_counts, int64_t* host_nbytes,
+                      uint32_t* n_sel);
 /* copy n spans src[src_off[i] .. +src_len[i]) -> dst[dst_off[i] ..) on the handle's stream (device pointers);
  * used to pack cross-partition payloads before the NCCL all-to-all */
 int  ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64_t* dev_src_off, const int64_t* dev_src_len,

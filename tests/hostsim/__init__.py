@@ -31,6 +31,8 @@ def lib():
         _lib = ctypes.CDLL(build())
         _lib.ck_host_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_walk.restype = ctypes.c_int
+        _lib.ck_host_walk_global.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
+        _lib.ck_host_walk_global.restype = ctypes.c_int
         _lib.ck_host_num_cols.restype = ctypes.c_int
         _lib.ck_host_vm_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_vm_walk.restype = ctypes.c_int
@@ -44,6 +46,14 @@ def walk(payload: bytes):
     L = lib()
     cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
     ok = L.ck_host_walk(payload, len(payload), cols.ctypes.data)
+    return bool(ok), cols
+
+
+def walk_global(payload: bytes):
+    """the same walker over the global-load reader (GRd): -> (accepted, cols)"""
+    L = lib()
+    cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
+    ok = L.ck_host_walk_global(payload, len(payload), cols.ctypes.data)
     return bool(ok), cols
 
 

@@ -370,3 +370,28 @@ def test_noncanonical_inputs_are_canonicalised_on_device(engine):
             assert st[i] == cls, (i, st[i], cls, r[:120])
     assert k == len(pubs)
     assert out.overlay is not None and (out.overlay[1] >= 0).sum() >= 40
+
+
+def test_exchange_plan_kernels_match_tensor_plan(engine):
+    """ck_exchange_plan (histogram -> scan -> stable scatter -> scan) against the device-agnostic tensor plan that
+    the world-size-2 gloo test covers (calfkit/engine/exchange.py), on a real publish table, for every rank of
+    several world sizes."""
+    import torch
+    from calfkit import synth
+    from calfkit.engine._lib import PUB_DTYPE
+    from calfkit.engine.exchange import plan_exchange, plan_exchange_device
+    recs = synth.tool_events(3000, seed=21) + synth.mixed_events(200, seed=22)
+    b = synth.pack(recs)
+    out = engine.run_tool_batch(b.data, b.offsets)
+    dev = torch.device("cuda", 0)
+    pubs = torch.from_numpy(out.pubs.view(np.int32).reshape(-1, PUB_DTYPE.itemsize // 4).copy()).to(dev)
+    off = torch.from_numpy(out.out_off.astype(np.int64)).to(dev)
+    ln = torch.from_numpy(out.out_len.astype(np.int32)).to(dev)
+    for world in (1, 2, 3, 8):
+        for rank in range(world):
+            want = plan_exchange(pubs, off, ln, rank, world)
+            got = plan_exchange_device(engine, rank, world, dev)
+            assert got.counts.tolist() == want.counts.tolist() and got.nbytes.tolist() == want.nbytes.tolist()
+            assert got.sel.to(torch.int64).tolist() == want.sel.tolist()
+            assert got.src_off.tolist() == want.src_off.tolist() and got.lens.tolist() == want.lens.tolist()
+            assert got.dst_off.tolist() == want.dst_off.tolist()

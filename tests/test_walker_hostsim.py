@@ -85,7 +85,7 @@ def test_table_driven_walker_equals_recursive_walker():
     """csrc/ck_vm.cuh (bytecode interpreter, the one the GPU runs) against csrc/ck_walk.cuh (recursive
     descent, the one fuzzed against pydantic above): same verdict and same columns on every input."""
     from calfkit import synth
-    from hostsim import vm_walk
+    from hostsim import vm_walk, walk_global
     rng = random.Random(11)
     seeds = [as_bytes(c["input"]) for c in golden("codec.json")] + [as_bytes(c["input"]) for c in golden("tool_node.json")]
     seeds += synth.tool_events(30, seed=1) + synth.tool_events(10, seed=2, size=None, full_history=True) + \
@@ -95,7 +95,9 @@ def test_table_driven_walker_equals_recursive_walker():
     def same(b):
         a1, c1 = walk(b)
         a2, c2 = vm_walk(b)
-        assert a1 == a2, b[:300]
+        a3, c3 = walk_global(b)                  # window reader (product) vs plain global reader: identical in every column
+        assert a1 == a2 == a3, b[:300]
+        assert (c1 == c3).all(), b[:300]
         if a1:
             assert (c1[2:50] == c2[2:50]).all(), b[:300]
     for s in seeds:
