@@ -267,6 +267,10 @@ class BatchEngine:
     def tool_plan_device(self, dev_aux, dev_aux_off) -> None:
         self._check(self.lib.ck_tool_plan_device(self.h, ptr(dev_aux), ptr(dev_aux_off)))
 
+    def launch_count(self) -> int:
+        """kernels launched by this engine so far"""
+        return int(self.lib.ck_launch_count(self.h))
+
     def sync(self) -> None:
         self._check(self.lib.ck_sync(self.h))
 

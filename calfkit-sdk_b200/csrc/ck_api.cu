@@ -45,6 +45,7 @@ struct ck_handle {
     const u8* cur_in = nullptr; const long long* cur_in_off = nullptr;
     uint32_t n = 0, n_payloads = 0, n_pubs = 0;
     bool tool_set = false; ck_tool_cfg h_tool_cfg{};
+    unsigned long long n_launch = 0;
     unsigned long long* h_grand = nullptr;   // pinned
     // profiling: asynchronous event pairs around every kernel, read back (and summed) on demand so
     // that timing the kernels does not serialise the stream during a timed region
@@ -59,6 +60,7 @@ struct ck_handle {
     char b_[512]; snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     (h)->err = b_; return 1; } } while (0)
 
+#define CKL(h) (h)->n_launch++,          // every kernel launch is counted (ck_launch_count: bench.py's gpu_launches)
 static int fail(ck_handle* h, const char* msg) { h->err = msg; return 1; }
 
 struct KTimer {
@@ -243,24 +245,24 @@ static int launch_decode(ck_handle* h) {
     CUDA_TRY(h, cudaMemsetAsync(h->d_ovl_off, 0xff, sizeof(long long) * (size_t)n, h->stream));      // no overlays yet
     {
         KTimer t(h, CK_K_WALK);
-        if (mode == 1) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
-        else if (mode == 2) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
-        else ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 0);
+        if (mode == 1) CKL(h) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        else if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        else CKL(h) ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 0);
         CUDA_TRY(h, cudaGetLastError());
     }
     {
         KTimer t(h, CK_K_CANON);
-        ck_canon_count_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen);
+        CKL(h) ck_canon_count_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (run_scan(h, h->d_clen, n, h->d_coff, 0)) return 1;
     {
         KTimer t(h, CK_K_CANON);
-        ck_canon_write_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen, h->d_coff, h->d_ovl, (long long)h->max_ovl,
+        CKL(h) ck_canon_write_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen, h->d_coff, h->d_ovl, (long long)h->max_ovl,
                                                                  h->d_ovl_off, h->d_ovl_len);
-        if (mode == 1) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else if (mode == 2) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 1);
+        if (mode == 1) CKL(h) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        else if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        else CKL(h) ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 1);
         CUDA_TRY(h, cudaGetLastError());
     }
     return 0;
@@ -292,9 +294,9 @@ static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32
     if (!tile_sum) { tile_sum = h->d_tile_sum; grand = h->d_grand; }
     u32 ntiles = (n + CK_SCAN_TILE - 1) / CK_SCAN_TILE;
     if (n) {
-        ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, tile_sum, pad);
-        ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(tile_sum, ntiles, grand);
-        ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, tile_sum, out_off, pad);
+        CKL(h) ck_scan_tiles_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, tile_sum, pad);
+        CKL(h) ck_scan_sums_kernel<<<1, CK_SCAN_BLOCK, 0, h->stream>>>(tile_sum, ntiles, grand);
+        CKL(h) ck_scan_apply_kernel<<<ntiles, CK_SCAN_BLOCK, 0, h->stream>>>(len, n, tile_sum, out_off, pad);
     }
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -306,7 +308,7 @@ static int scan_emit(ck_handle* h, u32 npay, const u8* aux) {
         KTimer t(h, CK_K_EMIT);
         if (npay) {
             u32 warps_per_block = 256 / 32;
-            ck_emit_kernel<<<(npay + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(
+            CKL(h) ck_emit_kernel<<<(npay + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(
                 view_of(h), h->d_lit, aux, h->d_glue, h->d_descs, h->d_out_off, npay, h->d_out, (long long)h->max_out);
         }
         CUDA_TRY(h, cudaGetLastError());
@@ -320,7 +322,7 @@ extern "C" int ck_tool_args(ck_handle* h) {
     if (!h->tool_set) return fail(h, "ck_tool_args: call ck_set_tool_node first");
     {
         KTimer t(h, CK_K_PLAN);
-        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
+        if (h->n) CKL(h) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
             h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 0, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -333,7 +335,7 @@ static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_of
     if (h->h_tool_cfg.tpl_nparts == 0 && aux_off == nullptr) return fail(h, "ck_tool_plan: node has no device template, host results required");
     {
         KTimer t(h, CK_K_PLAN);
-        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
+        if (h->n) CKL(h) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
             h->d_tool_cfg, h->d_lit, aux_off, aux, h->d_glue, 1, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -342,7 +344,7 @@ static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_of
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * h->n;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
+        if (npubs) CKL(h) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -369,7 +371,7 @@ extern "C" int ck_return_plan(ck_handle* h) {
     if (!h->tool_set) return fail(h, "ck_return_plan: call ck_set_tool_node (publish topic) first");
     {
         KTimer t(h, CK_K_PLAN);
-        if (h->n) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
+        if (h->n) CKL(h) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
             h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 2, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -377,7 +379,7 @@ extern "C" int ck_return_plan(ck_handle* h) {
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * h->n;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
+        if (npubs) CKL(h) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -453,7 +455,7 @@ extern "C" int ck_tailcall_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed) {
     if (n > h->max_payloads) return fail(h, "ck_tailcall_plan: more payloads than max_payloads");
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) ck_tailcall_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
+        if (n) CKL(h) ck_tailcall_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
             unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -461,7 +463,7 @@ extern "C" int ck_tailcall_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed) {
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * n;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, n, h->d_pubs, npubs,
+        if (npubs) CKL(h) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -475,7 +477,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     u32 n = h->n;
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, max_fanout, sequential, h->d_counts);
+        if (n) CKL(h) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, max_fanout, sequential, h->d_counts);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (run_scan(h, h->d_counts, n, h->d_slot_base, 0)) return 1;
@@ -486,7 +488,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     if (slots > h->max_payloads) return fail(h, "ck_fanout_plan: more payloads than max_payloads");
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
+        if (n) CKL(h) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
             h->d_slot_base, unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -494,7 +496,7 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     {
         KTimer t(h, CK_K_ROUTE);
         u32 npubs = 2 * (u32)slots;
-        if (npubs) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, n, h->d_pubs, npubs,
+        if (npubs) CKL(h) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, n, h->d_pubs, npubs,
             h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
@@ -538,7 +540,7 @@ extern "C" int ck_exchange_plan(ck_handle* h, uint32_t rank, uint32_t world, con
     {
         KTimer t(h, CK_K_ROUTE);
         CUDA_TRY(h, cudaMemsetAsync(h->d_x_nbytes, 0, sizeof(unsigned long long) * CK_X_MAXWORLD, h->stream));
-        ck_xplan_count_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, rank, world, h->d_x_hist, h->d_x_nbytes);
+        CKL(h) ck_xplan_count_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, rank, world, h->d_x_hist, h->d_x_nbytes);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (run_scan(h, h->d_x_hist, nh, h->d_x_base, 0, h->d_x_tile, h->d_x_grand)) return 1;
@@ -557,7 +559,7 @@ extern "C" int ck_exchange_plan(ck_handle* h, uint32_t rank, uint32_t world, con
     *n_sel = (u32)total;
     {
         KTimer t(h, CK_K_ROUTE);
-        ck_xplan_scatter_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, h->d_out_off, rank, world, h->d_x_base,
+        CKL(h) ck_xplan_scatter_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, h->d_out_off, rank, world, h->d_x_base,
                                                                   h->d_x_src_off, h->d_x_len, h->d_x_len32, h->d_x_pub);
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -569,11 +571,13 @@ extern "C" int ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64
                                uint32_t n, uint8_t* dev_dst, const int64_t* dev_dst_off) {
     cudaSetDevice(h->device);
     KTimer t(h, CK_K_EMIT);
-    if (n) ck_gather_spans_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(dev_src, (const long long*)dev_src_off, (const long long*)dev_src_len, n,
+    if (n) CKL(h) ck_gather_spans_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(dev_src, (const long long*)dev_src_off, (const long long*)dev_src_len, n,
                                                                      dev_dst, (const long long*)dev_dst_off);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
+
+extern "C" uint64_t ck_launch_count(ck_handle* h) { return h->n_launch; }
 
 extern "C" int ck_sync(ck_handle* h) {
     cudaSetDevice(h->device);

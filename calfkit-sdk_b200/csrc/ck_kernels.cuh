@@ -293,14 +293,12 @@ struct SegWriter {
 //           tool can be given its arguments (only used when the node has no device template)
 //   mode 1: classify + build the final payload from the device template or the host's results (aux)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-ck_plan_tool_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
-                    const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
-                    const long long* __restrict__ aux_off,    // per record [n+1] spans of the host results blob, or NULL
-                    const u8* __restrict__ aux, u8* __restrict__ glue,
-                    int mode, ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void
+ck_plan_tool_one(ck_view v, u32 i, u32* __restrict__ cols, u32 stride,
+                 const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
+                 const long long* __restrict__ aux_off,    // per record [n+1] spans of the host results blob, or NULL
+                 const u8* __restrict__ aux, u8* __restrict__ glue,
+                 int mode, ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
 #define COL(k) cols[(size_t)(k) * stride + i]
     const ck_tool_cfg& cfg = *cfgp;
     ck_pub none; none.payload = 0xffffffffu; none.topic_id = -1; none.topic_off = none.topic_len = 0; none.record = i;
@@ -442,6 +440,17 @@ ck_plan_tool_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
     COL(CK_COL_ACTION) = CK_ACT_RETURN; COL(CK_COL_NOUT) = nout;
 #undef COL
 }
+
+__global__ void __launch_bounds__(128)
+ck_plan_tool_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
+                    const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
+                    const long long* __restrict__ aux_off, const u8* __restrict__ aux, u8* __restrict__ glue,
+                    int mode, ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ck_plan_tool_one(v, i, cols, stride, cfgp, lit, aux_off, aux, glue, mode, descs, pay_len, pubs);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // agent fan-out: Agent.run's list[Call] branch (reference nodes/agent.py:177-211) followed by

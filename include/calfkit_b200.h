@@ -109,6 +109,7 @@ int  ck_gather_spans(ck_handle* h, const uint8_t* dev_src, const int64_t* dev_sr
 
 /* results ---------------------------------------------------------------------------------------- */
 int  ck_sync(ck_handle* h);
+uint64_t ck_launch_count(ck_handle* h);   /* kernels launched by this handle so far */
 int  ck_out_size(ck_handle* h, uint64_t* out_bytes, uint32_t* n_payloads, uint32_t* n_publishes);  /* waits */
 int  ck_fetch_columns(ck_handle* h, uint32_t* host_cols /* CK_NUM_COLS * n, column-major */);
 /* payload i = host_out[host_out_off[i] .. + host_out_len[i]); starts are 16-byte aligned, so
