@@ -237,12 +237,14 @@ def run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    l0 = eng.launch_count()
     ev0.record(stream)
     for k in range(args.steps):
         step(k)
     ev1.record(stream)
     torch.cuda.synchronize()
     sampler.stop_flag = True
+    gpu_launches = eng.launch_count() - l0
     ms_step = ev0.elapsed_time(ev1) / args.steps
     prof = eng.profile_read()
     eng.profile(False)
@@ -296,11 +298,145 @@ def run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -
         "clocks": sampler.summary(),
         "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "BatchEngine.submit(pinned host) + fanout_plan + fetch(pinned host)"},
-        "gpu_launches": args.steps * 14,
+        "gpu_launches": gpu_launches,
         "roofline": {"kernel": "ck_emit_kernel", "bound": "hbm", "achieved": algo_emit / emit_ms / 1e6, "peak": peak, "unit": "GB/s",
                      "frac": algo_emit / emit_ms / 1e6 / peak, "traffic": None, "share_of_step": emit_ms / ms_step, "kernels": kern},
         "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} events in {cpu_dt:.1f} s over {min(cores, len(sample))} processes (oracle/port.py agent_fanout)"},
+    }
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+def _cpu_reply_worker(chunk):
+    from oracle import port
+    n = 0
+    for r in chunk:
+        try:
+            port.reply_output(r)
+        except Exception:  # noqa: BLE001  (DeserializationError is part of the path)
+            pass
+        n += 1
+    return n, 0
+
+
+def run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -> None:
+    """SURVEY.md section 8f row 3, the client reply path (reference client/deserialize.py:15-89): every step validates a
+    batch of final reply envelopes and extracts NodeResult.output (first DataPart.data, else first TextPart.text)."""
+    import multiprocessing as mp
+    import random
+    import numpy as np
+    import torch
+    from calfkit import synth
+    from calfkit.engine import BatchEngine
+    n = args.events
+    rng = random.Random(7 + rank)
+    base = synth.tool_events(min(n, 20000), seed=4000 + rank)
+    recs = []
+    for i in range(n):
+        r = base[i % len(base)]
+        k = rng.randrange(4)
+        parts = [] if k == 0 else ['{"kind":"text","text":"It\'s sunny in %s","metadata":null}' % ("x" * rng.randrange(4, 40))]
+        if k >= 2:
+            parts.insert(rng.randrange(2), '{"kind":"data","data":{"temp":%d,"ok":true,"tags":["a","b"]},"schema_":null,"metadata":null}' % rng.randrange(40))
+        recs.append(r.replace(b'"final_output_parts":[]', ('"final_output_parts":[' + ",".join(parts) + "]").encode()))
+    batch = synth.pack(recs)
+    in_bytes = int(batch.data.nbytes)
+    eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096, max_out_bytes=n * 272 + (1 << 20))
+    d_in = torch.from_numpy(batch.data.copy()).to(dev)
+    d_off = torch.from_numpy(batch.offsets.copy()).to(dev)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+
+    def step():
+        eng.submit_device(d_in, d_off, n)
+        eng.reply_plan(0)
+
+    for _ in range(args.warmup):
+        step()
+    eng.sync()
+    eng.profile(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    gpu_launches = eng.launch_count() - l0
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    prof = eng.profile_read()
+    eng.profile(False)
+    out_bytes, npay, _npub = eng.out_size()
+    value = world * n / (ms_step / 1e3)
+    h_in = torch.from_numpy(batch.data.copy()).pin_memory()
+    h_off = torch.from_numpy(batch.offsets.copy()).pin_memory()
+    h_out = torch.empty(out_bytes + (1 << 20), dtype=torch.uint8).pin_memory()
+    h_o = torch.empty(npay + 1, dtype=torch.int64).pin_memory().numpy()
+    h_l = torch.empty(npay, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    d2h = 0
+    e2e_steps = 4
+    for k in range(2 + e2e_steps):
+        if k == 2:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        eng.submit(h_in.numpy(), h_off.numpy()); eng.reply_plan(0)
+        o, of, ln, pb = eng._fetch(out_buf=h_out.numpy(), off_buf=h_o, len_buf=h_l)
+        d2h = int(o.nbytes + of.nbytes + ln.nbytes)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    cols = eng.columns()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    kern = {k: {"ms_per_launch": ms / c, "launches": c} for k, (ms, c) in prof.items() if c}
+    walk_ms = kern["walk"]["ms_per_launch"]
+    from calfkit.engine._lib import COL as _COL, NUM_COLS as _NC
+    algo_walk = in_bytes + 8 * (n + 1) + 4 * (_NC - 10) * n            # the walker writes every column but the plan kernels'
+    # parity spot check against the oracle (byte-exact), outside the timed regions
+    from oracle import port
+    small = synth.pack(recs[:256])
+    eng.submit(small.data, small.offsets); eng.reply_plan(0)
+    chk = eng.fetch()
+    ok = True
+    for i, r in enumerate(recs[:256]):
+        try:
+            want = port.reply_output(r)[1]
+        except Exception:  # noqa: BLE001
+            want = b""
+        ok = ok and chk.payload(i) == want
+    cores = os.cpu_count() or 1
+    sample = recs[: max(cores * 400, 4000)]
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        chunks = [sample[i::cores] for i in range(cores) if sample[i::cores]]
+        pool.map(_cpu_reply_worker, [c[:2] for c in chunks])
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_reply_worker, chunks)
+        cpu_dt = time.perf_counter() - t0
+    cpu_n = sum(r[0] for r in res)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "reply: client-side projection of final reply envelopes to NodeResult.output (SURVEY 8f row 3; "
+                               "reference client/deserialize.py:15-89), auto output type",
+                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "out_bytes_per_event": out_bytes / n,
+                   "ok_fraction": float((cols[_COL["STATUS"]] == 0).mean()), "parity_vs_oracle_256": ok,
+                   "l2": "inputs (%.2f GB/step) larger than L2" % (in_bytes / 1e9)},
+        "clocks": sampler.summary(),
+        "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "BatchEngine.submit(pinned host) + reply_plan + fetch(pinned host)"},
+        "gpu_launches": gpu_launches,
+        "roofline": {"kernel": "ck_walk_kernel", "bound": "hbm", "achieved": algo_walk / walk_ms / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": algo_walk / walk_ms / 1e6 / peak, "traffic": None, "share_of_step": walk_ms / ms_step, "kernels": kern},
+        "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cpu_n} replies in {cpu_dt:.1f} s over {cores} processes (oracle/port.py reply_output)"},
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -318,7 +454,7 @@ def main() -> None:
     ap.add_argument("--events", type=int, default=1_000_000, help="events per GPU per step (config 2: 1M)")
     ap.add_argument("--cross", type=float, default=0.125, help="fraction of records on a foreign partition (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="events for the cpu_baseline leg (0 = auto)")
-    ap.add_argument("--workload", default="tool_event_1k", choices=["tool_event_1k", "fanout"],
+    ap.add_argument("--workload", default="tool_event_1k", choices=["tool_event_1k", "fanout", "reply"],
                     help="tool_event_1k = BASELINE.json configs[1] (the headline); fanout = configs[2]: 1 Agent -> 64 tools")
     ap.add_argument("--fanout", type=int, default=64)
     args = ap.parse_args()
@@ -353,6 +489,9 @@ def main() -> None:
 
     if args.workload == "fanout":
         run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus)
+        return
+    if args.workload == "reply":
+        run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus)
         return
     n = args.events
     recs = synth.tool_events(n, seed=1000 + rank)

@@ -261,6 +261,10 @@ class BatchEngine:
     def tool_plan(self, aux: np.ndarray | None = None, aux_off: np.ndarray | None = None) -> None:
         self._check(self.lib.ck_tool_plan(self.h, ptr(aux), ptr(aux_off)))
 
+    def reply_plan(self, mode: int = 0) -> None:
+        """client reply decode (client/deserialize.py:55-89): payload i = output value JSON; mode 0 auto, 1 text, 2 data"""
+        self._check(self.lib.ck_reply_plan(self.h, mode))
+
     def return_plan(self) -> None:
         self._check(self.lib.ck_return_plan(self.h))
 

@@ -387,6 +387,21 @@ extern "C" int ck_return_plan(ck_handle* h) {
     return 0;
 }
 
+// client reply decode: payload i = the output value of reply i (see ck_reply_plan_kernel)
+extern "C" int ck_reply_plan(ck_handle* h, uint32_t mode) {
+    cudaSetDevice(h->device);
+    if (mode > 2) return fail(h, "ck_reply_plan: mode must be 0 (auto), 1 (text) or 2 (data)");
+    {
+        KTimer t(h, CK_K_PLAN);
+        if (h->n) CKL(h) ck_reply_plan_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n, mode, h->d_glue,
+                                                                               h->d_descs, h->d_pay_len);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (scan_emit(h, h->n, nullptr)) return 1;
+    h->n_pubs = 0;
+    return 0;
+}
+
 extern "C" int ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const int64_t* dev_aux_off) {
     cudaSetDevice(h->device);
     return tool_plan_common(h, dev_aux, (const long long*)dev_aux_off);

@@ -27,7 +27,8 @@ enum {
     CK_ACT_CALL = 4,         // Call: push frame, publish to target
     CK_ACT_TAILCALL = 5,     // TailCall: pop + push inheriting callback
     CK_ACT_FANOUT = 6,       // list[Call]: one publish per pending tool call; handler return = input
-    CK_ACT_HOST_TOOL = 7     // tool result must come from the host (tool is not a device template)
+    CK_ACT_HOST_TOOL = 7,    // tool result must come from the host (tool is not a device template)
+    CK_ACT_REPLY = 8         // client reply: the payload is the output value (DataPart.data / TextPart.text as JSON)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -65,6 +66,9 @@ enum {
     CK_COL_ARGS_OFF, CK_COL_ARGS_LEN,             // its args value span
     CK_COL_RES_OFF, CK_COL_RES_LEN,               // existing tool_results[arg0] value span (len 0 = absent)
     CK_COL_NOUT,                                  // number of publishes this record produces
+    // client reply path (reference client/deserialize.py:55-89): the output of a final reply
+    CK_COL_ODATA_OFF, CK_COL_ODATA_LEN,           // first DataPart of final_output_parts: its `data` value span (len 0 = none)
+    CK_COL_OTEXT_OFF, CK_COL_OTEXT_LEN,           // first TextPart: its `text` JSON string span, quotes included (len 0 = none)
     CK_NUM_COLS
 };
 

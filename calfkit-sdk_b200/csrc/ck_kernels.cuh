@@ -210,6 +210,19 @@ __device__ __forceinline__ Span ck_dict_find(Rd& r, u32 obj, u32 key_off, u32 ke
 // either side of a splice point that do not fill a vector — is packed by this thread, 8 aligned bytes
 // per store, into the payload's glue slot and becomes a GLUE segment.
 // ------------------------------------------------------------------------------------------------
+#ifndef CK_PLAN_PF
+#define CK_PLAN_PF 1
+#endif
+#ifndef CK_PLAN_MINB
+#define CK_PLAN_MINB 1
+#endif
+__device__ __forceinline__ void ck_prefetch_l2(const u8* p) {
+#if CK_PLAN_PF == 2
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
 #define CK_DIRECT_MIN 48u
 struct SegWriter {
     ck_out_desc* d;
@@ -313,6 +326,16 @@ ck_plan_tool_one(ck_view v, u32 i, u32* __restrict__ cols, u32 stride,
     if (status != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; COL(CK_COL_NOUT) = 0; return; }
 
     u32 nframes = COL(CK_COL_NFRAMES), nargs = COL(CK_COL_NARGS), kinds = COL(CK_COL_ARGKINDS);
+#if CK_PLAN_PF
+    // the plan reads ~10 short, far-apart pieces of the record, one after the other (each a DRAM miss): start all
+    // those fetches now so that they overlap instead of queueing behind each other
+    if (mode != 0 && nframes > 0) {
+        u32 tro = COL(CK_COL_TR_OFF) + COL(CK_COL_TR_LEN), tpo = COL(CK_COL_TOP_OFF);
+        ck_prefetch_l2(rec + (tro > 16 ? tro - 16 : 0)); ck_prefetch_l2(rec + COL(CK_COL_ARG0_OFF)); ck_prefetch_l2(rec + COL(CK_COL_ARGS_OFF));
+        ck_prefetch_l2(rec + (tpo > 16 ? tpo - 16 : 0)); ck_prefetch_l2(rec + tpo + COL(CK_COL_TOP_LEN)); ck_prefetch_l2(rec + COL(CK_COL_CB_OFF));
+        ck_prefetch_l2(rec + COL(CK_COL_FOV_OFF)); ck_prefetch_l2(rec + COL(CK_COL_SOV_OFF));
+    }
+#endif
     SegWriter w; w.init(d, &r, lit, aux, glue + (size_t)i * CK_GLUE_STRIDE);
     Span call = {0, 0};
     if (mode == 2) {
@@ -441,7 +464,7 @@ ck_plan_tool_one(ck_view v, u32 i, u32* __restrict__ cols, u32 stride,
 #undef COL
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CK_PLAN_MINB)
 ck_plan_tool_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
                     const ck_tool_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
                     const long long* __restrict__ aux_off, const u8* __restrict__ aux, u8* __restrict__ glue,
@@ -655,6 +678,38 @@ ck_tailcall_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, co
     u32 nout = 1;
     if (cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = i; q.topic_id = cfg.publish_topic_id; pubs[2 * i + 1] = q; nout = 2; }
     COL(CK_COL_NOUT) = nout;
+#undef COL
+}
+
+// ------------------------------------------------------------------------------------------------
+// client reply path (reference client/deserialize.py:55-89): the output of a final reply
+// envelope is the first DataPart.data of final_output_parts, else the first TextPart.text (mode 0, auto);
+// only the TextPart (mode 1, output_type=str); only the DataPart (mode 2, a typed output: the host validates
+// the value).  Payload i = that value's JSON bytes; no publishes.  A reply without the wanted part is the
+// reference's DeserializationError: CK_ACT_RAISES.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ck_reply_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode, u8* __restrict__ glue,
+                     ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#define COL(k) cols[(size_t)(k) * stride + i]
+    ck_out_desc* d = descs + i;
+    pay_len[i] = 0; d->nseg = 0; d->total_len = 0; d->record = i;
+    COL(CK_COL_NOUT) = 0;
+    if (COL(CK_COL_STATUS) != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; return; }
+    u32 doff = COL(CK_COL_ODATA_OFF), dlen = COL(CK_COL_ODATA_LEN), toff = COL(CK_COL_OTEXT_OFF), tlen = COL(CK_COL_OTEXT_LEN);
+    u32 off, len;
+    if (mode != 1 && dlen) { off = doff; len = dlen; }
+    else if (mode != 2 && tlen) { off = toff; len = tlen; }
+    else { COL(CK_COL_ACTION) = CK_ACT_RAISES; return; }
+    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
+    Rd r; r.init(rec, rlen);
+    SegWriter w; w.init(d, &r, nullptr, nullptr, glue + (size_t)i * CK_GLUE_STRIDE);
+    w.add(CK_SRC_INPUT, off, len);
+    if (!w.finish(i)) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_STATUS) = CK_UNSUPPORTED; d->nseg = 0; d->total_len = 0; return; }
+    pay_len[i] = w.total;
+    COL(CK_COL_ACTION) = CK_ACT_REPLY;
 #undef COL
 }
 

@@ -103,9 +103,12 @@ typedef GRd Rd;        // the plan / fan-out kernels read a few scattered spots 
 // calls by value (cores return it next to their result).
 // -------------------------------------------------------------------------------------------------
 #ifndef CK_WIN_BYTES
-#define CK_WIN_BYTES 128
+#define CK_WIN_BYTES 160
 #endif
 #define CK_WIN_BACK 16
+#ifndef CK_WIN_PF2
+#define CK_WIN_PF2 0
+#endif
 #define CK_WIN_STRIDE (CK_WIN_BYTES + 16)     // per-thread slot; the pad spreads the slots over the banks
 #define CK_WIN_NONE 0x80000000u     // o = ap - wbase is then >= 2^31 for every position: always refills
 #if defined(__CUDA_ARCH__)
@@ -125,6 +128,11 @@ CK_HD_NOINLINE u32 ck_win_refill(const u8* gb, u32 ap, u32 lim) {
 #pragma unroll
     for (u32 k = 0; k < CK_WIN_BYTES; k += 16)
         if (wb + k < lim) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + k), "l"(src + k) : "memory");
+#if CK_WIN_PF2
+    // the window after this one: start pulling it towards L2 now, the next refill then waits for L2 instead of DRAM
+    if (wb + CK_WIN_BYTES < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + CK_WIN_BYTES));
+    if (wb + CK_WIN_BYTES + 128 < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + CK_WIN_BYTES + 128));
+#endif
     asm volatile("cp.async.wait_all;" ::: "memory");
 #else
     for (u32 k = 0; k < CK_WIN_BYTES; k += 16) if (wb + k < lim) for (u32 j = 0; j < 16; j++) ck_win_host[k + j] = gb[wb + k + j];
@@ -266,6 +274,12 @@ CK_HD u64 ck_lit_word(const char* lit, u32 L, u32 k) {      // bytes [k, k+8) of
     return w;
 }
 CK_HD u32 ck_lit_nb(u32 L, u32 k) { return (L - k >= 8) ? 8u : (L - k); }      // valid bytes of the word at k
+// Speculative fused literals: pydantic emits every optional field, and in practice most of them are `null`, so
+// long runs of `"key":null` pairs are tried as ONE literal first; a miss costs one 16-byte compare and falls back to
+// the field-by-field path, which accepts exactly the same bytes (the fused literal is one of its spellings).
+#ifndef CK_SPEC
+#define CK_SPEC 1
+#endif
 #ifndef CK_MATCH_INLINE
 #define CK_MATCH_INLINE 1
 #endif
@@ -648,7 +662,11 @@ CK_HD u32 ck_tool_call_part(R& r, u32& pos, u32 d, AnyCtx& cx, ToolCallSpans& o)
     if (PEEK('"')) { if (!ck_string(r, pos, t)) return 0; }
     else if (!ck_any_obj_or_null(r, pos, d + 1, cx)) return 0;
     o.args.len = pos - o.args.off;
-    if (!M(",\"tool_call_id\":") || !ck_string(r, pos, o.tool_call_id) || !M(",\"id\":") || !ck_string_or_null(r, pos, t) ||
+    if (!M(",\"tool_call_id\":") || !ck_string(r, pos, o.tool_call_id)) return 0;
+#if CK_SPEC
+    if (M(",\"id\":null,\"provider_name\":null,\"provider_details\":null,\"part_kind\":\"tool-call\"}")) return 1;
+#endif
+    if (!M(",\"id\":") || !ck_string_or_null(r, pos, t) ||
         !M(",\"provider_name\":") || !ck_string_or_null(r, pos, t) || !M(",\"provider_details\":") ||
         !ck_any_obj_or_null(r, pos, d + 1, cx) || !M(",\"part_kind\":\"")) return 0;
     if (M("tool-call\"}")) return 1;
@@ -681,6 +699,9 @@ CK_HD u32 ck_message_part(R& r, u32& pos, u32 d, AnyCtx& cx) {
                     !M(",\"part_kind\":\"system-prompt\"}")) return 0;
                 return 1;
             }
+#if CK_SPEC
+            if (M(",\"name\":null,\"part_kind\":\"user-prompt\"}")) return 1;
+#endif
             if (!M(",\"name\":") || !ck_string_or_null(r, pos, t) || !M(",\"part_kind\":\"user-prompt\"}")) return 0;
             return 1;
         }
@@ -760,7 +781,11 @@ CK_HD_NOINLINE u64 ck_message_core(const u8* g, u32 n, u32 pos, u32 st, u32 d, A
     u32 kind;
     if (M(",\"timestamp\":")) {
         if (seen & 2) return 0;
-        if (!ck_datetime_or_null(r, pos) || !M(",\"instructions\":") || !ck_string_or_null(r, pos, t) ||
+        if (!ck_datetime_or_null(r, pos)) return 0;
+#if CK_SPEC
+        if (M(",\"instructions\":null,\"kind\":\"request\",\"run_id\":null,\"metadata\":null}")) return CK_RET(pos | (1u << 30));
+#endif
+        if (!M(",\"instructions\":") || !ck_string_or_null(r, pos, t) ||
             !M(",\"kind\":\"request\",\"run_id\":") || !ck_string_or_null(r, pos, t) || !M(",\"metadata\":") ||
             !ck_any_obj_or_null(r, pos, d + 1, cx) || !M("}")) return 0;
         kind = 1;
@@ -835,28 +860,36 @@ CK_HD bool ck_overrides_or_null(R& r, u32& pos, u32 d, AnyCtx& cx) {
     return true;
 }
 
-// final_output_parts element (reference calfkit/models/payload.py:6-35): `kind` comes first
+// final_output_parts element (reference calfkit/models/payload.py:6-35): `kind` comes first.
+// returns 0 = no match, 1 = text (val = the `text` JSON string, quotes included), 2 = data (val = the `data` value),
+// 3 = file / tool part
 template <class R>
-CK_HD bool ck_content_part(R& r, u32& pos, u32 d, AnyCtx& cx) {
+CK_HD u32 ck_content_part(R& r, u32& pos, u32 d, AnyCtx& cx, Span& val) {
     Span t;
-    if (!M("{\"kind\":\"")) return false;
+    if (!M("{\"kind\":\"")) return 0;
     if (M("text\",\"text\":")) {
-        return ck_string(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+        val.off = pos;
+        bool ok = ck_string(r, pos, t);
+        val.len = pos - val.off;
+        return (ok && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}")) ? 1u : 0u;
     }
     if (M("data\",\"data\":")) {
         // the field's alias is "schema": a "schema_" key is ignored on validation and re-emitted as null
         // (SURVEY.md Appendix C item 2), so only null is a fixed point
-        return ck_any(r, pos, d + 1, cx) && M(",\"schema_\":null,\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+        val.off = pos;
+        bool ok = ck_any(r, pos, d + 1, cx);
+        val.len = pos - val.off;
+        return (ok && M(",\"schema_\":null,\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}")) ? 2u : 0u;
     }
     if (M("file\",\"media_type\":")) {
-        return ck_string(r, pos, t) && M(",\"uri\":") && ck_string_or_null(r, pos, t) && M(",\"data\":") &&
-               ck_string_or_null(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+        return (ck_string(r, pos, t) && M(",\"uri\":") && ck_string_or_null(r, pos, t) && M(",\"data\":") &&
+                ck_string_or_null(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}")) ? 3u : 0u;
     }
     if (M("tool\",\"tool_call_id\":")) {
-        return ck_string(r, pos, t) && M(",\"kwargs\":") && ck_any_obj(r, pos, d + 1, cx) && M(",\"tool_name\":") &&
-               ck_string(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}");
+        return (ck_string(r, pos, t) && M(",\"kwargs\":") && ck_any_obj(r, pos, d + 1, cx) && M(",\"tool_name\":") &&
+                ck_string(r, pos, t) && M(",\"metadata\":") && ck_any_obj_or_null(r, pos, d + 1, cx) && M("}")) ? 3u : 0u;
     }
-    return false;
+    return 0;
 }
 
 // skip one already-validated canonical value (used for second looks at spans proven canonical)
@@ -991,6 +1024,15 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M("}")) FAIL;
     SETSPAN(CK_COL_TC_OFF, a, pos);
 
+#if CK_SPEC
+    bool spec_tr = M(",\"tool_results\":{},\"uncommitted_message\":null,\"message_history\":[");
+    if (spec_tr) {
+        // ,"tool_results":{}  ,"uncommitted_message":null  ,"message_history":[      (lengths 18 / 27 / 20)
+        u32 e = pos;
+        o.set(CK_COL_TR_OFF, e - 20 - 27 - 2); o.set(CK_COL_TR_LEN, 2);
+        o.set(CK_COL_UNC_OFF, e - 20 - 4); o.set(CK_COL_UNC_LEN, 4);
+    } else {
+#endif
     if (!M(",\"tool_results\":{")) FAIL;
     a = pos - 1;
     if (!PEEK('}')) {
@@ -1017,6 +1059,9 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     SETSPAN(CK_COL_UNC_OFF, a, pos);
 
     if (!M(",\"message_history\":[")) FAIL;
+#if CK_SPEC
+    }
+#endif
     a = pos - 1;
     if (!PEEK(']')) {
         for (;;) {
@@ -1028,17 +1073,36 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M("]")) FAIL;
     SETSPAN(CK_COL_HIST_OFF, a, pos);
 
+#if CK_SPEC
+    if (M(",\"final_output_parts\":[],\"temp_instructions\":null,\"metadata\":null,\"overrides\":null},\"deps\":{\"correlation_id\":")) {
+        // ,"final_output_parts":[]  ,"temp_instructions":null  ,"metadata":null  ,"overrides":null  },"deps":{"correlation_id":
+        //  lengths                24                        25               16                17                          27
+        u32 e = pos;
+        o.set(CK_COL_FOP_OFF, e - 27 - 17 - 16 - 25 - 2); o.set(CK_COL_FOP_LEN, 2);
+        o.set(CK_COL_ODATA_OFF, 0); o.set(CK_COL_ODATA_LEN, 0); o.set(CK_COL_OTEXT_OFF, 0); o.set(CK_COL_OTEXT_LEN, 0);
+        o.set(CK_COL_TI_OFF, e - 27 - 17 - 16 - 4); o.set(CK_COL_TI_LEN, 4);
+        o.set(CK_COL_SMETA_OFF, e - 27 - 17 - 4); o.set(CK_COL_SMETA_LEN, 4);
+        o.set(CK_COL_SOV_OFF, e - 27 - 4); o.set(CK_COL_SOV_LEN, 4);
+    } else {
+#endif
     if (!M(",\"final_output_parts\":[")) FAIL;
     a = pos - 1;
+    Span odata = {0, 0}, otext = {0, 0};
     if (!PEEK(']')) {
         for (;;) {
-            if (!ck_content_part(r, pos, 5, cx)) FAIL;
+            Span val = {0, 0};
+            u32 pk = ck_content_part(r, pos, 5, cx, val);
+            if (!pk) FAIL;
+            if (pk == 1 && otext.len == 0) otext = val;            // first TextPart / first DataPart (client/deserialize.py:63-70)
+            if (pk == 2 && odata.len == 0) odata = val;
             if (PEEK(',')) { pos++; continue; }
             break;
         }
     }
     if (!M("]")) FAIL;
     SETSPAN(CK_COL_FOP_OFF, a, pos);
+    o.set(CK_COL_ODATA_OFF, odata.off); o.set(CK_COL_ODATA_LEN, odata.len);
+    o.set(CK_COL_OTEXT_OFF, otext.off); o.set(CK_COL_OTEXT_LEN, otext.len);
 
     if (!M(",\"temp_instructions\":")) FAIL;
     a = pos;
@@ -1057,6 +1121,9 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
 
     // ---- context.deps ----------------------------------------------------------------------
     if (!M("},\"deps\":{\"correlation_id\":")) FAIL;
+#if CK_SPEC
+    }
+#endif
     if (!ck_string(r, pos, t)) FAIL;
     o.set(CK_COL_CORR_OFF, t.off); o.set(CK_COL_CORR_LEN, t.len);
     if (!M(",\"provided_deps\":")) FAIL;
@@ -1099,11 +1166,18 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
                 }
                 if (!M("]")) FAIL;
             }
-            if (!M(",\"frame_id\":") || !ck_string(r, pos, t) || !M(",\"overrides\":")) FAIL;
-            u32 ov0 = pos;
-            if (!ck_overrides_or_null(r, pos, 6, cx)) FAIL;
-            u32 ov1 = pos;
-            if (!M("}")) FAIL;
+            if (!M(",\"frame_id\":") || !ck_string(r, pos, t)) FAIL;
+            u32 ov0, ov1;
+#if CK_SPEC
+            if (M(",\"overrides\":null}")) { ov1 = pos - 1; ov0 = ov1 - 4; } else
+#endif
+            {
+                if (!M(",\"overrides\":")) FAIL;
+                ov0 = pos;
+                if (!ck_overrides_or_null(r, pos, 6, cx)) FAIL;
+                ov1 = pos;
+                if (!M("}")) FAIL;
+            }
             nframes++;
             top0 = f0; top1 = pos; fov0 = ov0; fov1 = ov1; top_nargs = nargs; top_kinds = kinds;
             top_tgt = tgt; top_cb = cb; top_a0 = a0; top_a1 = a1;

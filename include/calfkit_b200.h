@@ -74,6 +74,11 @@ int  ck_tool_plan(ck_handle* h, const uint8_t* host_aux, const int64_t* host_aux
 /* ReturnCall of the state as it is on the wire (e.g. an Agent's final output after the host LLM step):
  * pop the current frame, publish to its callback topic and to the node's publish_topic. */
 int  ck_return_plan(ck_handle* h);
+/* client reply path (calfkit/client/deserialize.py:55-89): payload i = the output value of reply envelope i as JSON —
+ * mode 0: first DataPart.data of final_output_parts, else first TextPart.text (auto); 1: TextPart.text only
+ * (output_type=str); 2: DataPart.data only (typed output; the caller validates the value).  A reply without the
+ * wanted part (the reference raises DeserializationError) gets CK_ACT_RAISES and an empty payload.  No publishes. */
+int  ck_reply_plan(ck_handle* h, uint32_t mode);
 /* same as ck_tool_plan, aux blob already in HBM */
 int  ck_tool_plan_device(ck_handle* h, const uint8_t* dev_aux, const int64_t* dev_aux_off);
 

@@ -184,3 +184,39 @@ def aggregate(batches: dict[str, PendingToolBatch], state: State, correlation_id
         del batches[correlation_id]
         return batch.base_state
     return None
+
+
+# ---------------------------------------------------------------------------------------------------
+# client reply projection (reference calfkit/client/deserialize.py:15-89)
+# ---------------------------------------------------------------------------------------------------
+REPLY_UNSET: Any = object()
+
+
+def reply_output(payload: bytes, output_type: Any = REPLY_UNSET) -> tuple[str, bytes]:
+    """-> (correlation_id, JSON of NodeResult.output); raises what the reference raises (DeserializationError when
+    the wanted part is missing, pydantic ValidationError when a typed output does not validate)."""
+    from pydantic import TypeAdapter
+    import pydantic_core
+    from calfkit.exceptions import DeserializationError
+    from calfkit.models import DataPart, TextPart
+    envelope = decode(payload)
+    parts = envelope.context.state.final_output_parts               # deserialize.py:38-43
+    corr = envelope.context.deps.correlation_id
+    if output_type is REPLY_UNSET:                                     # _extract_auto, deserialize.py:64-72
+        for p in parts:
+            if isinstance(p, DataPart):
+                return corr, pydantic_core.to_json(p.data)
+        for p in parts:
+            if isinstance(p, TextPart):
+                return corr, pydantic_core.to_json(p.text)
+        raise DeserializationError("No DataPart or TextPart found in final_output_parts; cannot auto-detect output.")
+    if output_type is str:                                           # _extract_text, deserialize.py:75-80
+        for p in parts:
+            if isinstance(p, TextPart):
+                return corr, pydantic_core.to_json(p.text)
+        raise DeserializationError("No TextPart found in final_output_parts; expected output_type=str.")
+    for p in parts:                                                  # _extract_data, deserialize.py:83-89
+        if isinstance(p, DataPart):
+            return corr, pydantic_core.to_json(TypeAdapter(output_type).validate_python(p.data))
+    raise DeserializationError("No DataPart found in final_output_parts; expected output_type="
+                               f"{getattr(output_type, '__name__', str(output_type))}.")

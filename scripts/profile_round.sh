@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --events 262144 --cpu-sample 2000 > $O/${R}_launches_bench.log 2>&1
 # full captures of the three heaviest kernels (one launch each, after warm-up launches)
 for k in walk plan_tool emit; do
-  ncu --set full --clock-control none --import-source on -k regex:ck_${k}_kernel -s 3 -c 1 -f -o $O/${R}_${k} \
+  ncu --set full --clock-control none --import-source on -k regex:ck_${k}_kernel -s $([ $k = walk ] && echo 4 || echo 3) -c 1 -f -o $O/${R}_${k} \
       python scripts/quick_bench.py 1048576 > $O/${R}_ncu_${k}.log 2>&1
 done
 ls -la $O

@@ -395,3 +395,68 @@ def test_exchange_plan_kernels_match_tensor_plan(engine):
             assert got.sel.to(torch.int64).tolist() == want.sel.tolist()
             assert got.src_off.tolist() == want.src_off.tolist() and got.lens.tolist() == want.lens.tolist()
             assert got.dst_off.tolist() == want.dst_off.tolist()
+
+
+def test_reply_outputs_match_reference_goldens_and_oracle(engine):
+    """client reply path: ck_reply_plan + emit against tests/golden/replies.json (the unmodified
+    reference's deserialize_to_node_result) and against the oracle on replies produced by the tool / agent path."""
+    import pydantic_core
+    from oracle import port
+    from calfkit import synth
+    from calfkit.client.batch_reply import BatchReplyDecoder
+    from calfkit.engine._lib import CK_ACT_RAISES, CK_ACT_REPLY, COL
+    cases = golden("replies.json")
+    recs = [c["input"].encode() for c in cases]
+    b = synth.pack(recs)
+    for mode, label in ((0, "auto"), (1, "str"), (2, "dict")):
+        engine.submit(b.data, b.offsets)
+        engine.reply_plan(mode)
+        out = engine.fetch()
+        assert (out.cols[COL["STATUS"]] == 0).all()
+        for i, c in enumerate(cases):
+            exp = c["expect"][label]
+            if exp["ok"] or exp["error"] == "ValidationError":       # the typed validation is the host's step (as in the reference)
+                assert out.cols[COL["ACTION"], i] == CK_ACT_REPLY, (c["name"], label)
+                if exp["ok"]:
+                    assert out.payload(i).decode() == exp["output_json"], (c["name"], label)
+            else:
+                assert out.cols[COL["ACTION"], i] == CK_ACT_RAISES and out.payload(i) == b"", (c["name"], label)
+    # the host wrapper: same values / same exception classes as the reference, typed output included
+    dec = BatchReplyDecoder(engine)
+    for label, ot in (("auto", None), ("str", str), ("dict", dict)):
+        got = dec.decode(recs) if ot is None else dec.decode(recs, ot)
+        for c, g in zip(cases, got):
+            exp = c["expect"][label]
+            if exp["ok"]:
+                assert g.error is None and pydantic_core.to_json(g.output).decode() == exp["output_json"] and g.correlation_id == exp["correlation_id"]
+            else:
+                assert type(g.error).__name__ == exp["error"], (c["name"], label, g)
+    # replies as the path itself produces them: tool-stage events popped down to the client frame, random final parts
+    rng = random.Random(5)
+    recs2 = []
+    for r in synth.mixed_events(200, seed=33, hi=6000):
+        parts = []
+        for _ in range(rng.randrange(0, 4)):
+            k = rng.randrange(3)
+            if k == 0:
+                parts.append('{"kind":"text","text":%s,"metadata":null}' % json.dumps("t" * rng.randrange(0, 200) + "é\n", ensure_ascii=False))
+            elif k == 1:
+                parts.append('{"kind":"data","data":%s,"schema_":null,"metadata":null}' % json.dumps({"v": [round(rng.random(), 6) for _ in range(rng.randrange(0, 30))]}, separators=(",", ":")))
+            else:
+                parts.append('{"kind":"file","media_type":"text/plain","uri":null,"data":null,"metadata":null}')
+        recs2.append(r.replace(b'"final_output_parts":[]', ('"final_output_parts":[' + ",".join(parts) + "]").encode()))
+    b2 = synth.pack(recs2)
+    engine.submit(b2.data, b2.offsets)
+    engine.reply_plan(0)
+    out = engine.fetch()
+    n_ok = 0
+    for i, r in enumerate(recs2):
+        if out.cols[COL["STATUS"], i] != 0:
+            continue                                                # floats with > 15 digits: declared UNSUPPORTED, never wrong
+        n_ok += 1
+        try:
+            _corr, want = port.reply_output(r)
+            assert out.cols[COL["ACTION"], i] == CK_ACT_REPLY and out.payload(i) == want, i
+        except Exception as e:  # noqa: BLE001
+            assert type(e).__name__ == "DeserializationError" and out.cols[COL["ACTION"], i] == CK_ACT_RAISES, (i, repr(e))
+    assert n_ok > 50
