@@ -106,9 +106,6 @@ typedef GRd Rd;        // the plan / fan-out kernels read a few scattered spots 
 #define CK_WIN_BYTES 160
 #endif
 #define CK_WIN_BACK 16
-#ifndef CK_WIN_PF2
-#define CK_WIN_PF2 0
-#endif
 #define CK_WIN_STRIDE (CK_WIN_BYTES + 16)     // per-thread slot; the pad spreads the slots over the banks
 #define CK_WIN_NONE 0x80000000u     // o = ap - wbase is then >= 2^31 for every position: always refills
 #if defined(__CUDA_ARCH__)
@@ -128,11 +125,6 @@ CK_HD_NOINLINE u32 ck_win_refill(const u8* gb, u32 ap, u32 lim) {
 #pragma unroll
     for (u32 k = 0; k < CK_WIN_BYTES; k += 16)
         if (wb + k < lim) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + k), "l"(src + k) : "memory");
-#if CK_WIN_PF2
-    // the window after this one: start pulling it towards L2 now, the next refill then waits for L2 instead of DRAM
-    if (wb + CK_WIN_BYTES < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + CK_WIN_BYTES));
-    if (wb + CK_WIN_BYTES + 128 < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + CK_WIN_BYTES + 128));
-#endif
     asm volatile("cp.async.wait_all;" ::: "memory");
 #else
     for (u32 k = 0; k < CK_WIN_BYTES; k += 16) if (wb + k < lim) for (u32 j = 0; j < 16; j++) ck_win_host[k + j] = gb[wb + k + j];
@@ -1142,10 +1134,13 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
         for (;;) {
             u32 f0 = pos;
             Span tgt, cb;
-            if (!M("{\"target_topic\":") || !ck_string(r, pos, tgt) || !M(",\"callback_topic\":") || !ck_string(r, pos, cb) ||
-                !M(",\"input_args\":")) FAIL;
+            if (!M("{\"target_topic\":") || !ck_string(r, pos, tgt) || !M(",\"callback_topic\":") || !ck_string(r, pos, cb)) FAIL;
             u32 nargs = CK_NARGS_NULL, kinds = 0;
             Span a0 = {0, 0}, a1 = {0, 0};
+#if CK_SPEC
+            if (!M(",\"input_args\":null,\"frame_id\":")) {
+#endif
+            if (!M(",\"input_args\":")) FAIL;
             if (PEEK('n')) { if (!ck_null(r, pos)) FAIL; }
             else {
                 if (!M("[")) FAIL;
@@ -1166,7 +1161,11 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
                 }
                 if (!M("]")) FAIL;
             }
-            if (!M(",\"frame_id\":") || !ck_string(r, pos, t)) FAIL;
+            if (!M(",\"frame_id\":")) FAIL;
+#if CK_SPEC
+            }
+#endif
+            if (!ck_string(r, pos, t)) FAIL;
             u32 ov0, ov1;
 #if CK_SPEC
             if (M(",\"overrides\":null}")) { ov1 = pos - 1; ov0 = ov1 - 4; } else
@@ -1192,6 +1191,14 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     o.set(CK_COL_ARG0_OFF, top_a0.off); o.set(CK_COL_ARG0_LEN, top_a0.len);
     o.set(CK_COL_ARG1_OFF, top_a1.off); o.set(CK_COL_ARG1_LEN, top_a1.len);
     SETSPAN(CK_COL_FOV_OFF, fov0, fov1);
+#if CK_SPEC
+    if (M("]},\"metadata\":null}}")) {             // ]  },"metadata":  null  }}     (lengths 1 / 13 / 4 / 2)
+        u32 e = pos;
+        o.set(CK_COL_FRAMES_OFF, a); o.set(CK_COL_FRAMES_LEN, e - 19 - a);
+        o.set(CK_COL_NFRAMES, nframes);
+        o.set(CK_COL_WFMETA_OFF, e - 6); o.set(CK_COL_WFMETA_LEN, 4);
+    } else {
+#endif
     if (!M("]")) FAIL;
     SETSPAN(CK_COL_FRAMES_OFF, a, pos);
     o.set(CK_COL_NFRAMES, nframes);
@@ -1200,6 +1207,9 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!ck_any(r, pos, 3, cx)) FAIL;
     SETSPAN(CK_COL_WFMETA_OFF, a, pos);
     if (!M("}}")) FAIL;
+#if CK_SPEC
+    }
+#endif
     if (pos != r.n) FAIL;                 // trailing bytes (even whitespace) are not a fixed point
     // resolve tool_calls[input_args[0]] and tool_results[input_args[0]] (what ToolNodeDef.run looks up,
     // reference nodes/tool.py:45, models/state.py:78-79) from the recorded key spans
