@@ -131,7 +131,10 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);
 }
-__global__ void __launch_bounds__(CK_WALK_THREADS, 8)
+#ifndef CK_WALK_MINB
+#define CK_WALK_MINB 7
+#endif
+__global__ void __launch_bounds__(CK_WALK_THREADS, CK_WALK_MINB)
 ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRd>(v, n, cols, stride, mode); }
 __global__ void __launch_bounds__(CK_WALK_THREADS, 8)
 ck_walk_global_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<GRd>(v, n, cols, stride, mode); }

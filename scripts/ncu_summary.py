@@ -19,7 +19,7 @@ for w in want:
         print(f"{w} = {vals[hdr.index(w)]} {rows[1][hdr.index(w)]}")
 st = []
 for i, h in enumerate(hdr):
-    if "issue_stalled" in h and h.endswith("_per_warp_active.pct"):
-        try: st.append((float(vals[i]), h.split("issue_stalled_")[1].replace("_per_warp_active.pct", "")))
+    if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
+        try: st.append((float(vals[i]), h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")))
         except ValueError: pass
-print("stalls (% of warp-active cycles):", ", ".join(f"{n}={v:.0f}" for v, n in sorted(st, reverse=True)[:8]))
+print("stalls (warps stalled per issue-active cycle):", ", ".join(f"{n}={v:.2f}" for v, n in sorted(st, reverse=True)[:8]))
