@@ -637,16 +637,27 @@ def main() -> None:
     ms_step = ms_total / args.steps
     value = world * n / (ms_step / 1e3)
 
-    # ---- end to end (host buffers), double buffered over two engines -------------------------------
+    # ---- end to end (host buffers), pipelined over several engines (3 at N = 1, 2 at N > 1) -----------------
     # step k: lane k%2 takes the batch from pinned host memory (H2D + all kernels, asynchronous) while the
     # previous step's results are copied back from the other lane (D2H + wait): the two PCIe directions
     # and the kernels overlap, exactly as a worker consuming a stream of batches would run it.
-    if len(lanes) < 2:
-        lanes = [lane, Lane()]
+    if world == 1:
+        lanes = [lane, Lane(), Lane()]          # triple buffering: the D2H of step k-2 never waits for kernels
     h_in_np, h_off_np = h_in.numpy(), h_off.numpy()
     e2e_steps = max(4, min(args.steps, 8))
 
     def run_e2e(k_steps):
+        if world == 1:
+            # step k: lane k%3 takes the batch (H2D + kernels, asynchronous); the results of step k-2 — whose kernels
+            # finished a step ago — are copied back at the same time, so both PCIe directions stay busy
+            L = len(lanes)
+            for k in range(k_steps):
+                lanes[k % L].enqueue_host(h_in_np, h_off_np)
+                if k >= L - 1:
+                    lanes[(k - (L - 1)) % L].fetch_host()
+            for k in range(max(0, k_steps - (L - 1)), k_steps):
+                lanes[k % L].fetch_host()
+            return
         lanes[0].enqueue_host(h_in_np, h_off_np)
         lanes[0].exchange_host()
         for k in range(1, k_steps):
@@ -655,7 +666,7 @@ def main() -> None:
             lanes[k % 2].exchange_host()
         lanes[(k_steps - 1) % 2].fetch_host()
 
-    run_e2e(3)
+    run_e2e(4)
     barrier()
     t0 = time.perf_counter()
     run_e2e(e2e_steps)
@@ -752,7 +763,7 @@ def main() -> None:
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h_bytes[0],
                 "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "api": "BatchEngine.submit(pinned host) + tool_plan + fetch(pinned host), two engines double-buffered",
+                "api": "BatchEngine.submit(pinned host) + tool_plan + fetch(pinned host), %d engines pipelined" % len(lanes),
                 "timing": "host wall clock around the whole pipelined loop, synchronised on both sides (spans two streams), max over ranks"},
         "gpu_launches": gpu_launches,
         "roofline": roofline,

@@ -19,13 +19,11 @@ from calfkit.nodes import BaseNodeDef
 
 logger = logging.getLogger(__name__)
 
-_ENGINES: dict[int, BatchEngine] = {}
-
 
 def engine_for(node: BaseNodeDef, *, device: int = 0, max_records: int = 1 << 14, max_in_bytes: int = 64 << 20,
                extra_topics: list[str] | None = None) -> BatchEngine:
     """lazily created, per-node engine (also used by the object-level BaseNodeDef.handler)"""
-    eng = _ENGINES.get(id(node))
+    eng = getattr(node, "_ck_engine", None)     # the engine lives (and dies) with its node: no id()-keyed registry
     if eng is None:
         eng = BatchEngine(device, max_records=max_records, max_in_bytes=max_in_bytes,
                           max_out_bytes=8 * max_in_bytes, max_payloads=8 * max_records)
@@ -34,7 +32,7 @@ def engine_for(node: BaseNodeDef, *, device: int = 0, max_records: int = 1 << 14
             topics += list(t.subscribe_topics)
         eng.register_topics(topics + (extra_topics or []), num_partitions=0)
         node.configure_engine(eng)
-        _ENGINES[id(node)] = eng
+        node._ck_engine = eng
     return eng
 
 

@@ -60,8 +60,12 @@ int  ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t nparts, c
                       const uint8_t* blob, const uint32_t* part_offsets);
 
 /* decode: copy a batch of records (concatenated bytes + n+1 offsets, pinned or pageable host
- * memory) to HBM and run validate+extract.  ck_submit_device: the batch is already resident
- * (device pointers stay owned by the caller and must outlive the following plan/emit calls). */
+ * memory) to HBM and run validate+extract: records in the canonical spelling (what the reference's
+ * model_dump_json() emits) are recognised in place; any other valid spelling is re-emitted canonically
+ * on the device first (ck_fetch_overlay returns those bytes); invalid ones get a per-record status.
+ * ck_submit_device: the batch is already resident (device pointers stay owned by the caller and must
+ * outlive the following plan/emit calls; at least 64 readable bytes must follow the last record:
+ * the kernels read whole aligned vectors). */
 int  ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* host_off, uint32_t n);
 int  ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n);
 
