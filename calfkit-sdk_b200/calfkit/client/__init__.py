@@ -1,6 +1,5 @@
-from calfkit.client.base import BaseClient
+"""calfkit.client — Client / BaseClient / InvocationHandle / NodeResult, as in the reference package."""
+from calfkit.client._requests import BaseClient, InvocationHandle, NodeResult
 from calfkit.client.client import Client
-from calfkit.client.invocation_handle import InvocationHandle
-from calfkit.client.node_result import NodeResult
 
-__all__ = ["BaseClient", "Client", "InvocationHandle", "NodeResult"]
+__all__ = sorted(["Client", "BaseClient", "InvocationHandle", "NodeResult"])

@@ -1,18 +1,4 @@
-from __future__ import annotations
+"""Declared in calfkit/client/_requests.py; re-exported under the reference's module path (reference calfkit/client/node_result.py:11-32)."""
+from calfkit.client._requests import NodeResult  # noqa: F401
 
-from dataclasses import dataclass
-from typing import Any, Generic
-
-from calfkit._types import OutputT
-from calfkit.models import ContentPart
-from calfkit.models.messages import ModelMessage
-
-
-@dataclass(frozen=True)
-class NodeResult(Generic[OutputT]):
-    """Client-facing projection of a reply envelope (reference calfkit/client/node_result.py:11-32)."""
-    output: OutputT
-    output_parts: list[ContentPart]
-    message_history: list[ModelMessage]
-    metadata: Any
-    correlation_id: str
+__all__ = ['NodeResult']

@@ -1,17 +1,18 @@
-from calfkit.models.actions import (Call, Delegate, Emit, NodeResult, Parallel, Reply, ReturnCall,
-                                    Sequential, Silent, TailCall, _Call)
-from calfkit.models.envelope import Envelope
-from calfkit.models.payload import ContentPart, DataPart, FilePart, TextPart, ToolCallPart
-from calfkit.models.session_context import (BaseSessionRunContext, CallFrame, CallFrameStack, Deps,
-                                            SessionRunContext, Stack, WorkflowState)
-from calfkit.models.state import (BaseAgentActivityState, CoreMessageState, InFlightToolsState,
-                                  OverridesState, PendingToolBatch, State)
+"""calfkit.models — same public names as the reference package (calfkit/models/__init__.py); the wire models live in
+calfkit/models/wire.py, the result actions in calfkit/models/actions.py."""
+from calfkit.models import actions as _actions
+from calfkit.models import wire as _wire
 from calfkit.models.tool_context import ToolContext
 
-__all__ = [
-    "Call", "Delegate", "Emit", "NodeResult", "Parallel", "Reply", "ReturnCall", "Sequential",
-    "Silent", "TailCall", "_Call", "Envelope", "ContentPart", "DataPart", "FilePart", "TextPart",
-    "ToolCallPart", "BaseSessionRunContext", "CallFrame", "CallFrameStack", "Deps",
-    "SessionRunContext", "Stack", "WorkflowState", "BaseAgentActivityState", "CoreMessageState",
-    "InFlightToolsState", "OverridesState", "State", "PendingToolBatch", "ToolContext",
-]
+_EXPORTS = {
+    _actions: ("Call", "Delegate", "Emit", "NodeResult", "Parallel", "Reply", "ReturnCall", "Sequential", "Silent", "TailCall", "_Call"),
+    _wire: ("Envelope", "ContentPart", "DataPart", "FilePart", "TextPart", "ToolCallPart", "BaseSessionRunContext", "CallFrame",
+            "CallFrameStack", "Deps", "SessionRunContext", "Stack", "WorkflowState", "BaseAgentActivityState", "CoreMessageState",
+            "InFlightToolsState", "OverridesState", "State", "PendingToolBatch"),
+}
+__all__ = ["ToolContext"]
+for _mod, _names in _EXPORTS.items():
+    for _n in _names:
+        globals()[_n] = getattr(_mod, _n)
+        __all__.append(_n)
+del _mod, _names, _n

@@ -1,23 +1,4 @@
-"""Routing data of a node: id, subscribe topics, publish topic
-(reference calfkit/models/node_schema.py:6-21)."""
-from dataclasses import KW_ONLY, dataclass
+"""Routing data of a node (reference calfkit/models/node_schema.py:6-21): declared in calfkit/models/wire.py, re-exported under the reference's module path."""
+from calfkit.models.wire import BaseNodeSchema, BaseToolNodeSchema  # noqa: F401
 
-from calfkit.models.messages import ToolDefinition
-
-
-@dataclass
-class BaseNodeSchema:
-    _: KW_ONLY
-    node_id: str
-    subscribe_topics: list[str]
-    publish_topic: str | None
-
-    def __post_init__(self) -> None:
-        if not isinstance(self.subscribe_topics, (list, tuple)):
-            self.subscribe_topics = [self.subscribe_topics]
-
-
-@dataclass
-class BaseToolNodeSchema(BaseNodeSchema):
-    _: KW_ONLY
-    tool_schema: ToolDefinition
+__all__ = ['BaseNodeSchema', 'BaseToolNodeSchema']
