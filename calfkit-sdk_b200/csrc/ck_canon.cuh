@@ -19,6 +19,7 @@
 #define CK_CANON_CUH
 
 #include "ck_walk.cuh"
+#include "ck_float.cuh"
 
 #if defined(__CUDACC__)
 #define CK_HDR __host__ __device__          // recursive (mutually) functions: no forced inlining
@@ -301,8 +302,15 @@ CK_HD int cj_emit_number(const CIn& in, u32 a, u32 b, COut& o, bool as_float) {
     while (nd > 0 && D[nd - 1] == '0') nd--;                                  // trailing zeros are not significant
     if (overflow_digits) return CE_UNSUP;
     if (nd == 0) { if (neg) o.put('-'); CPUTS(o, "0.0"); return CE_OK; }      // +-0.0
-    if (nd > 15) return CE_UNSUP;                                             // needs a real shortest-digits printer
     if (e10 > 290 || e10 < -290) return CE_UNSUP;                             // near overflow / subnormal: not decided here
+    if (nd > 15) {
+        // 16-17 digits: only if they are exactly what repr() of the nearest double prints (csrc/ck_float.cuh, exact
+        // integer arithmetic); anything else would need a shortest-digits printer
+        if (nd > 17) return CE_UNSUP;
+        u64 m = 0;
+        for (u32 k = 0; k < nd; k++) m = m * 10 + (u64)(D[k] - '0');
+        if (!ckf_is_repr(m, e10 - (int)nd)) return CE_UNSUP;
+    }
     if (neg) o.put('-');
     // value = D[0].D[1..] * 10^(e10-1)
     int x = e10 - 1;

@@ -15,6 +15,7 @@
 #define CK_WALK_CUH
 
 #include "ck_common.h"
+#include "ck_float.cuh"
 
 #if defined(__CUDACC__)
 #define CK_HD __host__ __device__ __forceinline__
@@ -433,7 +434,8 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         // that is printed this way, and the value is far from overflow / subnormals (DBL_DIG argument).
         if (!allow_float || int_zero || int_len != 1) return false;
         if (is_float && r.at(frac_start + frac_len - 1) == '0') return false;
-        if (1 + frac_len > 15) return false;
+        if (1 + frac_len > 17) return false;
+        bool need_exact = (1 + frac_len > 15);      // 16-17 digits: decided exactly once the exponent is known
         p++;
         if (p >= r.n) return false;
         u8 sg = r.at(p);
@@ -445,6 +447,11 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         u32 x = 0, xl = 0;
         while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; x = x * 10 + (u32)(d - '0'); p++; if (++xl > 3) return false; }
         if (x > 290 || (sg == '-' ? x < 6 : x < 16)) return false;
+        if (need_exact) {
+            u64 m = (u64)(r.at(int_start) - '0');
+            for (u32 q = 0; q < frac_len; q++) m = m * 10 + (u64)(r.at(frac_start + q) - '0');
+            if (!ckf_is_repr(m, (sg == '-' ? -(int)x : (int)x) - (int)frac_len)) return false;
+        }
         return CK_RET(p);
     }
     if (p < r.n && r.at(p) == 'E') return false;
@@ -473,7 +480,16 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         if (lz == frac_len) { if (frac_len != 1) return false; sig = 1; }   // 0.0 / -0.0 only
         else { if (lz > 4) return false; sig = frac_len - lz; }             // < 1e-5 prints as 1e-6 ...
     }
-    if (sig > 15) return false;
+    if (sig > 15) {
+        // 16-17 significant digits (computed values such as 0.30000000000000004): a fixed point iff the literal is
+        // exactly what the shortest-round-trip printer emits for its double — decided in exact integer arithmetic
+        if (sig > 17) return false;
+        u64 m = 0; int k = -(int)frac_len;
+        for (u32 q = 0; q < int_len; q++) m = m * 10 + (u64)(r.at(int_start + q) - '0');
+        for (u32 q = 0; q < frac_len; q++) m = m * 10 + (u64)(r.at(frac_start + q) - '0');
+        while (m % 10 == 0) { m /= 10; k++; }
+        if (!ckf_is_repr(m, k)) return false;
+    }
     return CK_RET(p);
 }
 template <class R>
