@@ -401,7 +401,8 @@ CK_HD bool ck_string_or_null(R& r, u32& pos, Span& out) {
 // Numbers.  Canonical ints: -?(0|[1-9][0-9]*) except "-0".  Floats are accepted only in the
 // positional spelling whose round trip is provable without a shortest-digits printer:
 // -?INT.FRAC with <= 15 significant digits, no trailing fractional zero (except the single ".0"),
-// magnitude in [1e-5, 1e16)  (DBL_DIG argument, DESIGN.md §canonical numbers).
+// magnitude in [1e-5, 1e16)  (DBL_DIG argument, DESIGN.md §canonical numbers); with 16 or 17 digits the literal
+// must pass the exact "is repr of its double" test of ck_float.cuh.
 // -------------------------------------------------------------------------------------------------
 template <class R>
 CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allow_int, bool allow_float) {

@@ -460,3 +460,29 @@ def test_reply_outputs_match_reference_goldens_and_oracle(engine):
         except Exception as e:  # noqa: BLE001
             assert type(e).__name__ == "DeserializationError" and out.cols[COL["ACTION"], i] == CK_ACT_RAISES, (i, repr(e))
     assert n_ok > 50
+
+
+def test_long_floats_on_device(engine):
+    """16-17 digit floats (computed values such as 0.30000000000000004): accepted in place when they are the
+    shortest round-trip spelling (csrc/ck_float.cuh), in canonical and in re-spelled records; outputs byte-exact."""
+    import tools_def
+    from oracle import port
+    from calfkit import synth
+    from calfkit.engine import ToolTemplate
+    rng = random.Random(12)
+    _setup(engine, "get_weather", ToolTemplate.from_format("It's sunny in {location}"))
+    node = port.ToolNode.of(tools_def.get_weather)
+    base = synth.tool_events(300, seed=41)
+    recs = []
+    for k, r in enumerate(base):
+        vals = [repr(rng.choice([rng.random(), 0.1 + 0.2, rng.uniform(-1e6, 1e6), rng.random() * 1e-7, rng.random() * 1e18]))
+                for _ in range(rng.randrange(1, 6))]
+        i = r.index(b'"provided_deps":{') + len(b'"provided_deps":{')
+        j = r.index(b"}", i)
+        sep = b" , " if k % 3 == 0 else b","                       # every third record is re-spelled (canonicaliser path)
+        recs.append(r[:i] + b'"v":[' + sep.join(v.encode() for v in vals) + b"]" + r[j:])
+    b = synth.pack(recs)
+    out = engine.run_tool_batch(b.data, b.offsets)
+    assert (out.cols[0] == 0).all(), np.bincount(out.cols[0])
+    want = [(tp, k, pl) for r in recs for (tp, k, _c, pl) in port.tool_node_event(node, r)]
+    assert _pubs(out) == want
