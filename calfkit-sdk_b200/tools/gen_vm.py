@@ -445,8 +445,9 @@ def build() -> tuple[list[int], dict[str, int]]:
 
 
 def main():
+    import io
     words, labels = build()
-    with open(OUT, "w") as f:
+    with io.StringIO() as f:
         f.write("// GENERATED by calfkit-sdk_b200/tools/gen_vm.py — do not edit.\n")
         f.write("// Bytecode of the canonical-Envelope schema (one u32 per word; op = low 8 bits, arg = high 24).\n")
         f.write("#ifndef CK_VM_PROG_H\n#define CK_VM_PROG_H\n#include <stdint.h>\n\n")
@@ -462,6 +463,11 @@ def main():
         for i in range(0, len(words), 8):
             f.write("    " + ", ".join(f"0x{w:08x}u" for w in words[i:i + 8]) + ", \\\n")
         f.write("}\n\nstatic const uint32_t ck_vm_prog_host[CK_VM_PROG_WORDS] = CK_VM_PROG_INIT;\n\n#endif\n")
+        text = f.getvalue()
+    old = open(OUT).read() if os.path.exists(OUT) else None
+    if text != old:                      # an unchanged header keeps its mtime: no needless rebuild of the library
+        with open(OUT, "w") as g:
+            g.write(text)
 
     print(f"{OUT}: {len(words)} words, {len(labels)} labels")
 
