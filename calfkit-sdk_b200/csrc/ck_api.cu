@@ -261,8 +261,8 @@ static int launch_decode(ck_handle* h) {
         CKL(h) ck_canon_write_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen, h->d_coff, h->d_ovl, (long long)h->max_ovl,
                                                                  h->d_ovl_off, h->d_ovl_len);
         if (mode == 1) CKL(h) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else CKL(h) ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 1);
+        else if (mode == 2) CKL(h) ck_rewalk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
+        else CKL(h) ck_rewalk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 1);
         CUDA_TRY(h, cudaGetLastError());
     }
     return 0;

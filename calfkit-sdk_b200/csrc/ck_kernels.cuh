@@ -138,6 +138,11 @@ __global__ void __launch_bounds__(CK_WALK_THREADS, CK_WALK_MINB)
 ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRd>(v, n, cols, stride, mode); }
 __global__ void __launch_bounds__(CK_WALK_THREADS, 8)
 ck_walk_global_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<GRd>(v, n, cols, stride, mode); }
+// second walk of the decode pass (mode 1: only the records the canonicaliser re-emitted): the trusting readers
+__global__ void __launch_bounds__(CK_WALK_THREADS, CK_WALK_MINB)
+ck_rewalk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRdT>(v, n, cols, stride, mode); }
+__global__ void __launch_bounds__(CK_WALK_THREADS, 8)
+ck_rewalk_global_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<GRdT>(v, n, cols, stride, mode); }
 
 // ------------------------------------------------------------------------------------------------
 // canonicaliser kernels (ck_canon.cuh): one thread per record that the walker left as CK_NOT_CANONICAL.

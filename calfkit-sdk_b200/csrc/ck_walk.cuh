@@ -15,7 +15,6 @@
 #define CK_WALK_CUH
 
 #include "ck_common.h"
-#include "ck_float.cuh"
 
 #if defined(__CUDACC__)
 #define CK_HD __host__ __device__ __forceinline__
@@ -42,6 +41,7 @@ struct Span { u32 off, len; };
 // -------------------------------------------------------------------------------------------------
 struct GRd {
     static const bool kWindow = false;
+    static const bool kTrustFloats = false;   // see WRdT
     const u8* g;     // record start
     u32 n;           // record length
     const u64* wp;   // address of the cached aligned word
@@ -135,6 +135,7 @@ CK_HD_NOINLINE u32 ck_win_refill(const u8* gb, u32 ap, u32 lim) {
 
 struct WRd {
     static const bool kWindow = true;
+    static const bool kTrustFloats = false;
     const u8* g;     // record start
     u32 n;           // record length
     u32 wbase;       // window base in the aligned stream (multiple of 16), CK_WIN_NONE = nothing staged
@@ -191,6 +192,13 @@ struct WRd {
         x0 = ((u64)q1 << 32) | q0; x1 = ((u64)q3 << 32) | q2;
     }
 };
+
+// Readers for the second walk of the decode pass, over records the canonicaliser has just re-emitted: float literals
+// with 16-17 significant digits are taken on trust there, because ck_canon.cuh only emits such a literal after the
+// exact "is repr() of its double" test of ck_float.cuh.  The first walk (WRd / GRd) leaves them to the canonicaliser,
+// which keeps that arithmetic (bignums, 128-bit division) out of the hot kernel.
+struct WRdT : WRd { static const bool kTrustFloats = true; };
+struct GRdT : GRd { static const bool kTrustFloats = true; };
 
 // Look-ahead prefetch of the record stream into L1 (experiment knob): every lane walks its
 // own record, so almost every warp-level load has some lane missing L1; pulling the line CK_PF_DIST
@@ -402,7 +410,7 @@ CK_HD bool ck_string_or_null(R& r, u32& pos, Span& out) {
 // positional spelling whose round trip is provable without a shortest-digits printer:
 // -?INT.FRAC with <= 15 significant digits, no trailing fractional zero (except the single ".0"),
 // magnitude in [1e-5, 1e16)  (DBL_DIG argument, DESIGN.md §canonical numbers); with 16 or 17 digits the literal
-// must pass the exact "is repr of its double" test of ck_float.cuh.
+// is left to the canonicaliser, which applies the exact "is repr of its double" test of ck_float.cuh.
 // -------------------------------------------------------------------------------------------------
 template <class R>
 CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allow_int, bool allow_float) {
@@ -435,8 +443,7 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         // that is printed this way, and the value is far from overflow / subnormals (DBL_DIG argument).
         if (!allow_float || int_zero || int_len != 1) return false;
         if (is_float && r.at(frac_start + frac_len - 1) == '0') return false;
-        if (1 + frac_len > 17) return false;
-        bool need_exact = (1 + frac_len > 15);      // 16-17 digits: decided exactly once the exponent is known
+        if (1 + frac_len > (R::kTrustFloats ? 17u : 15u)) return false;     // 16-17 digits: the canonicaliser decides (WRdT)
         p++;
         if (p >= r.n) return false;
         u8 sg = r.at(p);
@@ -448,11 +455,6 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         u32 x = 0, xl = 0;
         while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; x = x * 10 + (u32)(d - '0'); p++; if (++xl > 3) return false; }
         if (x > 290 || (sg == '-' ? x < 6 : x < 16)) return false;
-        if (need_exact) {
-            u64 m = (u64)(r.at(int_start) - '0');
-            for (u32 q = 0; q < frac_len; q++) m = m * 10 + (u64)(r.at(frac_start + q) - '0');
-            if (!ckf_is_repr(m, (sg == '-' ? -(int)x : (int)x) - (int)frac_len)) return false;
-        }
         return CK_RET(p);
     }
     if (p < r.n && r.at(p) == 'E') return false;
@@ -481,16 +483,10 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         if (lz == frac_len) { if (frac_len != 1) return false; sig = 1; }   // 0.0 / -0.0 only
         else { if (lz > 4) return false; sig = frac_len - lz; }             // < 1e-5 prints as 1e-6 ...
     }
-    if (sig > 15) {
-        // 16-17 significant digits (computed values such as 0.30000000000000004): a fixed point iff the literal is
-        // exactly what the shortest-round-trip printer emits for its double — decided in exact integer arithmetic
-        if (sig > 17) return false;
-        u64 m = 0; int k = -(int)frac_len;
-        for (u32 q = 0; q < int_len; q++) m = m * 10 + (u64)(r.at(int_start + q) - '0');
-        for (u32 q = 0; q < frac_len; q++) m = m * 10 + (u64)(r.at(frac_start + q) - '0');
-        while (m % 10 == 0) { m /= 10; k++; }
-        if (!ckf_is_repr(m, k)) return false;
-    }
+    // 16-17 significant digits (computed values such as 0.30000000000000004) are a fixed point iff the literal is
+    // exactly what the shortest-round-trip printer emits for its double: decided by the canonicaliser in exact
+    // integer arithmetic (ck_float.cuh); this walk accepts them only on its say-so (WRdT)
+    if (sig > (R::kTrustFloats ? 17u : 15u)) return false;
     return CK_RET(p);
 }
 template <class R>

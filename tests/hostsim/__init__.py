@@ -34,6 +34,8 @@ def lib():
         _lib.ck_host_walk.restype = ctypes.c_int
         _lib.ck_host_walk_global.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_walk_global.restype = ctypes.c_int
+        _lib.ck_host_walk_trust.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
+        _lib.ck_host_walk_trust.restype = ctypes.c_int
         _lib.ck_host_num_cols.restype = ctypes.c_int
         _lib.ck_host_vm_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_vm_walk.restype = ctypes.c_int
@@ -56,6 +58,28 @@ def walk_global(payload: bytes):
     cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
     ok = L.ck_host_walk_global(payload, len(payload), cols.ctypes.data)
     return bool(ok), cols
+
+
+def walk_trust(payload: bytes):
+    """the second walk of the decode pass (WRdT): -> (accepted, cols)"""
+    L = lib()
+    cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
+    ok = L.ck_host_walk_trust(payload, len(payload), cols.ctypes.data)
+    return bool(ok), cols
+
+
+def decode(payload: bytes):
+    """the device decode pass as ck_submit runs it: walk; if not proven canonical, canonicalise and walk the re-emitted
+    bytes with the trusting reader.  -> (status 0 ok / other, canonical bytes or b"")"""
+    L = lib()
+    ok, _ = walk(payload)
+    if ok:
+        return 0, payload
+    st, out = canon(payload)
+    if st != 0:
+        return st, b""
+    cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
+    return (0 if L.ck_host_walk_trust(out, len(out), cols.ctypes.data) else 4), out
 
 
 def vm_walk(payload: bytes):
