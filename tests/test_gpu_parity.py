@@ -168,7 +168,7 @@ def test_device_walker_equals_host_build_on_fuzz(engine):
     b = synth.pack(recs)
     engine.submit(b.data, b.offsets)
     cols = engine.columns()
-    from hostsim import canon
+    from hostsim import canon, walk_trust
     ncmp = 50   # walker-owned columns (incl. the resolved tool call / existing result spans)
     for i, r in enumerate(recs):
         if len(r) == 0:
@@ -181,7 +181,7 @@ def test_device_walker_equals_host_build_on_fuzz(engine):
             assert cols[0, i] == st, (i, int(cols[0, i]), st, r[:200])
             if st != 0:
                 continue
-            ok, hc = walk(cbytes)
+            ok, hc = walk_trust(cbytes)          # the second walk of the decode pass (trusting reader, ck_walk.cuh WRdT)
             assert ok
         assert cols[0, i] == 0, (i, r[:200])
         assert (cols[2:ncmp, i] == hc[2:ncmp]).all(), i   # columns 0/1 (status/action) are owned by the kernels
