@@ -404,7 +404,7 @@ CK_HD int cj_emit_datetime(const CIn& in, u32 pos, COut& o) {
     const u8* s = in.p + a;
 #define two(k, v) cj_two(s, (k), (v))
     u32 y1, y2, mo, d, h, mi, sec;
-    if (!two(0, y1) || !two(2, y2) || s[4] != '-' || !two(5, mo) || s[7] != '-' || !two(8, d) || (s[10] != 'T' && s[10] != 't') ||
+    if (!two(0, y1) || !two(2, y2) || s[4] != '-' || !two(5, mo) || s[7] != '-' || !two(8, d) || (s[10] != 'T' && s[10] != 't' && s[10] != ' ' && s[10] != '_') ||
         !two(11, h) || s[13] != ':' || !two(14, mi) || s[16] != ':' || !two(17, sec)) return CE_UNSUP;
     u32 y = y1 * 100 + y2;
     if (y < 1 || mo < 1 || mo > 12 || d < 1 || h > 23 || mi > 59 || sec > 59) return CE_UNSUP;
@@ -412,7 +412,7 @@ CK_HD int cj_emit_datetime(const CIn& in, u32 pos, COut& o) {
     if (d > dim) return CE_UNSUP;
     u32 k = 19, len = b - a;
     u8 frac[6] = {'0', '0', '0', '0', '0', '0'}; bool has_frac = false;
-    if (k < len && s[k] == '.') {
+    if (k < len && (s[k] == '.' || s[k] == ',')) {
         k++;
         u32 nf = 0;
         while (k < len && cj_isdigit(s[k])) { if (nf < 6) frac[nf] = s[k]; nf++; k++; }
@@ -423,9 +423,9 @@ CK_HD int cj_emit_datetime(const CIn& in, u32 pos, COut& o) {
     u8 zone = 0; u32 oh = 0, om = 0; u8 sign = '+';
     if (k == len) zone = 0;
     else if ((s[k] == 'Z' || s[k] == 'z') && k + 1 == len) zone = 1;
-    else if ((s[k] == '+' || s[k] == '-') && k + 6 == len && s[k + 3] == ':') {
+    else if ((s[k] == '+' || s[k] == '-') && ((k + 6 == len && s[k + 3] == ':') || k + 5 == len)) {      // +HH:MM or +HHMM
         sign = s[k];
-        if (!two(k + 1, oh) || !two(k + 4, om) || oh > 23 || om > 59) return CE_UNSUP;
+        if (!two(k + 1, oh) || !two(k + (k + 6 == len ? 4 : 3), om) || oh > 23 || om > 59) return CE_UNSUP;
         zone = (oh == 0 && om == 0) ? 1 : 2;
     } else return CE_UNSUP;
 #undef two

@@ -104,3 +104,21 @@ def test_mutation_fuzz():
         if b:
             _check(bytes(b), stats)
     assert stats.get(0, 0) > 3000 and stats.get(3, 0) > 1000 and stats.get(2, 0) > 10000
+
+
+def test_datetime_spellings():
+    """separators T/t/space/_, fraction 1-9 digits after '.' or ',', Z/z, +HH:MM / +HHMM offsets: re-emitted exactly as pydantic
+    does, everything else declared unsupported or invalid, never re-spelled differently"""
+    from calfkit import synth
+    r = synth.tool_events(1, seed=3)[0]
+    i = r.index(b'"timestamp":"') + len(b'"timestamp":"')
+    j = r.index(b'"', i)
+    rng = random.Random(4)
+    stats: dict = {}
+    for _ in range(4000):
+        sep = rng.choice(["T", "t", " ", "_", "T", "x"])
+        frac = rng.choice(["", "", ".5", ",25", ".123456", ".1234567", ".000000", ".000", ".9999999999"])
+        zone = rng.choice(["", "Z", "z", "+00:00", "-00:00", "+0000", "+05:30", "-0530", "+23:59", "+24:00", "+01", "+1:00", "Z "])
+        s = f"{rng.randrange(1, 9999):04d}-{rng.randrange(0, 14):02d}-{rng.randrange(0, 33):02d}{sep}{rng.randrange(0, 25):02d}:{rng.randrange(0, 61):02d}:{rng.randrange(0, 61):02d}{frac}{zone}"
+        _check(r[:i] + s.encode() + r[j:], stats)
+    assert stats.get(0, 0) > 500
