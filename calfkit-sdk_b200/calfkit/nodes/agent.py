@@ -26,7 +26,7 @@ import pydantic_core
 
 from calfkit._types import AgentOutputT
 from calfkit.broker import Record
-from calfkit.engine._lib import CK_OK, COL, STATUS_NAMES
+from calfkit.engine._lib import CK_ACT_FANOUT, CK_OK, COL, STATUS_NAMES
 from calfkit.models import State
 from calfkit.models.messages import (ModelMessage, ModelRequest, ModelResponse, RetryPromptPart, ToolCallPart,
                                      ToolDefinition, ToolReturnPart)
@@ -165,12 +165,19 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
         engine.submit(data, offsets)
         cols = engine.columns()
         mv = memoryview(data)
+        ovl = engine.overlay()          # records that arrived in another spelling: their canonical re-emission (the columns refer to it)
         post: dict[str, list[tuple[int, bytes]]] = {"fanout": [], "return": []}
+        canonical_in: dict[int, Any] = {}
+        silent_returns: list[Record] = []
         for i in range(len(records)):
             if cols[COL["STATUS"], i] != CK_OK:
                 logger.error("record %d rejected: %s", i, STATUS_NAMES[int(cols[COL["STATUS"], i])])
                 continue
-            rec = mv[offsets[i]:offsets[i + 1]]
+            if ovl is not None and ovl[1][i] >= 0:
+                rec = memoryview(ovl[0])[int(ovl[1][i]):int(ovl[1][i]) + int(ovl[2][i])]
+            else:
+                rec = mv[offsets[i]:offsets[i + 1]]
+            canonical_in[i] = rec
             s0, s1 = 20, int(cols[COL["SOV_OFF"], i] + cols[COL["SOV_LEN"], i]) + 1       # the `state` object span
             state = State.model_validate_json(bytes(rec[s0:s1]))                             # LLM boundary
             fo, fl = int(cols[COL["FOV_OFF"], i]), int(cols[COL["FOV_LEN"], i])
@@ -180,10 +187,14 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
             deps = pydantic_core.from_json(bytes(rec[int(cols[COL["PD_OFF"], i]):][:int(cols[COL["PD_LEN"], i])]))
             action, new_state = self._llm_step(corr, state, deps)
             if action == "silent":
+                # Silent (aggregation still incomplete): nothing is routed, but the handler returns the inbound envelope and
+                # the worker publishes that return value to publish_topic (reference nodes/base.py:137-145, worker/worker.py:52-53)
+                if self.publish_topic:
+                    silent_returns.append(Record(self.publish_topic, bytes(rec), None, records[i].correlation_id or corr))
                 continue
             new_bytes = bytes(rec[:s0]) + new_state.model_dump_json().encode() + bytes(rec[s1:])
             post.setdefault(action, []).append((i, new_bytes))   # "tailcall": all requested tools invalid (agent.py:171-175)
-        produced: list[Record] = []
+        produced: list[Record] = list(silent_returns)
         now_ms = time.time_ns() // 1_000_000
         for kind, items in post.items():
             if not items:
@@ -202,7 +213,12 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
             for p in out.publishes():
                 src = recs2[p.record]
                 corr = src.correlation_id or (p.key.decode() if p.key else None)
-                produced.append(Record(p.topic, p.payload, p.key, corr))
+                payload = p.payload
+                if kind == "fanout" and p.key is None and out.cols[COL["ACTION"], p.record] == CK_ACT_FANOUT:
+                    # list[Call]: the handler's return value — what goes to publish_topic — is the INBOUND envelope, untouched:
+                    # run() worked on prepare_context's deep copy (reference nodes/base.py:64-68,88; tests/golden/agent_run.json)
+                    payload = bytes(canonical_in[items[p.record][0]])
+                produced.append(Record(p.topic, payload, p.key, corr))
         return produced
 
 

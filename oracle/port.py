@@ -146,9 +146,13 @@ def tool_node_event(node: ToolNode, payload: bytes, correlation_id: str | None =
 
 
 def agent_fanout(agent_name: str, subscribe_topic0: str, publish_topic: str | None,
-                 registry: dict[str, str], payload: bytes, sequential: bool = False) -> list[Published]:
-    """The data-parallel half of Agent.run after the (out-of-scope) LLM step: the state already
-    holds the tool calls; pending ones become Call(registry[name], state copy, id, agent_name)."""
+                 registry: dict[str, str], payload: bytes, sequential: bool = False, inbound: bytes | None = None) -> list[Published]:
+    """The data-parallel half of Agent.run after the (out-of-scope) LLM step (agent.py:132-211): `payload` is the
+    envelope with the post-LLM state (tool calls added, invalid ones already answered with a RetryPromptPart);
+    pending ones become Call(registry[name], state copy, id, agent_name).  `inbound`: the record the handler was
+    invoked with — for list[Call] the handler's return value, and so the publish_topic payload, is THAT envelope,
+    untouched (run() works on prepare_context's deep copy, nodes/base.py:64-68,88); without it the post-LLM
+    envelope stands in (what the device plan does: the host layer substitutes, calfkit/nodes/agent.py)."""
     envelope = decode(payload)
     correlation_id = envelope.context.deps.correlation_id
     ctx = prepare_context(envelope)
@@ -163,6 +167,8 @@ def agent_fanout(agent_name: str, subscribe_topic0: str, publish_topic: str | No
         output = [Call(registry[tc.tool_name], ctx.state.model_copy(deep=True), tc.tool_call_id, agent_name)
                   for tc in pending]
     pubs, returned = publish_action(subscribe_topic0, output, envelope, correlation_id)
+    if isinstance(output, list) and inbound is not None:
+        returned = decode(inbound)
     out: list[Published] = [(t, k, c, encode(e)) for (t, k, c, e) in pubs]
     if publish_topic:
         out.append((publish_topic, None, correlation_id, encode(returned)))

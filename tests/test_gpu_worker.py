@@ -63,10 +63,24 @@ def test_parallel_fanout_three_tools_and_aggregation():
         hs = [await client.invoke_node("go", "planner.input", deps={"tenant": f"t{i}"}) for i in range(20)]
         await worker.run(until_idle=True)
         res = [await h.result(timeout=5) for h in hs]
+        # publish_topic carries every handler return value (worker/worker.py:52-53): per conversation the inbound envelope
+        # of the fan-out turn (list[Call] returns the envelope it was given, nodes/base.py:88), two Silent returns while the
+        # aggregation is incomplete, and the final ReturnCall envelope
+        outs = client.broker.poll_batch(("planner.output",), 1000)
         await client.close()
-        return res
+        return res, outs
 
-    res = asyncio.run(go())
+    res, outs = asyncio.run(go())
+    import json as _json
+    by_corr: dict = {}
+    for rec in outs:
+        e = _json.loads(rec.value)
+        by_corr.setdefault(e["context"]["deps"]["correlation_id"], []).append(e)
+    assert len(by_corr) == 20 and all(len(v) == 4 for v in by_corr.values()), {k: len(v) for k, v in by_corr.items()}
+    for envs in by_corr.values():
+        first = [e for e in envs if not e["context"]["state"]["tool_calls"]]
+        assert len(first) == 1 and first[0]["context"]["state"]["uncommitted_message"] is not None      # the untouched inbound envelope
+        assert sum(1 for e in envs if e["context"]["state"]["final_output_parts"]) == 1
     for i, r in enumerate(res):
         assert r.output == f"A<v> | B<v> | C<v:t{i}>"
         calls = [m for m in r.message_history if getattr(m, "kind", "") == "response" and m.tool_calls]
