@@ -34,10 +34,150 @@ from calfkit.nodes.base import BaseNodeDef, pack_records
 logger = logging.getLogger(__name__)
 
 
+_SECTION_TITLES = {"args", "arguments", "params", "parameters", "keyword args", "keyword arguments", "other args", "other arguments",
+                   "other params", "other parameters", "raises", "exceptions", "returns", "yields", "receives", "examples", "example",
+                   "attributes", "functions", "methods", "classes", "modules", "warns", "warnings", "note", "notes", "see also"}
+_PARAM_TITLES = {"args", "arguments", "params", "parameters"}
+
+
+def _parse_docstring(doc: str | None, names: list[str]) -> tuple[str | None, dict[str, str]]:
+    """(description, {parameter: description}) of a Google / NumPy / Sphinx style docstring — what the reference obtains from
+    griffe (calfkit/_vendor/pydantic_ai/_griffe.py): the text before the first section (wrapped as <summary>…</summary> plus a
+    <returns> block when the docstring documents its return value), and the per-parameter texts, which go into the JSON
+    schema as `description`s.  Pinned by tests/golden/tool_schemas.json for the three styles; exotic layouts may differ."""
+    if not doc:
+        return None, {}
+    lines = inspect.cleandoc(doc).splitlines()
+    params: dict[str, str] = {}
+    main: list[str] = []
+    ret_type: str | None = None
+    ret_desc: str | None = None
+    i, n = 0, len(lines)
+    in_main = True
+
+    def indented(s: str) -> bool:
+        return s.startswith((" ", "\t"))
+
+    while i < n:
+        line = lines[i]
+        stripped = line.strip()
+        # ---- Sphinx field list
+        if stripped.startswith(":") and not indented(line) and ":" in stripped[1:]:
+            head, _, desc = stripped[1:].partition(":")
+            words = head.split()
+            kind = words[0] if words else ""
+            if kind in ("param", "parameter", "arg", "argument", "key", "keyword", "return", "returns", "rtype", "raises", "raise", "type", "var", "ivar", "cvar"):
+                in_main = False
+                body = [desc.strip()]
+                j = i + 1
+                while j < n and indented(lines[j]):
+                    body.append(lines[j].strip())
+                    j += 1
+                text = "\n".join(x for x in body if x)
+                if kind in ("param", "parameter", "arg", "argument", "key", "keyword") and words[-1] in names:
+                    params[words[-1]] = text
+                elif kind in ("return", "returns"):
+                    ret_desc = text
+                elif kind == "rtype":
+                    ret_type = text
+                i = j
+                continue
+        # ---- NumPy section: a title underlined with dashes
+        if i + 1 < n and stripped and lines[i + 1].strip() and set(lines[i + 1].strip()) == {"-"} and stripped.lower() in _SECTION_TITLES:
+            in_main = False
+            title = stripped.lower()
+            j = i + 2
+            entries: list[tuple[str, list[str]]] = []
+            while j < n and not (j + 1 < n and lines[j].strip() and lines[j + 1].strip() and set(lines[j + 1].strip()) == {"-"}):
+                raw = lines[j]
+                if raw.strip():
+                    if not indented(raw):
+                        entries.append((raw.strip(), []))
+                    elif entries:
+                        entries[-1][1].append(raw.strip())
+                j += 1
+            if title in _PARAM_TITLES:
+                for head, body in entries:
+                    name = head.split(":")[0].strip()
+                    if name in names:
+                        params[name] = "\n".join(body)
+            elif title == "returns" and entries:
+                head, body = entries[0]
+                ret_type = head.split(":")[-1].strip() or None
+                ret_desc = "\n".join(body)
+            i = j
+            continue
+        # ---- Google section: "Title:" on its own line, body indented
+        if stripped.endswith(":") and stripped[:-1].lower() in _SECTION_TITLES and not indented(line):
+            in_main = False
+            title = stripped[:-1].lower()
+            j = i + 1
+            entries = []
+            base_indent = None
+            while j < n and (not lines[j].strip() or indented(lines[j])):
+                raw = lines[j]
+                if raw.strip():
+                    indent = len(raw) - len(raw.lstrip())
+                    if base_indent is None:
+                        base_indent = indent
+                    if indent <= base_indent:
+                        entries.append((raw.strip(), []))
+                    elif entries:
+                        entries[-1][1].append(raw.strip())
+                j += 1
+            if title in _PARAM_TITLES:
+                for head, body in entries:
+                    if ":" not in head:
+                        continue
+                    h, _, desc = head.partition(":")
+                    name = h.split("(")[0].strip().lstrip("*")
+                    if name in names:
+                        params[name] = "\n".join([desc.strip()] + body).strip()
+            elif title == "returns" and entries:
+                head, body = entries[0]
+                if ":" in head and " " not in head.split(":")[0].strip():
+                    ret_type, _, first = head.partition(":")
+                    ret_type = ret_type.strip()
+                else:
+                    first = head
+                ret_desc = "\n".join([first.strip()] + body + [h for h, _ in entries[1:]]).strip()
+            i = j
+            continue
+        if in_main:
+            main.append(line)
+        i += 1
+    text = "\n".join(main).strip()
+    if ret_desc is not None:
+        type_tag = f"<type>{ret_type}</type>\n" if ret_type else ""
+        ret_xml = f"<returns>\n{type_tag}<description>{ret_desc}</description>\n</returns>"
+        text = f"<summary>{text}</summary>\n{ret_xml}" if text else ret_xml
+    return (text or None), params
+
+
+def _sorted_schema(value: Any, parent_key: str | None = None) -> Any:
+    """key order of pydantic's GenerateJsonSchema.sort: alphabetical, except the members of `properties` (declaration
+    order) and whatever sits under `default`; the schema travels inside OverridesState, so its byte order is part of the wire"""
+    if isinstance(value, dict):
+        keys = list(value) if parent_key in ("properties", "default") else sorted(value)
+        return {k: _sorted_schema(value[k], None if parent_key == "default" and False else k) for k in keys}
+    if isinstance(value, list):
+        return [_sorted_schema(v, parent_key) for v in value]
+    return value
+
+
+def _is_context_annotation(ann: Any) -> bool:
+    if isinstance(ann, str):
+        return ann.split("[")[0].split(".")[-1] in ("ToolContext", "RunContext")
+    origin = getattr(ann, "__origin__", None) or ann
+    return isinstance(origin, type) and issubclass(origin, ToolContext)
+
+
 @dataclass
 class Tool:
-    """Minimal stand-in for pydantic_ai.Tool: the callable + its ToolDefinition (name, docstring,
-    JSON schema of the keyword parameters).  reference: calfkit/_vendor/pydantic_ai/tools.py Tool."""
+    """Minimal stand-in for pydantic_ai.Tool: the callable + its ToolDefinition (name, description, JSON schema of the
+    parameters the model supplies).  reference: calfkit/_vendor/pydantic_ai/tools.py Tool + _function_schema.py — a first
+    parameter ANNOTATED with the context type is injected and hidden from the schema (_takes_ctx, :236-270); parameter
+    descriptions come from the docstring."""
     function: Callable[..., Any]
     takes_ctx: bool = False
     tool_def: ToolDefinition = field(init=False)
@@ -45,19 +185,28 @@ class Tool:
     def __post_init__(self) -> None:
         sig = inspect.signature(self.function)
         params = list(sig.parameters.values())
-        if params and (params[0].annotation is ToolContext or params[0].name == "ctx"):
+        try:
+            import typing
+            hints = typing.get_type_hints(self.function)
+        except Exception:  # noqa: BLE001  (unresolvable forward references: fall back to the raw annotations)
+            hints = {}
+        if params and _is_context_annotation(hints.get(params[0].name, params[0].annotation)):
             self.takes_ctx = True
             params = params[1:]
-        fields = {p.name: ((p.annotation if p.annotation is not inspect.Parameter.empty else Any),
-                           (... if p.default is inspect.Parameter.empty else p.default)) for p in params}
+        main, pdesc = _parse_docstring(inspect.getdoc(self.function), [p.name for p in params])
+        fields = {}
+        for p in params:
+            ann = hints.get(p.name, p.annotation if p.annotation is not inspect.Parameter.empty else Any)
+            default = ... if p.default is inspect.Parameter.empty else p.default
+            fields[p.name] = (ann, pydantic.Field(default, description=pdesc[p.name]) if p.name in pdesc else default)
         model = pydantic.create_model(f"{self.function.__name__}_args", **fields)      # type: ignore[call-overload]
         schema = model.model_json_schema()
         schema.pop("title", None)
         for prop in schema.get("properties", {}).values():
             prop.pop("title", None)
         schema.setdefault("additionalProperties", False)
-        self.tool_def = ToolDefinition(name=self.function.__name__, parameters_json_schema=schema,
-                                       description=inspect.getdoc(self.function))
+        schema.setdefault("properties", {})
+        self.tool_def = ToolDefinition(name=self.function.__name__, parameters_json_schema=_sorted_schema(schema), description=main)
 
 
 @dataclass
@@ -116,10 +265,14 @@ class ToolNodeDef(BaseToolNodeDef):
             blob, off, ln = engine.tool_args()
             cols = engine.columns()
             mv = memoryview(data)
+            ovl = engine.overlay() if self._tool.takes_ctx else None     # the column spans refer to the canonical spelling of a record
             results: list[bytes] = []
             for i in range(len(records)):
                 if cols[COL["ACTION"], i] == CK_ACT_HOST_TOOL:
-                    rec = mv[offsets[i]:offsets[i + 1]]
+                    if ovl is not None and ovl[1][i] >= 0:
+                        rec = memoryview(ovl[0])[int(ovl[1][i]):int(ovl[1][i]) + int(ovl[2][i])]
+                    else:
+                        rec = mv[offsets[i]:offsets[i + 1]]
                     results.append(self._call_host(blob[off[i]:off[i] + ln[i]].tobytes(), rec, cols, i))
                 else:
                     results.append(b"")

@@ -109,3 +109,55 @@ def test_murmur2_vectorised_matches_kafka_reference():
     assert _murmur2(b"foobar") == 0xFFFFFFFF & -790332482
     assert _murmur2(b"a-little-bit-long-string") == 0xFFFFFFFF & -985981536
     assert _murmur2(b"") == 275646681
+
+
+def test_tool_definitions_match_reference_byte_for_byte():
+    """What @agent_tool derives from a function — node id, topics and the ToolDefinition (name, description incl. the
+    <summary>/<returns> wrapping, JSON schema with per-parameter descriptions, key order) — against the unmodified
+    reference (tests/golden/tool_schemas.json, made by tests/golden/make_golden_schemas.py).  The definition travels in
+    OverridesState on the wire, so its byte order matters.  A context parameter is recognised by its ANNOTATION, as in
+    the reference (_function_schema._takes_ctx): an un-annotated `ctx` is an ordinary argument."""
+    import json
+    import os
+    import sys
+    from pydantic import TypeAdapter
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tools_def
+    import tools_more
+    from calfkit import agent_tool
+    from calfkit.models import ToolContext
+    tools_more.ToolContext = ToolContext
+    gold = {c["name"]: c for c in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tool_schemas.json")))["cases"]}
+    fns = {**tools_def.TOOLS, **tools_more.MORE}
+    assert set(fns) == set(gold)
+    for name, fn in fns.items():
+        node = agent_tool(fn)
+        g = gold[name]
+        assert (node.node_id, list(node.subscribe_topics), node.publish_topic) == (g["node_id"], g["subscribe_topics"], g["publish_topic"])
+        mine = json.dumps(json.loads(TypeAdapter(type(node.tool_schema)).dump_json(node.tool_schema)))
+        assert mine == json.dumps(g["tool_schema"]), name
+    assert agent_tool(tools_more.with_ctx)._tool.takes_ctx and not agent_tool(tools_more.contextual)._tool.takes_ctx
+
+
+def test_host_tool_call_with_context_from_columns():
+    """the host half of a contextual tool call (ToolNodeDef._call_host): the ToolContext is rebuilt from the column spans
+    of the record — here produced by the CPU build of the walker (tests/hostsim) — exactly as the GPU path hands them over"""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tools_more
+    from hostsim import walk
+    from calfkit import agent_tool, synth
+    from calfkit.models import ToolContext
+    tools_more.ToolContext = ToolContext
+    node = agent_tool(tools_more.with_ctx)
+    rec = synth.tool_events(1, seed=5)[0]
+    ok, cols = walk(rec)
+    assert ok
+    i = rec.index(b'"provided_deps":{') + len(b'"provided_deps":{')
+    rec2 = rec[:i] + b'"tenant":"acme",' + rec[i:]
+    ok, cols = walk(rec2)
+    assert ok
+    out = node._call_host(b'{"q":"ab","n":3}', memoryview(rec2), cols.reshape(-1, 1), 0)
+    assert out == b'"acme:ababab"'

@@ -44,8 +44,10 @@ def test_parallel_fanout_three_tools_and_aggregation():
         """b"""
         return f"B<{x}>"
 
+    from calfkit.models import ToolContext
+
     @agent_tool
-    def tool_c(ctx, x: str) -> str:
+    def tool_c(ctx: ToolContext, x: str) -> str:
         """c: contextual tool reading provided deps"""
         return f"C<{x}:{ctx.deps.provided_deps['tenant']}>"
 
