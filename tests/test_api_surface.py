@@ -161,3 +161,70 @@ def test_host_tool_call_with_context_from_columns():
     assert ok
     out = node._call_host(b'{"q":"ab","n":3}', memoryview(rec2), cols.reshape(-1, 1), 0)
     assert out == b'"acme:ababab"'
+
+
+def test_client_first_envelope_matches_reference_bytes():
+    """Client.invoke_node -> the first envelope of a correlation chain, byte for byte what the unmodified reference's client
+    publishes for the same arguments (tests/golden/client_invoke.json: deps, temp_instructions, history, run_args, tool
+    overrides carrying ToolDefinitions), unkeyed, with the same handle."""
+    import asyncio
+    import datetime as dt
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tools_def
+    import tools_more
+    from calfkit import _ids, agent_tool
+    from calfkit.client import Client
+    from calfkit.models import ToolContext, messages
+    tools_more.ToolContext = ToolContext
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "client_invoke.json")))
+    fixed = dt.datetime.fromisoformat(gold["frozen_clock"])
+
+    class Conn:
+        _connection = True
+
+        def __init__(self):
+            self.published = []
+
+        async def publish(self, envelope, topic, correlation_id, **kw):
+            self.published.append({"topic": topic, "correlation_id": correlation_id, "key": kw.get("key"), "payload": envelope.model_dump_json()})
+
+    class Disp:
+        def expect(self, correlation_id):
+            return None
+
+    history = [messages.ModelRequest(parts=[messages.UserPromptPart(content="earlier question")]),
+               messages.ModelResponse(parts=[messages.TextPart(content="earlier answer")], timestamp=fixed)]
+    overrides = [agent_tool(tools_def.TOOLS["get_weather"]), agent_tool(tools_more.with_defaults), agent_tool(tools_more.google_multiline)]
+    for case in gold["cases"]:
+        kw = dict(case["args"])
+        if kw.get("message_history") == "HISTORY":
+            kw["message_history"] = list(history)
+        if kw.get("tool_overrides") == "OVERRIDES":
+            kw["tool_overrides"] = list(overrides)
+        counter = [0]
+
+        def det():
+            counter[0] += 1
+            return f"{counter[0]:032x}"
+        _ids.set_id_source(det)
+        old_now = messages.now_utc
+        try:
+            conn = Conn()
+            client = Client(conn, "calf-client-reply-test", Disp())
+            handle = asyncio.run(client.invoke_node(**kw))
+        finally:
+            _ids.set_id_source(None)
+        assert len(conn.published) == 1
+        got = conn.published[0]
+        # the user-prompt timestamps are "now": align them with the golden's frozen clock before comparing bytes
+        want = case["publish"]
+        import re
+        stamp = fixed.isoformat().replace("+00:00", "Z")
+        norm = lambda s: re.sub(r'"timestamp":"[^"]+"', '"timestamp":"%s"' % stamp, s)   # noqa: E731
+        assert (got["topic"], got["correlation_id"], got["key"]) == (want["topic"], want["correlation_id"], want["key"]), case["name"]
+        assert norm(got["payload"]) == norm(want["payload"]), case["name"]
+        assert (handle.correlation_id, handle.topic, handle.reply_topic) == tuple(case["handle"][k] for k in ("correlation_id", "topic", "reply_topic"))
+        del old_now
