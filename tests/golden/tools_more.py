@@ -112,3 +112,80 @@ def google_multiline(text: str, width: int = 80) -> str:
 
 MORE = {f.__name__: f for f in (with_defaults, numeric, optional_and_lists, nested, no_doc, contextual, with_ctx, numpy_style, sphinx_style,
                                 google_multiline)}
+
+
+# ---- return-value variety (tests/golden/make_golden_returns.py): how a tool's Python return value lands in the envelope
+import dataclasses as _dc
+import datetime as _dt
+import decimal as _dec
+import enum as _enum
+import uuid as _uuid
+
+import pydantic as _pyd
+
+
+class Reading(_pyd.BaseModel):
+    city: str
+    temp: float
+    tags: list[str] = []
+
+
+@_dc.dataclass
+class Point:
+    x: int
+    y: float
+
+
+class Color(_enum.Enum):
+    RED = "red"
+
+
+def returns_dict(k: str) -> dict:
+    """d"""
+    return {"k": k, "n": [1, 2.5, None, True], "nested": {"é": "ü\n\t\"q\""}}
+
+
+def returns_list(n: int) -> list:
+    """l"""
+    return [i * 1.5 for i in range(n)]
+
+
+def returns_none(x: str) -> None:
+    """n"""
+    return None
+
+
+def returns_bool(x: str) -> bool:
+    """b"""
+    return x == "yes"
+
+
+def returns_model(city: str) -> Reading:
+    """m"""
+    return Reading(city=city, temp=21.700000000000003, tags=["a"])
+
+
+def returns_dataclass(x: int) -> Point:
+    """dc"""
+    return Point(x=x, y=0.1 + 0.2)
+
+
+def returns_datetime(x: str) -> _dt.datetime:
+    """dt"""
+    return _dt.datetime(2026, 1, 2, 3, 4, 5, 600, tzinfo=_dt.timezone.utc)
+
+
+def returns_tuple_set(x: str) -> tuple:
+    """t"""
+    return (x, 1, frozenset([3]))
+
+
+def returns_misc(x: str) -> dict:
+    """misc"""
+    return {"dec": _dec.Decimal("1.50"), "uuid": _uuid.UUID(int=5), "enum": Color.RED, "bytes": b"hi", "date": _dt.date(2026, 1, 2),
+            "big": 2 ** 70, "neg0": -0.0, "exp": 1e22, "small": 1e-7}
+
+
+RETURNS = {f.__name__: (f, a) for f, a in ((returns_dict, {"k": "v"}), (returns_list, {"n": 4}), (returns_none, {"x": "a"}), (returns_bool, {"x": "yes"}),
+                                            (returns_model, {"city": "Kraków"}), (returns_dataclass, {"x": 3}), (returns_datetime, {"x": "a"}),
+                                            (returns_tuple_set, {"x": "a"}), (returns_misc, {"x": "a"}))}

@@ -228,3 +228,47 @@ def test_client_first_envelope_matches_reference_bytes():
         assert norm(got["payload"]) == norm(want["payload"]), case["name"]
         assert (handle.correlation_id, handle.topic, handle.reply_topic) == tuple(case["handle"][k] for k in ("correlation_id", "topic", "reply_topic"))
         del old_now
+
+
+def test_host_tool_return_values_encode_like_the_reference():
+    """ToolNodeDef._call_host's JSON for a tool's Python return value (dict, list, None, pydantic model, dataclass, datetime,
+    Decimal / UUID / Enum / bytes, big ints, 17-digit floats) is exactly what the unmodified reference put into
+    tool_results[id].return_value (tests/golden/tool_returns.json)."""
+    import json
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tools_more
+    from calfkit import agent_tool
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tool_returns.json")))["cases"]
+    for case in gold:
+        assert case["raises"] is None
+        fn, args = tools_more.RETURNS[case["name"]]
+        node = agent_tool(fn)
+        got = node._call_host(json.dumps(args, ensure_ascii=False).encode(), memoryview(b""), np.zeros((1, 1), dtype=np.uint32), 0)
+        payload = case["publishes"][0]["payload"]
+        want_prefix = '"tool_results":{"call_1":{"return_value":'
+        i = payload.index(want_prefix) + len(want_prefix)
+        j = payload.index(',"content":null,"metadata":{"tool_call_id":"call_1"}', i)
+        assert got.decode() == payload[i:j], case["name"]
+
+
+def test_product_reply_projection_matches_reference_goldens():
+    """calfkit.client.deserialize (the per-request projection behind InvocationHandle.result) on tests/golden/replies.json"""
+    import json
+    import os
+    import pydantic_core
+    from calfkit.client.deserialize import _UNSET, deserialize_to_node_result
+    from calfkit.models import Envelope
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "replies.json")))["cases"]
+    for case in gold:
+        for label, ot in (("auto", _UNSET), ("str", str), ("dict", dict)):
+            exp = case["expect"][label]
+            try:
+                res = deserialize_to_node_result(Envelope.model_validate_json(case["input"]), ot)
+                assert exp["ok"] and pydantic_core.to_json(res.output).decode() == exp["output_json"] and res.correlation_id == exp["correlation_id"]
+            except AssertionError:
+                raise
+            except Exception as e:  # noqa: BLE001
+                assert not exp["ok"] and type(e).__name__ == exp["error"], (case["name"], label, repr(e))
