@@ -272,3 +272,40 @@ def test_product_reply_projection_matches_reference_goldens():
                 raise
             except Exception as e:  # noqa: BLE001
                 assert not exp["ok"] and type(e).__name__ == exp["error"], (case["name"], label, repr(e))
+
+
+def test_agent_host_half_matches_reference_run():
+    """The host half of the Agent node (Agent._llm_step: aggregation gate, history bookkeeping around the model call, invalid
+    tool handling, routing decision) against the unmodified reference's Agent.run on the same inbound envelopes and the same
+    scripted model answers (tests/golden/agent_run.json): same action, same post-LLM state bytes (the RetryPromptPart
+    timestamps are "now" on both sides and are aligned before comparing), same pending batch."""
+    import datetime as dt
+    import json
+    import os
+    import re
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tools_def
+    from calfkit import Agent, agent_tool
+    from calfkit.models import Envelope, messages
+    from calfkit.nodes import FunctionModelClient
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "agent_run.json")))["cases"]
+    tools = [agent_tool(tools_def.TOOLS[n]) for n in ("get_weather", "get_temperature", "count_chars")]
+    fixed = dt.datetime(2026, 1, 1, tzinfo=dt.timezone.utc)
+    norm = lambda s: re.sub(r'"timestamp":"[^"]+"', '"timestamp":"T"', s)   # noqa: E731
+    want_action = {"list[Call]": "fanout", "Call": "fanout", "TailCall": "tailcall", "ReturnCall": "return"}
+    for case in gold:
+        answer = case["model_answer"]
+
+        def model(msgs, tool_defs, answer=answer):
+            if isinstance(answer, str):
+                return messages.ModelResponse(parts=[messages.TextPart(content=answer)], timestamp=fixed)
+            return messages.ModelResponse(parts=[messages.ToolCallPart(tool_name=t, args=a, tool_call_id=c) for (t, a, c) in answer], timestamp=fixed)
+        agent = Agent("planner", subscribe_topics="planner.input", publish_topic="planner.output", tools=tools,
+                      model_client=FunctionModelClient(model), sequential_only_mode=case["sequential"])
+        env = Envelope.model_validate_json(case["input"])
+        action, state = agent._llm_step(env.context.deps.correlation_id, env.context.state, env.context.deps.provided_deps)
+        assert action == want_action[case["action"]], (case["name"], action)
+        assert norm(state.model_dump_json()) == norm(case["post_llm_state"]), case["name"]
+        pend = sorted(next(iter(agent._pending_batches.values())).expected_tool_call_ids) if agent._pending_batches else None
+        assert pend == case["pending_batch_ids"], case["name"]
