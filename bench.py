@@ -744,6 +744,10 @@ def main() -> None:
     sample_n = args.cpu_sample or max(cores * 8000, 20000)       # ~10-20 s of CPU work on all cores
     sample = [batch.record(i) for i in range(min(sample_n, n))]
     cpu_value, cpu_dt, cpu_n = cpu_arm(sample, cores, start="spawn")   # CUDA is initialised in this process: no fork
+    try:                                                                # SURVEY 8d also asks for the single-core figure
+        one_core_value, _dt1, _n1 = cpu_arm(sample[:3000], 1, start="spawn")
+    except Exception:  # noqa: BLE001  (never let the extra figure cost the bench line)
+        one_core_value = None
     # parity spot check against the oracle on the same bytes (byte-exact), outside all timed regions
     from oracle import port
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
@@ -774,7 +778,8 @@ def main() -> None:
         "gpu_launches": gpu_launches,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes (oracle/port.py)"},
+                         "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes (oracle/port.py)",
+                         "one_core": {"value": one_core_value, "unit": UNIT, "sample": "3000 events, 1 process"}},
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
