@@ -160,13 +160,27 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
         engine.set_tool_node(self.publish_topic, None)        # publish-topic id for the ReturnCall plan
         engine.set_agent_node(self.name, self.subscribe_topics[0], self.publish_topic, registry)
 
+    # ---- per-request tool registries (overrides.override_agent_tools, reference agent.py:71-75) ------------------------
+    def _use_registry(self, engine, registry: dict[str, str]) -> list[str]:
+        """point the device fan-out plan at a request's own tool registry; returns the topic list to restore afterwards"""
+        topics = [engine.topic_names[i] for i in sorted(engine.topic_names)]
+        extra = [t for t in dict.fromkeys(registry.values()) if t not in engine.topic_ids]
+        if extra:
+            engine.register_topics(topics + extra, num_partitions=engine.num_partitions)    # same order first: ids stay put
+        engine.set_agent_node(self.name, self.subscribe_topics[0], self.publish_topic, registry)
+        return topics
+
+    def _restore_registry(self, engine, topics: list[str]) -> None:
+        engine.register_topics(topics, num_partitions=engine.num_partitions)
+        self.configure_engine(engine)
+
     def process_batch(self, engine, records: list[Record]) -> list[Record]:
         data, offsets = pack_records(records)
         engine.submit(data, offsets)
         cols = engine.columns()
         mv = memoryview(data)
         ovl = engine.overlay()          # records that arrived in another spelling: their canonical re-emission (the columns refer to it)
-        post: dict[str, list[tuple[int, bytes]]] = {"fanout": [], "return": []}
+        post: dict[Any, list[tuple[int, bytes]]] = {"fanout": [], "return": []}
         canonical_in: dict[int, Any] = {}
         silent_returns: list[Record] = []
         for i in range(len(records)):
@@ -193,24 +207,37 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
                     silent_returns.append(Record(self.publish_topic, bytes(rec), None, records[i].correlation_id or corr))
                 continue
             new_bytes = bytes(rec[:s0]) + new_state.model_dump_json().encode() + bytes(rec[s1:])
-            post.setdefault(action, []).append((i, new_bytes))   # "tailcall": all requested tools invalid (agent.py:171-175)
+            group: Any = action                                   # "tailcall": all requested tools invalid (agent.py:171-175)
+            if action == "fanout" and new_state.overrides is not None and new_state.overrides.override_agent_tools is not None:
+                # this request brought its own tool set: its calls are routed with that registry, in a group of their own
+                reg = {t.tool_schema.name: t.subscribe_topics[0] for t in new_state.overrides.override_agent_tools}
+                if reg != {t.tool_schema.name: t.subscribe_topics[0] for t in self.tools}:
+                    group = ("fanout", tuple(sorted(reg.items())))
+            post.setdefault(group, []).append((i, new_bytes))
         produced: list[Record] = list(silent_returns)
         now_ms = time.time_ns() // 1_000_000
-        for kind, items in post.items():
+        for group, items in post.items():
             if not items:
                 continue
+            kind, override_registry = (group[0], dict(group[1])) if isinstance(group, tuple) else (group, None)
             recs2 = [Record(records[i].topic, b, records[i].key, records[i].correlation_id) for i, b in items]
             d2, o2 = pack_records(recs2)
-            engine.submit(d2, o2)                                                            # re-validated on the device
-            seed = int(np.random.SeedSequence().entropy) & ((1 << 63) - 1)
-            if kind == "fanout":
-                engine.fanout_plan(now_ms, seed, max_fanout=256, sequential=self.sequential_only_mode)
-            elif kind == "return":
-                engine.return_plan()
-            else:
-                engine.tailcall_plan(now_ms, seed)
-            out = engine.fetch()
-            for p in out.publishes():
+            saved_topics = self._use_registry(engine, override_registry) if override_registry is not None else None
+            try:
+                engine.submit(d2, o2)                                                        # re-validated on the device
+                seed = int(np.random.SeedSequence().entropy) & ((1 << 63) - 1)
+                if kind == "fanout":
+                    engine.fanout_plan(now_ms, seed, max_fanout=256, sequential=self.sequential_only_mode)
+                elif kind == "return":
+                    engine.return_plan()
+                else:
+                    engine.tailcall_plan(now_ms, seed)
+                out = engine.fetch()
+                publishes = list(out.publishes())                 # topic ids are resolved against the registry in force
+            finally:
+                if saved_topics is not None:
+                    self._restore_registry(engine, saved_topics)
+            for p in publishes:
                 src = recs2[p.record]
                 corr = src.correlation_id or (p.key.decode() if p.key else None)
                 payload = p.payload

@@ -315,3 +315,49 @@ def test_agent_host_half_matches_reference_run():
         assert norm(state.model_dump_json()) == norm(case["post_llm_state"]), case["name"]
         pend = sorted(next(iter(agent._pending_batches.values())).expected_tool_call_ids) if agent._pending_batches else None
         assert pend == case["pending_batch_ids"], case["name"]
+
+
+def test_agent_per_request_registry_switch_and_restore():
+    """A request that brings its own tools (overrides.override_agent_tools, reference agent.py:71-75) is routed with that
+    registry: the Agent points the engine at it for that group of the batch and puts the node's own configuration back
+    afterwards — checked here on a recording stand-in for the engine (the device plan itself is the same fan-out kernel)."""
+    from calfkit import Agent, agent_tool
+    from calfkit.nodes import FunctionModelClient
+
+    @agent_tool
+    def own(x: str) -> str:
+        """own"""
+        return x
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+            self.topic_names, self.topic_ids, self.num_partitions = {}, {}, 8
+
+        def register_topics(self, names, num_partitions=0):
+            uniq = list(dict.fromkeys(names))
+            self.topic_names = dict(enumerate(uniq))
+            self.topic_ids = {n: i for i, n in enumerate(uniq)}
+            self.calls.append(("register_topics", tuple(uniq)))
+
+        def set_tool_node(self, publish_topic, template):
+            self.calls.append(("set_tool_node", publish_topic))
+
+        def set_agent_node(self, name, cb, publish_topic, registry):
+            assert all(t in self.topic_ids for t in registry.values())
+            self.calls.append(("set_agent_node", tuple(sorted(registry.items()))))
+
+    agent = Agent("planner", subscribe_topics="planner.input", publish_topic="planner.output", tools=[own],
+                  model_client=FunctionModelClient(lambda m, t: None))
+    eng = Rec()
+    eng.register_topics(["planner.input", "planner.output", "tool.own.input"], num_partitions=8)
+    agent.configure_engine(eng)
+    ids_before = dict(eng.topic_ids)
+    eng.calls.clear()
+    saved = agent._use_registry(eng, {"other": "tool.other.input", "own": "tool.own.input"})
+    assert saved == ["planner.input", "planner.output", "tool.own.input"]
+    assert all(eng.topic_ids[k] == v for k, v in ids_before.items()) and "tool.other.input" in eng.topic_ids      # ids stay put
+    assert eng.calls[-1] == ("set_agent_node", (("other", "tool.other.input"), ("own", "tool.own.input")))
+    agent._restore_registry(eng, saved)
+    assert eng.topic_ids == ids_before
+    assert eng.calls[-1] == ("set_agent_node", (("own", "tool.own.input"),)) and ("set_tool_node", "planner.output") in eng.calls
