@@ -253,7 +253,7 @@ class ToolNodeDef(BaseToolNodeDef):
         else:
             result = self._tool.function(**kwargs)
         if inspect.isawaitable(result):
-            raise TypeError("async tools must be awaited by the caller: wrap them with asyncio.run or use a sync tool")
+            result = _run_awaitable(result)      # `async def` tools (the reference awaits them, nodes/tool.py:64)
         return pydantic_core.to_json(result)
 
     def process_batch(self, engine, records: list[Record]) -> list[Record]:
@@ -292,6 +292,23 @@ class ToolNodeDef(BaseToolNodeDef):
                 corr = p.key.decode()
             produced.append(Record(p.topic, p.payload, p.key, corr))
         return produced
+
+
+def _run_awaitable(aw: Any) -> Any:
+    """Drive an async tool to completion from the (synchronous) batch step: directly when no event loop is running in
+    this thread, else on a short-lived worker thread with its own loop (Worker.run calls the batch step from inside its
+    loop, where asyncio.run() is not allowed)."""
+    import asyncio
+
+    async def _wrap():
+        return await aw
+    try:
+        asyncio.get_running_loop()
+    except RuntimeError:
+        return asyncio.run(_wrap())
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        return ex.submit(asyncio.run, _wrap()).result()
 
 
 def _jstr(raw: bytes) -> str:

@@ -361,3 +361,24 @@ def test_agent_per_request_registry_switch_and_restore():
     agent._restore_registry(eng, saved)
     assert eng.topic_ids == ids_before
     assert eng.calls[-1] == ("set_agent_node", (("own", "tool.own.input"),)) and ("set_tool_node", "planner.output") in eng.calls
+
+
+def test_async_host_tools_are_awaited():
+    """`async def` tools (the reference awaits the tool call, nodes/tool.py:64): driven to completion by the batch step,
+    outside and inside a running event loop (Worker.run calls the step from its loop)."""
+    import asyncio
+    import numpy as np
+    from calfkit import agent_tool
+
+    @agent_tool
+    async def slow_upper(text: str) -> str:
+        """upper-case, asynchronously"""
+        await asyncio.sleep(0.01)
+        return text.upper()
+
+    cols = np.zeros((1, 1), dtype=np.uint32)
+    assert slow_upper._call_host(b'{"text":"abc"}', memoryview(b""), cols, 0) == b'"ABC"'
+
+    async def inside_loop():
+        return slow_upper._call_host(b'{"text":"xyz"}', memoryview(b""), cols, 0)
+    assert asyncio.run(inside_loop()) == b'"XYZ"'
