@@ -256,7 +256,26 @@ class ToolNodeDef(BaseToolNodeDef):
             result = _run_awaitable(result)      # `async def` tools (the reference awaits them, nodes/tool.py:64)
         return pydantic_core.to_json(result)
 
+    def _host_results(self, n: int, args_of, record_of, cols: np.ndarray) -> tuple[list[bytes], set[int]]:
+        """run the Python callable for every record that reached the tool; a tool that raises fails ITS record only (the
+        reference handler would raise for that one message and FastStream would go on with the next): it is logged, gets a
+        placeholder result and its publishes are dropped after the plan"""
+        results: list[bytes] = []
+        failed: set[int] = set()
+        for i in range(n):
+            if cols[COL["ACTION"], i] != CK_ACT_HOST_TOOL:
+                results.append(b"")
+                continue
+            try:
+                results.append(self._call_host(args_of(i), record_of(i), cols, i))
+            except Exception:  # noqa: BLE001  (user code)
+                logger.exception("record %d: tool %s raised; nothing is published for this record", i, self.name)
+                failed.add(i)
+                results.append(b"null")
+        return results, failed
+
     def process_batch(self, engine, records: list[Record]) -> list[Record]:
+        failed: set[int] = set()
         data, offsets = pack_records(records)
         engine.submit(data, offsets)
         if self._template is not None:
@@ -266,16 +285,9 @@ class ToolNodeDef(BaseToolNodeDef):
             cols = engine.columns()
             mv = memoryview(data)
             ovl = engine.overlay() if self._tool.takes_ctx else None     # the column spans refer to the canonical spelling of a record
-            results: list[bytes] = []
-            for i in range(len(records)):
-                if cols[COL["ACTION"], i] == CK_ACT_HOST_TOOL:
-                    if ovl is not None and ovl[1][i] >= 0:
-                        rec = memoryview(ovl[0])[int(ovl[1][i]):int(ovl[1][i]) + int(ovl[2][i])]
-                    else:
-                        rec = mv[offsets[i]:offsets[i + 1]]
-                    results.append(self._call_host(blob[off[i]:off[i] + ln[i]].tobytes(), rec, cols, i))
-                else:
-                    results.append(b"")
+            results, failed = self._host_results(len(records), lambda i: blob[off[i]:off[i] + ln[i]].tobytes(),
+                                                 lambda i: (memoryview(ovl[0])[int(ovl[1][i]):int(ovl[1][i]) + int(ovl[2][i])]
+                                                            if ovl is not None and ovl[1][i] >= 0 else mv[offsets[i]:offsets[i + 1]]), cols)
             aux_off = np.zeros(len(records) + 1, dtype=np.int64)
             np.cumsum([len(r) for r in results], out=aux_off[1:])
             engine.tool_plan(np.frombuffer(b"".join(results) or b"\0", dtype=np.uint8), aux_off)
@@ -287,6 +299,8 @@ class ToolNodeDef(BaseToolNodeDef):
             logger.error("record %d: the reference handler would raise here (bad input_args / empty call stack)", i)
         produced = []
         for p in out.publishes():
+            if p.record in failed:
+                continue
             corr = records[p.record].correlation_id
             if corr is None and p.key is not None:
                 corr = p.key.decode()

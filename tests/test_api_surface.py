@@ -382,3 +382,24 @@ def test_async_host_tools_are_awaited():
     async def inside_loop():
         return slow_upper._call_host(b'{"text":"xyz"}', memoryview(b""), cols, 0)
     assert asyncio.run(inside_loop()) == b'"XYZ"'
+
+
+def test_a_raising_tool_fails_only_its_record():
+    """user code that raises costs its own record (logged, nothing published for it), not the batch — as with the reference,
+    where the handler raises for that one message and the consumer moves on"""
+    import numpy as np
+    from calfkit import agent_tool
+    from calfkit.engine._lib import CK_ACT_HOST_TOOL, CK_ACT_SILENT, COL, NUM_COLS
+
+    @agent_tool
+    def picky(x: int) -> int:
+        """fails on odd input"""
+        if x % 2:
+            raise ValueError("odd")
+        return x * 10
+
+    cols = np.zeros((NUM_COLS, 4), dtype=np.uint32)
+    cols[COL["ACTION"]] = [CK_ACT_HOST_TOOL, CK_ACT_HOST_TOOL, CK_ACT_SILENT, CK_ACT_HOST_TOOL]
+    args = [b'{"x":2}', b'{"x":3}', b"", b'{"x":4}']
+    results, failed = picky._host_results(4, lambda i: args[i], lambda i: memoryview(b""), cols)
+    assert results == [b"20", b"null", b"", b"40"] and failed == {1}
