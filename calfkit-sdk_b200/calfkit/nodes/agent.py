@@ -199,7 +199,11 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
                 state.overrides = OverridesState.model_validate_json(bytes(rec[fo:fo + fl]))
             corr = pydantic_core.from_json(b'"' + bytes(rec[int(cols[COL["CORR_OFF"], i]):][:int(cols[COL["CORR_LEN"], i])]) + b'"')
             deps = pydantic_core.from_json(bytes(rec[int(cols[COL["PD_OFF"], i]):][:int(cols[COL["PD_LEN"], i])]))
-            action, new_state = self._llm_step(corr, state, deps)
+            try:
+                action, new_state = self._llm_step(corr, state, deps)
+            except Exception:  # noqa: BLE001  (model client / lost-batch RuntimeError: this record only, as one failing handler call in the reference)
+                logger.exception("[%s] agent step failed for record %d; nothing is published for it", corr[:8], i)
+                continue
             if action == "silent":
                 # Silent (aggregation still incomplete): nothing is routed, but the handler returns the inbound envelope and
                 # the worker publishes that return value to publish_topic (reference nodes/base.py:137-145, worker/worker.py:52-53)
