@@ -65,30 +65,73 @@ def cpu_arm(records, cores: int, start: str = "fork"):
     return n / dt, dt, n
 
 
+class ReferencePool:
+    """worker processes running the UNMODIFIED reference (oracle/_ref mirror, or /root/reference in the build
+    container); the oracle port when no reference tree is present.  kind = "reference" | "port"."""
+    def __init__(self, cores: int):
+        from oracle import ref_harness, ref_runner
+        self.kind = "reference" if ref_harness.available() else "port"
+        self.pool = ref_runner.Pool(cores, None if self.kind == "reference" else _cpu_worker)
+        self.cores = cores
+
+    def run(self, records):
+        return self.pool.run(records)
+
+    def close(self):
+        self.pool.close()
+
+    def describe(self) -> str:
+        return ("unmodified reference code (oracle/_ref mirror of /root/reference/calfkit): Envelope.model_validate_json -> "
+                "ToolNodeDef.handler -> _publish_action -> model_dump_json, sync tool on the anyio thread as in the stock path"
+                if self.kind == "reference" else "oracle/port.py (no reference tree present)")
+
+
+WORKLOADS = {
+    "tool_event_1k": "tool_event_1k: tool-stage Envelope JSON (1152+-16 B), single @agent_tool node get_weather (BASELINE.json configs[1])",
+    "fanout": "fanout: 1 Agent node -> F @agent_tool nodes (BASELINE.json configs[2]), post-LLM agent-stage envelopes",
+    "reply": "reply: client-side projection of final reply envelopes to NodeResult.output (SURVEY 8f row 3)",
+    "mixed": "mixed: sizes log-uniform 128 B-64 KB, 256 subscribe_topics (BASELINE.json configs[4])",
+}
+
+
+def bench_config(args, world: int) -> dict:
+    """the `config` object of the JSON line: a pure function of the command line, identical on both arms"""
+    return {"workload": WORKLOADS[args.workload], "events_per_gpu_per_step": args.events, "seed": 1000,
+            "partitions": NUM_PARTITIONS, "cross_partition_fraction": args.cross if world > 1 else 0.0,
+            "sharding": "records by Kafka partition -> GPU" if world > 1 else "single GPU",
+            "tool": "device template " + repr(TOOL_FMT),
+            "l2": "inputs and outputs per step (> 1 GB each at 1 M events) far exceed the 126 MB L2: every step streams from HBM",
+            "broker_io": "excluded on both arms (FastStream/aiokafka are not installable offline)"}
+
+
 def run_reference(args, rank: int, world: int) -> None:
+    """the reference's own CPU implementation of the path (oracle/ref_runner.py: validate -> ToolNodeDef.handler ->
+    _publish_action -> dump, unmodified reference code) on all host cores; each step a bounded sample of the SAME
+    seeded batch the GPU arm consumes"""
     if rank != 0:
         return
     from calfkit import synth
     cores = os.cpu_count() or 1
-    per_step = max(cores * 2000, 8000)                 # ~2 s of work per step on all cores
-    recs = synth.tool_events(per_step, seed=77)
-    for _ in range(args.warmup):
-        cpu_arm(recs[: max(cores * 16, 64)], cores)
-    t_total, n_total = 0.0, 0
+    per_step = min(args.events, max(cores * 400, 4000))           # ~1-2 s of work per step on all cores
+    recs = synth.tool_events(per_step, seed=1000)                  # = the first per_step records of the GPU arm's rank-0 batch
+    pool = ReferencePool(cores)
+    for _ in range(max(args.warmup, 1)):
+        pool.run(recs[: max(cores * 8, 64)])
+    t_total, n_total, kind = 0.0, 0, pool.kind
     for _ in range(args.steps):
-        _v, dt, n = cpu_arm(recs, cores)
+        _v, dt, n = pool.run(recs)
         t_total += dt
         n_total += n
+    pool.close()
     value = n_total / t_total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "tool_event_1k: 1152+-16 B tool-stage Envelope JSON, one @agent_tool node (get_weather)",
-                   "events_per_step": per_step, "note": "reference's own CPU path restated on pydantic-core (oracle/port.py); "
-                   "broker I/O excluded on both arms (FastStream/aiokafka are not installable offline)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} events/step x {args.steps} steps over {cores} processes"},
+        "config": bench_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"first {per_step} events of the batch per step x {args.steps} steps over {cores} processes; "
+                                   + pool.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -108,6 +151,15 @@ def hbm_peak_gbs():
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+def teardown(world: int) -> None:
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -318,7 +370,9 @@ def run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     torch.cuda.synchronize()
-    os._exit(0)
+    del stream
+    eng.close()
+    teardown(world)
 
 
 def _cpu_reply_worker(chunk):
@@ -451,7 +505,9 @@ def run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) ->
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     torch.cuda.synchronize()
-    os._exit(0)
+    del stream
+    eng.close()
+    teardown(world)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -513,10 +569,13 @@ def main() -> None:
     from calfkit.engine.exchange import exchange as run_exchange, plan_exchange_device
     launches = [0]
 
+    all_lanes = []
+
     class Lane:
         """one BatchEngine (= one CUDA stream + its HBM buffers) with torch views of its result tables and
         a pinned host landing buffer; two lanes ping-pong in the end-to-end loop (double buffering)"""
         def __init__(self):
+            all_lanes.append(self)
             self.eng = eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096)
             eng.register_topics(topics, num_partitions=NUM_PARTITIONS)
             eng.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))
@@ -540,6 +599,10 @@ def main() -> None:
             self.h_pubs = torch.empty(2 * n * PUB_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(PUB_DTYPE)
             self.d2h = 0
             self.rbytes = 0
+
+        def close(self):
+            self.t_pubs = self.t_out_off = self.t_out_len = self.t_out = self.stream = None
+            self.eng.close()
 
         def gather(self, plan, buf):
             eng = self.eng
@@ -691,20 +754,19 @@ def main() -> None:
     d2h_bytes = [lanes[0].d2h]
 
     def shutdown():
-        # orderly teardown, then leave without running interpreter finalisers (pinned tensors wrapping
-        # foreign device memory must not outlive the CUDA context)
+        # orderly teardown: drop every torch view of library-owned device memory, destroy the engines (streams +
+        # HBM buffers) while the CUDA context is alive, leave the process group, and return normally so that
+        # interpreter exit hooks (the driver's loaded-.so record) run
         sys.stdout.flush()
         sys.stderr.flush()
-        try:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-                dist.destroy_process_group()
-        finally:
-            os._exit(0)
+        torch.cuda.synchronize()
+        for ln_ in all_lanes:
+            ln_.close()
+        teardown(world)
 
     if rank != 0:
         shutdown()
+        return
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     peak, peak_src = hbm_peak_gbs()
@@ -738,16 +800,24 @@ def main() -> None:
                              "frac": (in_bytes + out_payload_bytes) / ms_step / 1e6 / peak},
                 "kernels": kern, "sum_kernel_ms_per_step": kern_step_ms}
 
-    # ---- CPU baseline: the oracle port on a bounded sample, all host cores ----------------------------
+    # ---- CPU baseline: the reference's own code on a bounded sample of the same batch, all host cores -------------
     os.sched_setaffinity(0, all_cpus)
     cores = os.cpu_count() or 1
-    sample_n = args.cpu_sample or max(cores * 8000, 20000)       # ~10-20 s of CPU work on all cores
+    sample_n = args.cpu_sample or max(cores * 1500, 20000)       # ~10-30 s of CPU work over all cores
     sample = [batch.record(i) for i in range(min(sample_n, n))]
-    cpu_value, cpu_dt, cpu_n = cpu_arm(sample, cores, start="spawn")   # CUDA is initialised in this process: no fork
-    try:                                                                # SURVEY 8d also asks for the single-core figure
-        one_core_value, _dt1, _n1 = cpu_arm(sample[:3000], 1, start="spawn")
-    except Exception:  # noqa: BLE001  (never let the extra figure cost the bench line)
-        one_core_value = None
+    rpool = ReferencePool(cores)
+    rpool.run(sample[: max(cores * 8, 64)])
+    cpu_value, cpu_dt, cpu_n = rpool.run(sample)
+    cpu_kind, cpu_desc = rpool.kind, rpool.describe()
+    rpool.close()
+    try:                                                                # second figures: the oracle port, and one core
+        port_value, _dtp, _np = cpu_arm(sample, cores, start="spawn")
+        one = ReferencePool(1)
+        one.run(sample[:64])
+        one_core_value, _dt1, _n1 = one.run(sample[:2000])
+        one.close()
+    except Exception:  # noqa: BLE001  (never let the extra figures cost the bench line)
+        port_value = one_core_value = None
     # parity spot check against the oracle on the same bytes (byte-exact), outside all timed regions
     from oracle import port
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
@@ -763,13 +833,9 @@ def main() -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "tool_event_1k: tool-stage Envelope JSON (1152+-16 B), single @agent_tool node get_weather "
-                               "(BASELINE.json configs[1])",
-                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "out_bytes_mean": out_payload_bytes / max(npay, 1),
-                   "publishes_per_event": 2, "partitions": NUM_PARTITIONS, "cross_partition_fraction": args.cross if world > 1 else 0.0,
-                   "sharding": "records by Kafka partition -> GPU" if world > 1 else "single GPU",
-                   "l2": "inputs (%.2f GB) and outputs larger than the 126 MB L2: every step streams from HBM" % (in_bytes / 1e9),
-                   "tool": "device template " + repr(TOOL_FMT), "accepted_fraction": ok_frac, "parity_spot_check_256": parity_ok},
+        "config": bench_config(args, world),
+        "workload_stats": {"record_bytes_mean": in_bytes / n, "out_bytes_mean": out_payload_bytes / max(npay, 1), "publishes_per_event": 2,
+                           "accepted_fraction": ok_frac, "parity_spot_check_256": parity_ok, "in_gb_per_step": in_bytes / 1e9},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h_bytes[0],
                 "ms_per_step": e2e_ms, "steps": e2e_steps,
@@ -777,9 +843,10 @@ def main() -> None:
                 "timing": "host wall clock around the whole pipelined loop, synchronised on both sides (spans two streams), max over ranks"},
         "gpu_launches": gpu_launches,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes (oracle/port.py)",
-                         "one_core": {"value": one_core_value, "unit": UNIT, "sample": "3000 events, 1 process"}},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": cpu_kind,
+                         "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes; " + cpu_desc,
+                         "oracle_port": {"value": port_value, "unit": UNIT, "cores": cores, "sample": "same events, oracle/port.py"},
+                         "one_core": {"value": one_core_value, "unit": UNIT, "sample": "2000 events, 1 process, same code"}},
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -11,8 +11,11 @@ touch at import time, and then imports these reference modules unmodified:
     calfkit.nodes.base          (BaseNodeDef.handler / prepare_context / _publish_action)
     calfkit.nodes.tool          (ToolNodeDef.run, agent_tool)
 
-Nothing here travels to the GPU box (/root/reference does not exist there); it is used only by
-tests/golden/make_golden.py in this container.  Never imported by the product.
+/root/reference exists only in the build container.  oracle/build_ref.py (run by __graft_entry__.build()) mirrors
+the reference's package tree byte for byte into oracle/_ref/ (git-ignored build output that ships with the gpurun
+snapshot), and this module loads the reference from there when /root/reference is absent — so bench.py's CPU arm
+times the reference's own code on the GPU box's host cores.  Used by tests/golden/make_golden*.py (here) and by
+bench.py's `--impl reference` / cpu_baseline legs.  Never imported by the product.
 """
 from __future__ import annotations
 
@@ -21,7 +24,14 @@ import itertools
 import sys
 import types
 
-REF_ROOT = "/root/reference"
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference/calfkit") else os.path.join(_HERE, "_ref")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "calfkit", "nodes"))
 
 _uuid_counter = itertools.count(1)
 _uuid_hook = None  # callable() -> 32-hex string, installed by tests for deterministic frame ids

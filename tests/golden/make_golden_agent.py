@@ -59,6 +59,19 @@ Envelope, State = ref.Envelope, models.State
 TOOLS = {name: ref.agent_tool(fn) for name, fn in tools_def.TOOLS.items()}
 FIXED_TS = "2026-01-01T00:00:00Z"
 
+# freeze the clock: every `timestamp` default_factory of the vendored message types is _utils.now_utc, which reads
+# `datetime.now(tz=...)` through its module global — a frozen datetime class there makes this file reproducible byte for byte
+import datetime as _dt  # noqa: E402
+
+
+class _FrozenDatetime(_dt.datetime):
+    @classmethod
+    def now(cls, tz=None):
+        return cls(2026, 1, 1, 0, 0, 1, tzinfo=tz)
+
+
+sys.modules["calfkit._vendor.pydantic_ai._utils"].datetime = _FrozenDatetime
+
 
 def inbound(corr: str, history_json: str = "[]", stage_prompt: str | None = "What's the weather in Paris and Tokyo?") -> bytes:
     unc = "null"
