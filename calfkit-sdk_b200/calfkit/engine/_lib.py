@@ -39,7 +39,9 @@ PUB_DTYPE = np.dtype([("payload", "<u4"), ("topic_id", "<i4"), ("topic_off", "<u
 EXPORTS = ["ck_create", "ck_destroy", "ck_last_error", "ck_version", "ck_register_topics", "ck_set_tool_node", "ck_submit",
            "ck_submit_device", "ck_tool_args", "ck_tool_plan", "ck_tool_plan_device", "ck_return_plan", "ck_set_agent_node", "ck_set_agent_tool_topic_ids", "ck_fanout_plan", "ck_tailcall_plan", "ck_exchange_plan", "ck_launch_count", "ck_reply_plan",
            "ck_sync", "ck_out_size", "ck_fetch_columns", "ck_fetch_output", "ck_fetch_overlay", "ck_fetch_topic_hist", "ck_stream",
-           "ck_device_buffers", "ck_device_buffers2", "ck_gather_spans", "ck_profile", "ck_profile_read"]
+           "ck_device_buffers", "ck_device_buffers2", "ck_gather_spans", "ck_profile", "ck_profile_read", "ck_fetch_cols",
+           "ck_host_alloc", "ck_host_free", "ck_canon_stats", "ck_fetch_output_async",
+           "ck_fetch_cols_async"]
 
 _lib = None
 
@@ -81,6 +83,12 @@ def load() -> C.CDLL:
         "ck_out_size": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "ck_fetch_columns": (C.c_int, [vp, u32p]),
         "ck_fetch_output": (C.c_int, [vp, u8p, C.c_uint64, i64p, u32p, vp]),
+        "ck_fetch_cols": (C.c_int, [vp, u32p, C.c_uint32, u32p]),
+        "ck_fetch_cols_async": (C.c_int, [vp, u32p, C.c_uint32, u32p]),
+        "ck_fetch_output_async": (C.c_int, [vp, u8p, C.c_uint64, i64p, u32p, vp]),
+        "ck_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(vp)]),
+        "ck_host_free": (None, [vp]),
+        "ck_canon_stats": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
         "ck_fetch_overlay": (C.c_int, [vp, u8p, C.c_uint64, i64p, u32p, C.POINTER(C.c_uint64)]),
         "ck_fetch_topic_hist": (C.c_int, [vp, u32p, C.c_uint32]),
         "ck_stream": (vp, [vp]),

@@ -23,7 +23,7 @@ import pydantic_core
 from typing_extensions import Self
 
 from calfkit.broker import Record
-from calfkit.engine._lib import CK_ACT_HOST_TOOL, CK_ACT_RAISES, CK_OK, COL, STATUS_NAMES
+from calfkit.engine._lib import CK_ACT_HOST_TOOL, CK_ACT_RAISES, CK_OK, CK_UNSUPPORTED, COL, STATUS_NAMES
 from calfkit.engine.batch import ToolTemplate
 from calfkit.models import SessionRunContext, State, ToolContext
 from calfkit.models.actions import NodeResult
@@ -274,11 +274,14 @@ class ToolNodeDef(BaseToolNodeDef):
                 results.append(b"null")
         return results, failed
 
-    def process_batch(self, engine, records: list[Record]) -> list[Record]:
+    def process_batch(self, engine, records: list[Record], force_host: bool = False) -> list[Record]:
+        """force_host: evaluate the Python callable even though the node has a device template — used for the records the
+        template declined (`args` given as a JSON string, a non-string argument ...: the reference's args_as_dict / the
+        callable itself handle those, nodes/tool.py:53-64), so nothing is dropped on the template path"""
         failed: set[int] = set()
         data, offsets = pack_records(records)
         engine.submit(data, offsets)
-        if self._template is not None:
+        if self._template is not None and not force_host:
             engine.tool_plan()
         else:
             blob, off, ln = engine.tool_args()
@@ -292,10 +295,15 @@ class ToolNodeDef(BaseToolNodeDef):
             np.cumsum([len(r) for r in results], out=aux_off[1:])
             engine.tool_plan(np.frombuffer(b"".join(results) or b"\0", dtype=np.uint8), aux_off)
         out = engine.fetch()
+        declined = []
         for i in np.nonzero(out.cols[COL["STATUS"]] != CK_OK)[0]:
+            if out.cols[COL["STATUS"], i] == CK_UNSUPPORTED and out.cols[COL["ACTION"], i] == CK_ACT_RAISES and not force_host \
+                    and self._template is not None:
+                declined.append(int(i))                      # the template declined it: the host-tool path below takes over
+                continue
             logger.error("record %d rejected: %s at byte %d", i, STATUS_NAMES[int(out.cols[COL["STATUS"], i])],
                          int(out.cols[COL["ERR"], i]))
-        for i in np.nonzero(out.cols[COL["ACTION"]] == CK_ACT_RAISES)[0]:
+        for i in np.nonzero((out.cols[COL["ACTION"]] == CK_ACT_RAISES) & (out.cols[COL["STATUS"]] == CK_OK))[0]:
             logger.error("record %d: the reference handler would raise here (bad input_args / empty call stack)", i)
         produced = []
         for p in out.publishes():
@@ -305,6 +313,8 @@ class ToolNodeDef(BaseToolNodeDef):
             if corr is None and p.key is not None:
                 corr = p.key.decode()
             produced.append(Record(p.topic, p.payload, p.key, corr))
+        if declined:
+            produced += self.process_batch(engine, [records[i] for i in declined], force_host=True)
         return produced
 
 

@@ -2,19 +2,31 @@
 
 Same constructor, add_nodes, register_handlers (idempotence guard -> RuntimeError) and async run().
 The reference's run() hands control to FastStream, which then delivers ONE record at a time to
-node.handler.  Here run() is the batch loop itself: poll up to `batch_records` records per node from
-the broker, push them through the node's CUDA plan (node.process_batch -> BatchEngine), produce the
-routed outputs, repeat.  One BatchEngine (one CUDA stream, one set of HBM buffers) per node.
+node.handler.  Here run() is the batch loop itself.  Two paths per node:
+
+  * device-template tool nodes (the data-parallel hot path): `broker.poll_arena` -> one pinned batch arena ->
+    `LanePipeline.push` (H2D + decode + plan + encode + route on one of K lanes while an older step's results come
+    back) -> `broker.produce_publishes(PublishBatch)`.  No Python object per record.
+  * nodes with a host half (Python tools, the Agent's LLM boundary): `broker.poll_batch` -> `node.process_batch`
+    (engine for decode / plan / encode, Python only for the user callable) -> `broker.produce_batch`.
+
+A poll is bounded by records AND bytes, an engine-level failure splits the batch and retries (dequeued records are never
+lost), and records the device declines as CK_UNSUPPORTED are re-run through the host-tool path.
 """
 from __future__ import annotations
 
 import asyncio
 import logging
+import os
 from typing import Any
+
+import numpy as np
 
 from calfkit.broker import Record
 from calfkit.client import Client
 from calfkit.engine import BatchEngine
+from calfkit.engine._lib import CK_ACT_RAISES, CK_OK, CK_UNSUPPORTED, STATUS_NAMES
+from calfkit.engine.lane import LanePipeline, PublishBatch
 from calfkit.nodes import BaseNodeDef
 
 logger = logging.getLogger(__name__)
@@ -39,7 +51,14 @@ def engine_for(node: BaseNodeDef, *, device: int = 0, max_records: int = 1 << 14
 class Worker:
     def __init__(self, client: Client, nodes: list[BaseNodeDef] | None = None, max_workers: int = 1,
                  group_id: str | None = None, extra_publish_kwargs: dict[str, Any] | None = None,
-                 extra_subscribe_kwargs: dict[str, Any] | None = None, *, device: int = 0, batch_records: int = 1 << 14):
+                 extra_subscribe_kwargs: dict[str, Any] | None = None, *, device: int | None = None,
+                 batch_records: int = 1 << 14, batch_bytes: int = 64 << 20, lanes: int = 3,
+                 route_topics: list[str] | None = None):
+        """Reference signature (worker/worker.py:13-31) plus keyword-only engine knobs: `device` (default: LOCAL_RANK of a
+        one-process-per-GPU launch, else 0), the batch bounds a poll honours (records AND bytes: a batch never exceeds what
+        the engines were sized for), the number of pipelined lanes per device-template node, and `route_topics`: names of
+        topics owned by OTHER workers that this worker's outputs go to (agents' input topics ...) so that the device resolves
+        them to ids too; names it does not know are still routed, grouped by hash on the host."""
         self._client = client
         self._nodes = nodes or list()
         self._max_workers = max_workers
@@ -47,9 +66,14 @@ class Worker:
         self._extra_publish_kwargs = extra_publish_kwargs or {}
         self._extra_subscribe_kwargs = extra_subscribe_kwargs or {}
         self._prepared = False
-        self._device = device
+        self._device = device if device is not None else int(os.environ.get("LOCAL_RANK", 0))
         self._batch_records = batch_records
+        self._batch_bytes = batch_bytes
+        self._lanes = lanes
+        self._route_topics = list(route_topics or [])
         self._subs: list[tuple[BaseNodeDef, Any]] = []
+        self._pipes: dict[int, LanePipeline] = {}
+        self.stats = {"records": 0, "publishes": 0, "rejected": 0, "raises": 0, "host_fallback": 0, "steps": 0}
 
     def add_nodes(self, *nodes: BaseNodeDef) -> None:
         self._nodes.extend(nodes)
@@ -68,18 +92,89 @@ class Worker:
             self._subs.append((node, subscriber))
         self._prepared = True
 
+    # ---- device-template tool nodes: arena in -> pipelined lanes -> publish batch out, no Python per record ----------
+    def _pipeline(self, node: BaseNodeDef) -> LanePipeline:
+        pipe = self._pipes.get(id(node))
+        if pipe is None:
+            topics = list(node.subscribe_topics) + ([node.publish_topic] if node.publish_topic else []) + self._route_topics
+
+            def configure(eng: BatchEngine) -> None:
+                eng.register_topics(topics, num_partitions=getattr(self._client._connection, "num_partitions", 0))
+                node.configure_engine(eng)
+            pipe = LanePipeline(self._device, configure, lanes=self._lanes, max_records=self._batch_records,
+                                max_in_bytes=self._batch_bytes)
+            self._pipes[id(node)] = pipe
+        return pipe
+
+    def _produce_fast(self, node: BaseNodeDef, batch: PublishBatch) -> None:
+        broker = self._client._connection
+        n = batch.source.n
+        self.stats["records"] += n
+        bad = batch.status != CK_OK
+        nbad = int(np.count_nonzero(bad))
+        if nbad:
+            self.stats["rejected"] += nbad
+            for i in np.nonzero(bad & (batch.status != CK_UNSUPPORTED))[0][:8]:
+                logger.error("record %d rejected: %s", int(i), STATUS_NAMES[int(batch.status[i])])
+            # the device declined these (a construct the template / fast path does not cover, e.g. `args` given as a JSON
+            # string or a non-string template argument): the host-tool path handles them, nothing is dropped silently
+            redo = np.nonzero((batch.status == CK_UNSUPPORTED) & (batch.action == CK_ACT_RAISES))[0]
+            if len(redo):
+                self.stats["host_fallback"] += len(redo)
+                recs = [Record(node.subscribe_topics[0], batch.source.record(int(i))) for i in redo]
+                self._run_host(node, recs, force_host=True)
+        self.stats["raises"] += int(np.count_nonzero((batch.action == CK_ACT_RAISES) & ~bad))
+        self.stats["publishes"] += batch.n_publishes
+        broker.produce_publishes(batch)
+
+    # ---- host-side nodes (Python tools, the Agent's LLM boundary): per-record objects are inherent there -----------
+    def _run_host(self, node: BaseNodeDef, records: list[Record], **kw: Any) -> None:
+        """never loses a dequeued record: an engine-level failure (a batch the buffers cannot hold) splits the batch and
+        retries; a single record that still fails is logged and dropped alone"""
+        broker = self._client._connection
+        engine = engine_for(node, device=self._device, max_records=self._batch_records, max_in_bytes=self._batch_bytes)
+        try:
+            broker.produce_batch(node.process_batch(engine, records, **kw) if kw else node.process_batch(engine, records))
+            self.stats["records"] += 0 if kw else len(records)
+        except Exception:  # noqa: BLE001  (EngineError: capacity; user code outside the per-record guards)
+            if len(records) == 1:
+                logger.exception("node %s: record dropped after failing alone", node.name)
+                return
+            mid = len(records) // 2
+            logger.warning("node %s: batch of %d failed, retrying in halves", node.name, len(records))
+            self._run_host(node, records[:mid], **kw)
+            self._run_host(node, records[mid:], **kw)
+
     def step(self) -> int:
         """one pass over all nodes: poll -> CUDA batch -> produce.  Returns the number of records consumed."""
         broker = self._client._connection
         consumed = 0
+        self.stats["steps"] += 1
         for node, sub in self._subs:
-            records: list[Record] = broker.poll_batch(sub.topics, self._batch_records)
+            if getattr(node, "_template", None) is not None:
+                pipe = self._pipeline(node)
+                arena = broker.poll_arena(sub.topics, self._batch_records, self._batch_bytes)
+                if arena is not None:
+                    consumed += arena.n
+                    done = pipe.push(arena)
+                    if done is not None:
+                        self._produce_fast(node, done)
+                elif pipe.pending:                             # input idle: flush what is in flight
+                    for done in pipe.drain():
+                        consumed += 1                          # keeps run(until_idle) going until the outputs are produced
+                        self._produce_fast(node, done)
+                continue
+            records: list[Record] = broker.poll_batch(sub.topics, self._batch_records, self._batch_bytes)
             if not records:
                 continue
             consumed += len(records)
-            engine = engine_for(node, device=self._device, max_records=self._batch_records)
-            broker.produce_batch(node.process_batch(engine, records))
+            self._run_host(node, records)
         return consumed
+
+    def close(self) -> None:
+        for pipe in self._pipes.values():
+            pipe.close()
+        self._pipes.clear()
 
     async def run(self, *, until_idle: bool = False, idle_sleep: float = 0.001, **extra_run_args: Any) -> None:
         """Run the worker as a service (reference: blocks in FastStream(...).run()); `until_idle=True`

@@ -26,7 +26,7 @@ struct ck_handle {
     u8* d_in = nullptr; long long* d_in_off = nullptr;
     u8* d_out = nullptr; long long* d_out_off = nullptr;
     u8* d_aux = nullptr; long long* d_aux_off = nullptr; u8* d_glue = nullptr;
-    u8* d_ovl = nullptr; long long* d_ovl_off = nullptr; u32* d_ovl_len = nullptr; u32* d_clen = nullptr; long long* d_coff = nullptr;
+    u8* d_ovl = nullptr; long long* d_ovl_off = nullptr; u32* d_ovl_len = nullptr; ck_canon_ctl* d_canon_ctl = nullptr; u32* d_canon_list = nullptr;
     uint64_t max_ovl = 0;
     u32* d_cols = nullptr; ck_out_desc* d_descs = nullptr; u32* d_pay_len = nullptr; ck_pub* d_pubs = nullptr;
     unsigned long long* d_tile_sum = nullptr; unsigned long long* d_grand = nullptr;
@@ -121,8 +121,8 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     ALLOC(h->d_ovl, h->max_ovl + CK_PAD);
     ALLOC(h->d_ovl_off, sizeof(long long) * ((size_t)max_records + 1));
     ALLOC(h->d_ovl_len, sizeof(u32) * (size_t)max_records);
-    ALLOC(h->d_clen, sizeof(u32) * (size_t)max_records);
-    ALLOC(h->d_coff, sizeof(long long) * ((size_t)max_records + 1));
+    ALLOC(h->d_canon_ctl, sizeof(ck_canon_ctl));
+    ALLOC(h->d_canon_list, sizeof(u32) * (size_t)max_records);
     ALLOC(h->d_cols, sizeof(u32) * (size_t)CK_NUM_COLS * max_records);
     ALLOC(h->d_descs, sizeof(ck_out_desc) * (size_t)h->max_payloads);
     ALLOC(h->d_pay_len, sizeof(u32) * (size_t)h->max_payloads);
@@ -149,7 +149,7 @@ extern "C" void ck_destroy(ck_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_ovl, h->d_ovl_off, h->d_ovl_len, h->d_clen, h->d_coff, h->d_cols, h->d_descs, h->d_pay_len,
+    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_ovl, h->d_ovl_off, h->d_ovl_len, h->d_canon_ctl, h->d_canon_list, h->d_cols, h->d_descs, h->d_pay_len,
                     h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_agent_cfg, h->d_counts, h->d_slot_base, h->d_agent_tables, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
                     h->d_tab_len, h->d_tab_id, h->d_tab_names, h->d_x_hist, h->d_x_base, h->d_x_nbytes, h->d_x_src_off, h->d_x_len, h->d_x_dst_off,
                     h->d_x_len32, h->d_x_pub, h->d_x_tile, h->d_x_grand};
@@ -228,6 +228,7 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
 
 static ck_view view_of(ck_handle* h) {
     ck_view v; v.in = h->cur_in; v.off = h->cur_in_off; v.ovl = h->d_ovl; v.ovl_off = h->d_ovl_off; v.ovl_len = h->d_ovl_len;
+    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list;
     return v;
 }
 
@@ -238,31 +239,25 @@ static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32
 // (count -> scan -> write) and walk those again in their canonical spelling
 static int launch_decode(ck_handle* h) {
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "vm")) ? 1 : (e && !strcmp(e, "global")) ? 2 : 0; }   // development A/B switch
+    if (mode < 0) { const char* e = getenv("CK_WALKER"); mode = (e && !strcmp(e, "global")) ? 2 : 0; }   // development A/B switch
     u32 n = h->n;
     if (!n) return 0;
     ck_view v = view_of(h);
     CUDA_TRY(h, cudaMemsetAsync(h->d_ovl_off, 0xff, sizeof(long long) * (size_t)n, h->stream));      // no overlays yet
+    CUDA_TRY(h, cudaMemsetAsync(h->d_canon_ctl, 0, sizeof(ck_canon_ctl), h->stream));
     {
         KTimer t(h, CK_K_WALK);
-        if (mode == 1) CKL(h) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
-        else if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
+        if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
         else CKL(h) ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 0);
         CUDA_TRY(h, cudaGetLastError());
     }
     {
+        // the records the walker listed (usually none: both kernels exit at once) are re-emitted canonically into the
+        // overlay and walked again in that spelling
         KTimer t(h, CK_K_CANON);
-        CKL(h) ck_canon_count_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen);
-        CUDA_TRY(h, cudaGetLastError());
-    }
-    if (run_scan(h, h->d_clen, n, h->d_coff, 0)) return 1;
-    {
-        KTimer t(h, CK_K_CANON);
-        CKL(h) ck_canon_write_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_clen, h->d_coff, h->d_ovl, (long long)h->max_ovl,
-                                                                 h->d_ovl_off, h->d_ovl_len);
-        if (mode == 1) CKL(h) ck_walk_vm_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else if (mode == 2) CKL(h) ck_rewalk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 1);
-        else CKL(h) ck_rewalk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 1);
+        u32 blocks = (n + 63) / 64; if (blocks > 148 * 8) blocks = 148 * 8;
+        CKL(h) ck_canon_kernel<<<blocks, 64, 0, h->stream>>>(v, n, h->d_cols, n, h->d_ovl, (long long)h->max_ovl, h->d_ovl_off, h->d_ovl_len);
+        CKL(h) ck_rewalk_list_kernel<<<blocks, 64, 0, h->stream>>>(v, n, h->d_cols, n);
         CUDA_TRY(h, cudaGetLastError());
     }
     return 0;
@@ -330,25 +325,28 @@ extern "C" int ck_tool_args(ck_handle* h) {
     return scan_emit(h, h->n, nullptr);
 }
 
+// plan (modes 1 / 2) staged through shared memory, publishes routed in the same kernel (ck_plan2.cuh)
+static int launch_plan2(ck_handle* h, const u8* aux, const long long* aux_off, int mode) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(h, cudaFuncSetAttribute(ck_plan_tool2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CK_P2_SMEM));
+        attr_set = true;
+    }
+    KTimer t(h, CK_K_PLAN);
+    if (h->n) CKL(h) ck_plan_tool2_kernel<<<(h->n + CK_P2_THREADS - 1) / CK_P2_THREADS, CK_P2_THREADS, CK_P2_SMEM, h->stream>>>(
+        view_of(h), h->n, h->d_cols, h->n, h->d_tool_cfg, h->d_lit, aux_off, aux, h->d_glue, mode, h->d_descs, h->d_pay_len, h->d_pubs,
+        h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 static int tool_plan_common(ck_handle* h, const u8* aux, const long long* aux_off) {
     if (!h->tool_set) return fail(h, "ck_tool_plan: call ck_set_tool_node first");
     if (h->h_tool_cfg.tpl_nparts == 0 && aux_off == nullptr) return fail(h, "ck_tool_plan: node has no device template, host results required");
-    {
-        KTimer t(h, CK_K_PLAN);
-        if (h->n) CKL(h) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
-            h->d_tool_cfg, h->d_lit, aux_off, aux, h->d_glue, 1, h->d_descs, h->d_pay_len, h->d_pubs);
-        CUDA_TRY(h, cudaGetLastError());
-    }
+    if (launch_plan2(h, aux, aux_off, 1)) return 1;
     // NOTE: payload sizes are bounded by in + per-record constant; the caller sizes max_out accordingly
     if (scan_emit(h, h->n, aux)) return 1;
-    {
-        KTimer t(h, CK_K_ROUTE);
-        u32 npubs = 2 * h->n;
-        if (npubs) CKL(h) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
-            h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
-        CUDA_TRY(h, cudaGetLastError());
-        h->n_pubs = npubs;
-    }
+    h->n_pubs = 2 * h->n;
     return 0;
 }
 
@@ -369,21 +367,9 @@ extern "C" int ck_tool_plan(ck_handle* h, const uint8_t* host_aux, const int64_t
 extern "C" int ck_return_plan(ck_handle* h) {
     cudaSetDevice(h->device);
     if (!h->tool_set) return fail(h, "ck_return_plan: call ck_set_tool_node (publish topic) first");
-    {
-        KTimer t(h, CK_K_PLAN);
-        if (h->n) CKL(h) ck_plan_tool_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(view_of(h), h->n, h->d_cols, h->n,
-            h->d_tool_cfg, h->d_lit, nullptr, nullptr, h->d_glue, 2, h->d_descs, h->d_pay_len, h->d_pubs);
-        CUDA_TRY(h, cudaGetLastError());
-    }
+    if (launch_plan2(h, nullptr, nullptr, 2)) return 1;
     if (scan_emit(h, h->n, nullptr)) return 1;
-    {
-        KTimer t(h, CK_K_ROUTE);
-        u32 npubs = 2 * h->n;
-        if (npubs) CKL(h) ck_route_kernel<<<(npubs + 255) / 256, 256, 0, h->stream>>>(view_of(h), h->d_cols, h->n, h->d_pubs, npubs,
-            h->tab, h->num_partitions, h->d_topic_hist, h->hist_cap);
-        CUDA_TRY(h, cudaGetLastError());
-        h->n_pubs = npubs;
-    }
+    h->n_pubs = 2 * h->n;
     return 0;
 }
 
@@ -620,8 +606,44 @@ extern "C" int ck_fetch_columns(ck_handle* h, uint32_t* host_cols) {
     return 0;
 }
 
-extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, uint32_t* host_out_len,
-                               ck_publish* host_pubs) {
+// selected column rows only (a worker needs status / action / the key span, not all 55 columns of a million records)
+static int fetch_cols_impl(ck_handle* h, const uint32_t* which, uint32_t k, uint32_t* host_rows, bool wait);
+extern "C" int ck_fetch_cols(ck_handle* h, const uint32_t* which, uint32_t k, uint32_t* host_rows) { return fetch_cols_impl(h, which, k, host_rows, true); }
+extern "C" int ck_fetch_cols_async(ck_handle* h, const uint32_t* which, uint32_t k, uint32_t* host_rows) { return fetch_cols_impl(h, which, k, host_rows, false); }
+static int fetch_cols_impl(ck_handle* h, const uint32_t* which, uint32_t k, uint32_t* host_rows, bool wait) {
+    cudaSetDevice(h->device);
+    for (uint32_t j = 0; j < k; j++) {
+        if (which[j] >= CK_NUM_COLS) return fail(h, "ck_fetch_cols: no such column");
+        if (h->n) CUDA_TRY(h, cudaMemcpyAsync(host_rows + (size_t)j * h->n, h->d_cols + (size_t)which[j] * h->n, sizeof(u32) * (size_t)h->n,
+                                             cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (wait) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// how many records of the current batch went through the canonicaliser pass, and the overlay bytes it produced (waits)
+extern "C" int ck_canon_stats(ck_handle* h, uint32_t* n_listed, uint64_t* overlay_bytes) {
+    cudaSetDevice(h->device);
+    ck_canon_ctl c{};
+    if (h->n) CUDA_TRY(h, cudaMemcpyAsync(&c, h->d_canon_ctl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (n_listed) *n_listed = c.count;
+    if (overlay_bytes) *overlay_bytes = c.cursor;
+    return 0;
+}
+
+// page-locked host memory for the batch arenas (calfkit/engine/lane.py): what cudaMemcpyAsync needs to overlap the
+// two PCIe directions with the kernels
+extern "C" int ck_host_alloc(uint64_t bytes, void** out) {
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { g_create_error = std::string("ck_host_alloc: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+extern "C" void ck_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int fetch_output_impl(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, uint32_t* host_out_len,
+                             ck_publish* host_pubs, bool wait) {
     cudaSetDevice(h->device);
     uint64_t total = 0;
     if (ck_out_size(h, &total, nullptr, nullptr)) return 1;
@@ -631,15 +653,25 @@ extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, in
     if (host_out_off && h->n_payloads) CUDA_TRY(h, cudaMemcpyAsync(host_out_off, h->d_out_off, sizeof(long long) * ((size_t)h->n_payloads + 1), cudaMemcpyDeviceToHost, h->stream));
     if (host_out_len && h->n_payloads) CUDA_TRY(h, cudaMemcpyAsync(host_out_len, h->d_pay_len, sizeof(u32) * (size_t)h->n_payloads, cudaMemcpyDeviceToHost, h->stream));
     if (host_pubs && h->n_pubs) CUDA_TRY(h, cudaMemcpyAsync(host_pubs, h->d_pubs, sizeof(ck_pub) * (size_t)h->n_pubs, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (wait) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
+}
+extern "C" int ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, uint32_t* host_out_len,
+                               ck_publish* host_pubs) {
+    return fetch_output_impl(h, host_out, cap, host_out_off, host_out_len, host_pubs, true);
+}
+// same copies, queued only (the destination must be page-locked for them to be asynchronous): the caller overlaps its
+// own work and calls ck_sync before reading
+extern "C" int ck_fetch_output_async(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, uint32_t* host_out_len,
+                                     ck_publish* host_pubs) {
+    return fetch_output_impl(h, host_out, cap, host_out_off, host_out_len, host_pubs, false);
 }
 
 extern "C" int ck_fetch_overlay(ck_handle* h, uint8_t* host_ovl, uint64_t cap, int64_t* host_off, uint32_t* host_len, uint64_t* used) {
     cudaSetDevice(h->device);
     if (!h->n) { if (used) *used = 0; return 0; }
     long long total = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&total, h->d_coff + h->n, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&total, &h->d_canon_ctl->cursor, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(host_off, h->d_ovl_off, sizeof(long long) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(host_len, h->d_ovl_len, sizeof(u32) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -80,15 +80,11 @@ enum {
 enum { CK_SRC_INPUT = 0, CK_SRC_LIT = 1, CK_SRC_AUX = 2, CK_SRC_GLUE = 3 };   // input record / literal pool / per-batch aux blob / per-payload glue slot
 #define CK_GLUE_STRIDE 512    // bytes of scratch per payload in which a plan thread assembles the new text of a splice
 typedef struct {
-    uint32_t src_off[CK_MAX_SEGS];   // offset inside the source (INPUT: relative to the record start)
-    uint32_t len_src[CK_MAX_SEGS];   // (len << 2) | src
     uint32_t nseg;
     uint32_t record;                 // index of the input record this output derives from
-    uint32_t topic_off, topic_len;   // destination topic string: span in the INPUT record, or
-    int32_t  topic_id;               //   >= 0: already-resolved registered topic id (then topic_len = 0)
-    uint32_t payload_of;             // 0xffffffff, or index of an earlier output whose bytes are identical
-    uint32_t has_key;                // 1: key = correlation id (nodes/base.py:86,103,117,134); 0: unkeyed
     uint32_t total_len;
-} ck_out_desc;
+    uint32_t pad;
+    uint32_t seg[CK_MAX_SEGS][2];    // {offset inside the source (INPUT: relative to the record start), (len << 2) | src}
+} ck_out_desc;                       // 144 B; a payload with n segments occupies the first 16 + 8 n bytes
 
 #endif

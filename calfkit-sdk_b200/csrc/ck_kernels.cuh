@@ -12,7 +12,6 @@
 
 #include <cuda_runtime.h>
 #include "ck_walk.cuh"
-#include "ck_vm.cuh"
 #include "ck_canon.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -20,9 +19,11 @@
 // the canonical re-emission of the records that arrived in a non-canonical spelling (ck_canon.cuh).
 // Every stage after decode reads a record through ck_rec(), i.e. its canonical bytes.
 // ------------------------------------------------------------------------------------------------
+struct ck_canon_ctl { unsigned long long cursor; u32 count; u32 pad; };   // overlay bytes handed out, records listed
 struct ck_view {
     const u8* in; const long long* off;
     const u8* ovl; const long long* ovl_off; const u32* ovl_len;     // ovl_off[i] < 0: record i has no overlay
+    ck_canon_ctl* canon_ctl; u32* canon_list;                        // records the walker left to the canonicaliser
 };
 __device__ __forceinline__ const u8* ck_rec(const ck_view& v, u32 i, u32& len) {
     long long o = v.ovl_off[i];
@@ -79,35 +80,7 @@ __device__ __forceinline__ u32 ck_fnv1a(const u8* p, u32 n) {
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
-__constant__ uint32_t ck_vm_prog_dev[CK_VM_PROG_WORDS] = CK_VM_PROG_INIT;
-
 #define CK_WALK_THREADS 128
-__global__ void __launch_bounds__(CK_WALK_THREADS)
-ck_walk_vm_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
-    // the schema bytecode and one 64-byte window per thread live in shared memory
-    __shared__ u32 s_prog[CK_VM_PROG_WORDS];
-    __shared__ u32 s_win[CK_WALK_THREADS * CK_VMWIN_WORDS];
-    for (u32 k = threadIdx.x; k < CK_VM_PROG_WORDS; k += CK_WALK_THREADS) s_prog[k] = ck_vm_prog_dev[k];
-    __syncthreads();
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u32 len; const u8* rec;
-    if (mode == 0) { long long a = v.off[i]; len = (u32)(v.off[i + 1] - a); rec = v.in + a; }
-    else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }
-    WalkOut o; o.base = cols + i; o.stride = stride;
-    u32 status, stop = 0;
-    if (len == 0) status = CK_EMPTY;
-    else {
-        VRd r; r.init(rec, len, s_win + threadIdx.x * CK_VMWIN_WORDS);
-        AnyCtx cx;
-        cx.kfill = 0;
-        VmDicts dk;
-        status = ck_vm_walk(r, s_prog, o, cx, dk, stop) ? CK_OK : (mode ? CK_UNSUPPORTED : CK_NOT_CANONICAL);
-    }
-    o.set(CK_COL_STATUS, status);
-    o.set(CK_COL_ERR, stop);
-}
-
 // recursive-descent walker (csrc/ck_walk.cuh), one thread per record.  R = WRd: the record is staged through a
 // per-thread shared-memory window (dynamic shared memory: blockDim.x * CK_WIN_STRIDE bytes); R = GRd: plain
 // global loads (kept for A/B, CK_WALKER=global).
@@ -130,6 +103,10 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
     }
     o.set(CK_COL_STATUS, status);
     o.set(CK_COL_ERR, stop);
+    if (mode == 0 && status == CK_NOT_CANONICAL && v.canon_ctl) {      // rare: hand the record to the canonicaliser pass
+        u32 k = atomicAdd(&v.canon_ctl->count, 1u);
+        v.canon_list[k] = i;
+    }
 }
 #ifndef CK_WALK_MINB
 #define CK_WALK_MINB 7
@@ -138,49 +115,54 @@ __global__ void __launch_bounds__(CK_WALK_THREADS, CK_WALK_MINB)
 ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRd>(v, n, cols, stride, mode); }
 __global__ void __launch_bounds__(CK_WALK_THREADS, 8)
 ck_walk_global_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<GRd>(v, n, cols, stride, mode); }
-// second walk of the decode pass (mode 1: only the records the canonicaliser re-emitted): the trusting readers
-__global__ void __launch_bounds__(CK_WALK_THREADS, CK_WALK_MINB)
-ck_rewalk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRdT>(v, n, cols, stride, mode); }
-__global__ void __launch_bounds__(CK_WALK_THREADS, 8)
-ck_rewalk_global_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<GRdT>(v, n, cols, stride, mode); }
 
 // ------------------------------------------------------------------------------------------------
 // canonicaliser kernels (ck_canon.cuh): one thread per record that the walker left as CK_NOT_CANONICAL.
 //   count: verdict + canonical length (the emitter runs with a zero-capacity sink)
 //   write: after the exclusive scan of the lengths, emit into the overlay buffer
 // ------------------------------------------------------------------------------------------------
+// One launch for the whole pass: the walker listed the records it could not prove canonical (usually none: the kernel
+// then exits at once); every listed record is re-emitted canonically into the overlay — counting pass, space handed out
+// by one atomic on a byte cursor (overlay order is irrelevant: ovl_off[i] says where), writing pass; ck_rewalk_list_kernel
+// then walks them again in that spelling with the trusting reader.
 __global__ void __launch_bounds__(64)
-ck_canon_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32* __restrict__ clen) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u32 need = 0;
-    if (cols[(size_t)CK_COL_STATUS * stride + i] == CK_NOT_CANONICAL) {
+ck_canon_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u8* __restrict__ ovl, long long ovl_cap,
+                long long* __restrict__ ovl_off, u32* __restrict__ ovl_len) {
+    u32 cnt = v.canon_ctl->count;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        u32 i = v.canon_list[k];
         long long a = v.off[i];
         u32 len = (u32)(v.off[i + 1] - a), out_len = 0;
         u32 st = ck_canonicalise(v.in + a, len, nullptr, 0, out_len);
-        if (st == CK_OK) need = (out_len + 15u) & ~15u;
-        else cols[(size_t)CK_COL_STATUS * stride + i] = st;
+        if (st != CK_OK) { cols[(size_t)CK_COL_STATUS * stride + i] = st; continue; }
+        u32 need = (out_len + 15u) & ~15u;
+        long long o0 = (long long)atomicAdd(&v.canon_ctl->cursor, (unsigned long long)need);
+        if (o0 + need > ovl_cap) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; continue; }   // overlay buffer full
+        st = ck_canonicalise(v.in + a, len, ovl + o0, need, out_len);
+        if (st != CK_OK) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; continue; }
+        for (u32 b = out_len; b < need; b++) ovl[o0 + b] = 0;
+        ovl_len[i] = out_len;
+        ovl_off[i] = o0;
     }
-    clen[i] = need;
 }
 
+// second walk of the listed records, over the canonical bytes the kernel above wrote (a separate launch: the walker
+// reads through the non-coherent path)
 __global__ void __launch_bounds__(64)
-ck_canon_write_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, const u32* __restrict__ clen,
-                      const long long* __restrict__ coff, u8* __restrict__ ovl, long long ovl_cap,
-                      long long* __restrict__ ovl_off, u32* __restrict__ ovl_len) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u32 need = clen[i];
-    if (!need) return;
-    long long o0 = coff[i];
-    if (o0 + need > ovl_cap) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; return; }   // overlay buffer full
-    long long a = v.off[i];
-    u32 out_len = 0;
-    u32 st = ck_canonicalise(v.in + a, (u32)(v.off[i + 1] - a), ovl + o0, need, out_len);
-    if (st != CK_OK) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; return; }
-    for (u32 k = out_len; k < need; k++) ovl[o0 + k] = 0;
-    ovl_len[i] = out_len;
-    ovl_off[i] = o0;
+ck_rewalk_list_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride) {
+    u32 cnt = v.canon_ctl->count;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        u32 i = v.canon_list[k];
+        if (v.ovl_off[i] < 0) continue;
+        u32 len; const u8* rec = ck_rec(v, i, len);
+        WalkOut o; o.base = cols + i; o.stride = stride;
+        u32 stop = 0;
+        GRdT r; r.init(rec, len);
+        AnyCtx cx; cx.kfill = 0;
+        u32 status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_UNSUPPORTED;   // never happens by construction (hostsim fuzz)
+        o.set(CK_COL_STATUS, status);
+        o.set(CK_COL_ERR, stop);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,7 +226,7 @@ struct SegWriter {
         d = dd; r = rr; lit = l; aux = a; slot = s; n = 0; total = 0; in_glue = false; overflow = false; gfill = 0; grun = 0; acc = 0; cnt = 0;
     }
     __device__ __forceinline__ void seg(u32 src, u32 off, u32 len) {
-        if (n < CK_MAX_SEGS) { d->src_off[n] = off; d->len_src[n] = (len << 2) | src; n++; } else overflow = true;
+        if (n < CK_MAX_SEGS) { d->seg[n][0] = off; d->seg[n][1] = (len << 2) | src; n++; } else overflow = true;
     }
     // append the low `nb` (1..8) bytes of `chunk` to the open run: 8 aligned bytes per store
     __device__ __forceinline__ void put8(unsigned long long chunk, u32 nb) {
@@ -400,7 +382,7 @@ ck_plan_tool_one(ck_view v, u32 i, u32* __restrict__ cols, u32 stride,
         COL(CK_COL_ACTION) = CK_ACT_HOST_TOOL; COL(CK_COL_NOUT) = 0;
         return;
     }
-    if (cfg.tpl_nparts == 0) {
+    if (cfg.tpl_nparts == 0 || aux_off != nullptr) {             // host results, when supplied, win over the template
         if (aux_off == nullptr) { COL(CK_COL_ACTION) = CK_ACT_HOST_TOOL; COL(CK_COL_NOUT) = 0; return; }
         long long r0 = aux_off[i], r1 = aux_off[i + 1];
         rv_src[0] = CK_SRC_AUX; rv_off[0] = (u32)r0; rv_len[0] = (u32)(r1 - r0); rv_n = 1;
@@ -939,7 +921,7 @@ ck_emit_kernel(ck_view vw, const u8* __restrict__ lit,
     u32 my_len = 0;
     const u8* my_ptr = rec;
     if (lane < nseg) {
-        u32 so = d->src_off[lane], ls = d->len_src[lane];
+        uint2 sg = *(const uint2*)d->seg[lane]; u32 so = sg.x, ls = sg.y;
         u32 src = ls & 3u;
         my_len = ls >> 2;
         my_ptr = (src == CK_SRC_INPUT) ? rec + so : (src == CK_SRC_LIT ? lit + so : (src == CK_SRC_AUX ? aux + so
@@ -1011,6 +993,7 @@ ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
         tid = p.topic_id;
         if (tid < 0 && p.topic_len && tab.cap) {
             u32 h = ck_fnv1a(rec + p.topic_off, p.topic_len);
+            pubs[j].pad = h;
             u32 slot = h & (tab.cap - 1);
             for (u32 probe = 0; probe < tab.cap; probe++) {
                 u32 th = tab.hash[slot];
@@ -1039,5 +1022,7 @@ ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
         if ((threadIdx.x & 31) == (u32)(__ffs(peers) - 1)) atomicAdd(topic_hist + tid, __popc(peers));
     }
 }
+
+#include "ck_plan2.cuh"
 
 #endif  // CK_KERNELS_CUH

@@ -34,7 +34,7 @@ typedef struct {           /* one publish; mirrors struct ck_pub in csrc/ck_kern
     uint32_t record;       /* input record this publish derives from */
     uint32_t has_key;      /* 1: key = correlation id bytes (nodes/base.py:86,103,117,134) */
     int32_t  partition;    /* murmur2(key) % num_partitions, -1 when unkeyed */
-    uint32_t pad;
+    uint32_t pad;          /* FNV-1a of the topic name (set when the name was looked up): groups unregistered topics */
 } ck_publish;
 
 /* lifecycle ------------------------------------------------------------------------------------ */
@@ -121,11 +121,25 @@ int  ck_sync(ck_handle* h);
 uint64_t ck_launch_count(ck_handle* h);   /* kernels launched by this handle so far */
 int  ck_out_size(ck_handle* h, uint64_t* out_bytes, uint32_t* n_payloads, uint32_t* n_publishes);  /* waits */
 int  ck_fetch_columns(ck_handle* h, uint32_t* host_cols /* CK_NUM_COLS * n, column-major */);
+/* records of the current batch that were not in the canonical spelling (re-emitted into the overlay, or rejected), and the
+ * overlay bytes in use; 0 / 0 means every column span refers to the submitted bytes */
+int  ck_canon_stats(ck_handle* h, uint32_t* n_listed, uint64_t* overlay_bytes);
+/* k selected rows of the column table: host_rows[j * n + i] = column which[j] of record i */
+int  ck_fetch_cols(ck_handle* h, const uint32_t* which, uint32_t k, uint32_t* host_rows);
+/* page-locked host memory for batch arenas: the landing zone of polled record batches (reference seam: the consume loop
+ * FastStream runs under calfkit/worker/worker.py:45-51) and of the produced payloads; copies to and from it overlap with
+ * the kernels and with each other.  ck_last_error(NULL) after a failure. */
+int  ck_host_alloc(uint64_t bytes, void** out);
+void ck_host_free(void* p);
 /* payload i = host_out[host_out_off[i] .. + host_out_len[i]); starts are 16-byte aligned, so
  * host_out_off[i+1] - host_out_off[i] is the length rounded up to 16 and *out_bytes of ck_out_size is
  * the padded total */
 int  ck_fetch_output(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off /* n_payloads+1 */,
                      uint32_t* host_out_len /* n_payloads */, ck_publish* host_pubs /* n_publishes */);
+/* the same copies queued only (page-locked destinations): overlap host work, then ck_sync before reading */
+int  ck_fetch_output_async(ck_handle* h, uint8_t* host_out, uint64_t cap, int64_t* host_out_off, uint32_t* host_out_len,
+                           ck_publish* host_pubs);
+int  ck_fetch_cols_async(ck_handle* h, const uint32_t* which, uint32_t k, uint32_t* host_rows);
 /* canonical re-emissions of the records that were submitted in a non-canonical spelling: record i has one iff
  * host_off[i] >= 0 (then host_ovl[host_off[i] .. + host_len[i]) are its canonical bytes; column spans of that
  * record refer to them) */

@@ -13,13 +13,13 @@ def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, "hostsim.cpp"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_walk.cuh"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_common.h"),
-            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm.cuh"),
-            os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_vm_prog.h"),
+            os.path.join(HERE, "ck_vm.cuh"),
+            os.path.join(HERE, "ck_vm_prog.h"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_canon.cuh"),
             os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_float.cuh")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
-                               "-o", _LIB, srcs[0]])
+                               "-I", os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc"), "-o", _LIB, srcs[0]])
     return _LIB
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Compiles the canonical-Envelope schema into the bytecode the device walker interprets
-(csrc/ck_vm.cuh) and writes csrc/ck_vm_prog.h.
+(tests/hostsim/ck_vm.cuh) and writes tests/hostsim/ck_vm_prog.h.
 
 The program is the canonical key order of the reference's wire models (SURVEY.md Appendix A;
 calfkit/models/*.py, _vendor/pydantic_ai/messages.py, tools.py) written as a sequence of
@@ -8,7 +8,7 @@ calfkit/models/*.py, _vendor/pydantic_ai/messages.py, tools.py) written as a seq
 interprets it per record; every literal below is a byte string pydantic's `model_dump_json()`
 emits between two values.
 
-    python calfkit-sdk_b200/tools/gen_vm.py        # regenerates csrc/ck_vm_prog.h (committed)
+    python tests/hostsim/gen_vm.py        # regenerates tests/hostsim/ck_vm_prog.h (committed)
 """
 from __future__ import annotations
 
@@ -16,8 +16,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT = os.path.join(HERE, "..", "csrc", "ck_vm_prog.h")
-COMMON = os.path.join(HERE, "..", "csrc", "ck_common.h")
+OUT = os.path.join(HERE, "ck_vm_prog.h")
+COMMON = os.path.join(HERE, "..", "..", "calfkit-sdk_b200", "csrc", "ck_common.h")
 
 OPS = ["FAIL", "OK", "LIT", "ALT", "PEEKJ", "JMP", "CALL", "RET", "CATCH", "UNCATCH",
        "STR", "STRN", "ANYV", "NUM", "BOOL", "DT", "TAGSCANP",
@@ -448,7 +448,7 @@ def main():
     import io
     words, labels = build()
     with io.StringIO() as f:
-        f.write("// GENERATED by calfkit-sdk_b200/tools/gen_vm.py — do not edit.\n")
+        f.write("// GENERATED by tests/hostsim/gen_vm.py — do not edit.\n")
         f.write("// Bytecode of the canonical-Envelope schema (one u32 per word; op = low 8 bits, arg = high 24).\n")
         f.write("#ifndef CK_VM_PROG_H\n#define CK_VM_PROG_H\n#include <stdint.h>\n\n")
         f.write("enum {\n" + "".join(f"    VOP_{n} = {i},\n" for n, i in OP.items()) + "};\n\n")

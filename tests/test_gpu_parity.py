@@ -143,7 +143,7 @@ def _murmur2(data: bytes) -> int:
 def test_device_walker_equals_host_build_on_fuzz(engine):
     """The g++ build of the walker was fuzzed against pydantic on the CPU (tests/test_walker_hostsim.py);
     here the nvcc build must agree with it column for column on the same inputs."""
-    from hostsim import vm_walk as walk      # the same source the GPU kernel compiles (csrc/ck_vm.cuh)
+    from hostsim import walk                  # g++ build of the source the GPU kernel compiles (csrc/ck_walk.cuh)
     from calfkit import synth
     rng = random.Random(1)
     seeds = [as_bytes(c["input"]) for c in golden("codec.json")] + synth.tool_events(50, seed=2) + \

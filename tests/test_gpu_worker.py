@@ -168,3 +168,59 @@ def test_all_tools_invalid_tailcall_retry():
 
     for r in asyncio.run(go()):
         assert r.output == "gave up after 2 retry prompts: nope"
+
+
+def test_worker_fast_path_arenas_match_oracle():
+    """Row g: polled batches land as pinned arenas, run through the pipelined lanes of a device-template tool node and come
+    out as publish batches — byte-exact against the oracle, bounded polls (records AND bytes), the records the template
+    declines (args as a JSON string / non-string argument) re-run through the host tool, nothing lost."""
+    _skip_without_cuda()
+    import numpy as np
+    import tools_def
+    from calfkit import Client, Worker, agent_tool, synth
+    from calfkit.engine.lane import Arena, PinnedPool
+    from oracle import port
+
+    recs = synth.tool_events(3000, seed=31) + synth.tool_events(300, seed=32, size=None, full_history=True)
+    # OpenAI-style args (a JSON string) and a numeric argument: the device template declines both
+    recs[7] = recs[7].replace(b'"args":{"location":"', b'"args":"{\\"location\\":\\"').replace(b'"},"tool_call_id"', b'\\"}","tool_call_id"', 1)
+    recs[11] = recs[11][:recs[11].index(b'"args":{"location":')] + b'"args":{"location":42}' + recs[11][recs[11].index(b',"tool_call_id"'):]
+    recs[13] = b"{ " + recs[13][1:]                       # non-canonical spelling: canonicalised on the device
+    recs[17] = recs[17][:200]                              # truncated: json_invalid, reported, nothing published
+    node_def = agent_tool(tools_def.get_weather, device_template="It's sunny in {location}")
+    client = Client.connect("localhost")
+    pool = PinnedPool()
+    client.broker.produce_arena("tool.get_weather.input", Arena.pack(recs, pool))
+    got: dict[str, list] = {"weather_agent.input": [], "tool.get_weather.output": []}
+    for t in got:
+        client.broker.sink(t, lambda b, idx, t=t: got[t].extend((k, p) for (_t, k, p, _j) in b.iter_records(idx)))
+    worker = Worker(client, nodes=[node_def], batch_records=512, batch_bytes=400_000, lanes=3, route_topics=["weather_agent.input"])
+    asyncio.run(worker.run(until_idle=True))
+    # host fallbacks are produced per record
+    for t in got:
+        got[t] += [(r.key, r.value) for r in client.broker.poll_batch((t,), 100)]
+    node = port.ToolNode.of(tools_def.get_weather)
+    want: dict[str, list] = {t: [] for t in got}
+    for r in recs:
+        try:
+            for (tp, k, _c, pl) in port.tool_node_event(node, r):
+                want[tp].append((k, pl))
+        except Exception:  # noqa: BLE001  (the invalid record)
+            pass
+    for t in got:
+        assert sorted(got[t], key=lambda x: x[1]) == sorted(want[t], key=lambda x: x[1]), t
+    assert worker.stats["records"] == len(recs) and worker.stats["host_fallback"] == 2 and worker.stats["rejected"] == 3
+    assert worker.stats["steps"] >= 7                     # 3300 records in polls of <= 512 records / 400 kB
+    worker.close()
+
+
+def test_quickstart_with_device_template_goes_through_the_fast_path():
+    _skip_without_cuda()
+    spec = importlib.util.spec_from_file_location("quickstart2", os.path.join(ROOT, "examples", "quickstart", "run_quickstart.py"))
+    qs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(qs)
+    from calfkit import agent_tool
+    qs.get_weather = agent_tool(qs.get_weather._tool.function, device_template="It's sunny in {location}")
+    outs = asyncio.run(qs.main(60))
+    cities = ["Tokyo", "Paris", "São Paulo", "Kraków", "北京"]
+    assert outs == [f"It's sunny in {cities[i % 5]}" for i in range(60)]
