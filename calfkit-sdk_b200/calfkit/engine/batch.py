@@ -235,6 +235,30 @@ class BatchEngine:
         """TailCall to the agent's own subscribe topic (agent.py:171-175)."""
         self._check(self.lib.ck_tailcall_plan(self.h, unix_ms, seed))
 
+    # ---- aggregation gate on the device (csrc/ck_gate.cuh; reference nodes/agent.py:57-68) ---------------------------
+    def gate_create(self, max_entries: int = 1 << 14, max_slots: int | None = None, arena_bytes: int = 256 << 20) -> None:
+        self._check(self.lib.ck_gate_create(self.h, max_entries, max_slots if max_slots is not None else 16 * max_entries, arena_bytes))
+        self.gate_arena_bytes = arena_bytes
+
+    def gate_register(self) -> None:
+        """after fanout_plan: every record that went out as list[Call] becomes a pending entry of the gate"""
+        self._check(self.lib.ck_gate_register(self.h))
+
+    def gate_arrive(self, stamp_base: int) -> None:
+        """run the gate over the submitted batch of arrivals; ACTION afterwards: SILENT / GATE_COMPLETE / GATE_PASS"""
+        self._check(self.lib.ck_gate_arrive(self.h, stamp_base))
+
+    def gate_stats(self) -> dict[str, int]:
+        out = np.zeros(5, dtype=np.uint64)
+        self._check(self.lib.ck_gate_stats(self.h, ptr(out)))
+        st = dict(zip(["entries_used", "slots_used", "arena_used", "live", "failures"], (int(x) for x in out)))
+        if st["failures"]:
+            raise EngineError(f"aggregation gate out of capacity ({st}): raise max_entries / max_slots / arena_bytes")
+        return st
+
+    def gate_reset(self) -> None:
+        self._check(self.lib.ck_gate_reset(self.h))
+
     # ------------------------------------------------------------------------------------------
     def submit(self, data: np.ndarray, offsets: np.ndarray) -> None:
         """H2D + decode of a host batch (uint8 bytes, int64 offsets[n+1]); asynchronous."""

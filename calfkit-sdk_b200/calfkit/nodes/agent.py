@@ -26,7 +26,7 @@ import pydantic_core
 
 from calfkit._types import AgentOutputT
 from calfkit.broker import Record
-from calfkit.engine._lib import CK_ACT_FANOUT, CK_OK, COL, STATUS_NAMES
+from calfkit.engine._lib import CK_ACT_FANOUT, CK_ACT_GATE_COMPLETE, CK_ACT_SILENT, CK_OK, COL, STATUS_NAMES
 from calfkit.models import State
 from calfkit.models.messages import (ModelMessage, ModelRequest, ModelResponse, RetryPromptPart, ToolCallPart,
                                      ToolDefinition, ToolReturnPart)
@@ -59,7 +59,8 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
         self.tools = tools or list()
         self.sequential_only_mode = sequential_only_mode
         self.model_client = model_client
-        self._pending_batches: dict[str, PendingToolBatch] = dict()
+        self._pending_batches: dict[str, PendingToolBatch] = dict()     # host mirror of the gate (object-level callers, CPU tests)
+        self._gate_stamp = 0                                            # records this node consumed so far: arrival order for the device gate
         self._instruction_fns: list[Callable[..., str | None]] = []
         if not isinstance(subscribe_topics, (list, tuple)):
             subscribe_topics = [subscribe_topics]
@@ -96,10 +97,11 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
         del self._pending_batches[corr]
         return batch.base_state
 
-    def _llm_step(self, corr: str, state: State, deps: dict[str, Any]) -> tuple[str, State]:
-        """-> (action, new state) with action in {"silent", "fanout", "return", "tailcall"}"""
+    def _llm_step(self, corr: str, state: State, deps: dict[str, Any], gated: bool = False) -> tuple[str, State]:
+        """-> (action, new state) with action in {"silent", "fanout", "return", "tailcall"}.  gated: the aggregation gate
+        already ran on the device (ck_gate_arrive): `state` is the merged base state or a pass-through."""
         registry = self._registry(state)
-        if not self.sequential_only_mode:
+        if not self.sequential_only_mode and not gated:
             merged = self._aggregate(corr, state)
             if merged is None:
                 return "silent", state
@@ -146,7 +148,7 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
             if state.all_call_ids_complete(*[tc.tool_call_id for tc in state.latest_tool_calls()]):
                 return "tailcall", state
             pending = [tc for tc in state.latest_tool_calls() if tc.tool_call_id not in state.tool_results]
-            if not self.sequential_only_mode and len(pending) > 1:
+            if not self.sequential_only_mode and len(pending) > 1 and not gated:
                 self._pending_batches[corr] = PendingToolBatch(
                     expected_tool_call_ids=frozenset(tc.tool_call_id for tc in pending), base_state=state.model_copy(deep=True))
             return "fanout", state
@@ -159,6 +161,9 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
         registry = {t.tool_schema.name: t.subscribe_topics[0] for t in self.tools}
         engine.set_tool_node(self.publish_topic, None)        # publish-topic id for the ReturnCall plan
         engine.set_agent_node(self.name, self.subscribe_topics[0], self.publish_topic, registry)
+        if not self.sequential_only_mode and not getattr(engine, "_gate_ready", False):
+            engine.gate_create(max_entries=getattr(engine, "max_records", 1 << 14))      # pending fan-outs live in HBM
+            engine._gate_ready = True
 
     # ---- per-request tool registries (overrides.override_agent_tools, reference agent.py:71-75) ------------------------
     def _use_registry(self, engine, registry: dict[str, str]) -> list[str]:
@@ -177,7 +182,18 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
     def process_batch(self, engine, records: list[Record]) -> list[Record]:
         data, offsets = pack_records(records)
         engine.submit(data, offsets)
-        cols = engine.columns()
+        gated = not self.sequential_only_mode and getattr(engine, "_gate_ready", False)
+        merged_env = None
+        if gated:
+            # the aggregation gate runs on the device: of the N tool returns of a fan-out N-1 end here as Silent without ever
+            # becoming Python objects; the completing one comes back as the envelope carrying base_state + collected results
+            engine.gate_arrive(self._gate_stamp)
+            self._gate_stamp += len(records)
+            merged_env = engine.fetch()
+            st = engine.gate_stats()
+            if st["live"] == 0 and st["arena_used"] > engine.gate_arena_bytes // 2:
+                engine.gate_reset()
+        cols = merged_env.cols if merged_env is not None else engine.columns()
         mv = memoryview(data)
         ovl = engine.overlay()          # records that arrived in another spelling: their canonical re-emission (the columns refer to it)
         post: dict[Any, list[tuple[int, bytes]]] = {"fanout": [], "return": []}
@@ -187,20 +203,30 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
             if cols[COL["STATUS"], i] != CK_OK:
                 logger.error("record %d rejected: %s", i, STATUS_NAMES[int(cols[COL["STATUS"], i])])
                 continue
+            if gated and cols[COL["ACTION"], i] == CK_ACT_SILENT:
+                if self.publish_topic:          # handler return of a Silent: the inbound envelope (nodes/base.py:137-145, worker.py:52-53)
+                    corr_raw = merged_env.record_bytes(i)[int(cols[COL["CORR_OFF"], i]):][:int(cols[COL["CORR_LEN"], i])].tobytes()
+                    silent_returns.append(Record(self.publish_topic, merged_env.payload(i), None,
+                                                 records[i].correlation_id or pydantic_core.from_json(b'"' + corr_raw + b'"')))
+                continue
             if ovl is not None and ovl[1][i] >= 0:
                 rec = memoryview(ovl[0])[int(ovl[1][i]):int(ovl[1][i]) + int(ovl[2][i])]
             else:
                 rec = mv[offsets[i]:offsets[i + 1]]
             canonical_in[i] = rec
             s0, s1 = 20, int(cols[COL["SOV_OFF"], i] + cols[COL["SOV_LEN"], i]) + 1       # the `state` object span
-            state = State.model_validate_json(bytes(rec[s0:s1]))                             # LLM boundary
+            state_json = bytes(rec[s0:s1])
+            if gated and cols[COL["ACTION"], i] == CK_ACT_GATE_COMPLETE:
+                merged = merged_env.payload(i)          # inbound[:20] + merged state + inbound[s1:]
+                state_json = merged[s0:len(merged) - (len(rec) - s1)]
+            state = State.model_validate_json(state_json)                                    # LLM boundary
             fo, fl = int(cols[COL["FOV_OFF"], i]), int(cols[COL["FOV_LEN"], i])
             if fl and rec[fo] != ord("n"):
                 state.overrides = OverridesState.model_validate_json(bytes(rec[fo:fo + fl]))
             corr = pydantic_core.from_json(b'"' + bytes(rec[int(cols[COL["CORR_OFF"], i]):][:int(cols[COL["CORR_LEN"], i])]) + b'"')
             deps = pydantic_core.from_json(bytes(rec[int(cols[COL["PD_OFF"], i]):][:int(cols[COL["PD_LEN"], i])]))
             try:
-                action, new_state = self._llm_step(corr, state, deps)
+                action, new_state = self._llm_step(corr, state, deps, gated=gated)
             except Exception:  # noqa: BLE001  (model client / lost-batch RuntimeError: this record only, as one failing handler call in the reference)
                 logger.exception("[%s] agent step failed for record %d; nothing is published for it", corr[:8], i)
                 continue
@@ -232,6 +258,8 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
                 seed = int(np.random.SeedSequence().entropy) & ((1 << 63) - 1)
                 if kind == "fanout":
                     engine.fanout_plan(now_ms, seed, max_fanout=256, sequential=self.sequential_only_mode)
+                    if gated:
+                        engine.gate_register()          # list[Call] records become pending entries of the device gate
                 elif kind == "return":
                     engine.return_plan()
                 else:

@@ -34,6 +34,8 @@ struct ck_handle {
     u32* d_counts = nullptr; long long* d_slot_base = nullptr; u32* d_agent_tables = nullptr;
     bool agent_set = false; ck_agent_cfg h_agent_cfg{};
     u32* d_topic_hist = nullptr;
+    // aggregation gate (allocated by ck_gate_create)
+    ck_gate gate{}; bool gate_set = false; u32* d_rec_entry = nullptr;
     // exchange planning (allocated on first use)
     u32* d_x_hist = nullptr; long long* d_x_base = nullptr; unsigned long long* d_x_nbytes = nullptr;
     long long *d_x_src_off = nullptr, *d_x_len = nullptr, *d_x_dst_off = nullptr; u32 *d_x_len32 = nullptr, *d_x_pub = nullptr;
@@ -154,6 +156,8 @@ extern "C" void ck_destroy(ck_handle* h) {
                     h->d_tab_len, h->d_tab_id, h->d_tab_names, h->d_x_hist, h->d_x_base, h->d_x_nbytes, h->d_x_src_off, h->d_x_len, h->d_x_dst_off,
                     h->d_x_len32, h->d_x_pub, h->d_x_tile, h->d_x_grand};
     for (void* p : ptrs) if (p) cudaFree(p);
+    void* gptrs[] = {h->gate.keys, h->gate.vals, h->gate.entries, h->gate.slots, h->gate.arena, h->gate.ctr, h->d_rec_entry};
+    for (void* p : gptrs) if (p) cudaFree(p);
     if (h->h_grand) cudaFreeHost(h->h_grand);
     if (h->h_x) cudaFreeHost(h->h_x);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -502,6 +506,80 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
         CUDA_TRY(h, cudaGetLastError());
         h->n_pubs = npubs;
     }
+    return 0;
+}
+
+// ---- aggregation gate (csrc/ck_gate.cuh) ------------------------------------------------------------------------------
+extern "C" int ck_gate_create(ck_handle* h, uint32_t max_entries, uint32_t max_slots, uint64_t arena_bytes) {
+    cudaSetDevice(h->device);
+    if (h->gate_set) return fail(h, "ck_gate_create: already created");
+    if (arena_bytes >= (1ull << 32)) return fail(h, "ck_gate_create: arena must be smaller than 4 GiB (32-bit segment offsets)");
+    ck_gate g{};
+    u32 cap = 64; while (cap < 4 * (uint64_t)max_entries) cap <<= 1;
+    g.cap = cap; g.max_entries = max_entries; g.max_slots = max_slots; g.arena_cap = arena_bytes;
+    CUDA_TRY(h, cudaMalloc((void**)&g.keys, sizeof(unsigned long long) * cap));
+    CUDA_TRY(h, cudaMalloc((void**)&g.vals, sizeof(u32) * cap));
+    CUDA_TRY(h, cudaMalloc((void**)&g.entries, sizeof(ck_gate_entry) * (size_t)max_entries));
+    CUDA_TRY(h, cudaMalloc((void**)&g.slots, sizeof(ck_gate_slot) * (size_t)max_slots));
+    CUDA_TRY(h, cudaMalloc((void**)&g.arena, arena_bytes + CK_PAD));
+    CUDA_TRY(h, cudaMalloc((void**)&g.ctr, sizeof(unsigned long long) * 8));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rec_entry, sizeof(u32) * (size_t)h->max_records));
+    CUDA_TRY(h, cudaMemsetAsync(g.keys, 0, sizeof(unsigned long long) * cap, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(g.ctr, 0, sizeof(unsigned long long) * 8, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->gate = g; h->gate_set = true;
+    return 0;
+}
+
+extern "C" int ck_gate_reset(ck_handle* h) {
+    cudaSetDevice(h->device);
+    if (!h->gate_set) return fail(h, "ck_gate_reset: call ck_gate_create first");
+    CUDA_TRY(h, cudaMemsetAsync(h->gate.keys, 0, sizeof(unsigned long long) * h->gate.cap, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->gate.ctr, 0, sizeof(unsigned long long) * 8, h->stream));
+    return 0;
+}
+
+extern "C" int ck_gate_stats(ck_handle* h, uint64_t* out5) {
+    cudaSetDevice(h->device);
+    if (!h->gate_set) return fail(h, "ck_gate_stats: call ck_gate_create first");
+    CUDA_TRY(h, cudaMemcpyAsync(out5, h->gate.ctr, sizeof(unsigned long long) * 5, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// after ck_fanout_plan on a batch of post-LLM envelopes: every record that went out as list[Call] becomes a pending entry
+extern "C" int ck_gate_register(ck_handle* h) {
+    cudaSetDevice(h->device);
+    if (!h->gate_set) return fail(h, "ck_gate_register: call ck_gate_create first");
+    u32 n = h->n;
+    if (!n) return 0;
+    KTimer t(h, CK_K_FANOUT);
+    CKL(h) ck_gate_register_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->gate, h->d_rec_entry);
+    CKL(h) ck_gate_copy_base_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(view_of(h), n, h->gate, h->d_rec_entry);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+// a batch of records arriving at the agent's topic: probe -> resolve -> merge -> encode.  Per record (column ACTION):
+// CK_ACT_SILENT (collected, set still incomplete: only the handler-return publish), CK_ACT_GATE_COMPLETE (payload i = the
+// envelope carrying base_state + collected results), CK_ACT_GATE_PASS (no pending fan-out: continue with the inbound state).
+extern "C" int ck_gate_arrive(ck_handle* h, uint64_t stamp_base) {
+    cudaSetDevice(h->device);
+    if (!h->gate_set) return fail(h, "ck_gate_arrive: call ck_gate_create first");
+    if (!h->tool_set) return fail(h, "ck_gate_arrive: call ck_set_tool_node (publish topic) first");
+    u32 n = h->n;
+    {
+        KTimer t(h, CK_K_PLAN);
+        if (n) {
+            CKL(h) ck_gate_probe_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->gate, stamp_base, h->d_rec_entry);
+            CKL(h) ck_gate_resolve_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->gate, stamp_base, h->d_rec_entry,
+                h->h_tool_cfg.publish_topic_id, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
+            CKL(h) ck_gate_merge_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->gate, h->d_rec_entry, h->d_glue, h->d_descs, h->d_pay_len);
+        }
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (scan_emit(h, n, h->gate.arena)) return 1;
+    h->n_pubs = 2 * n;
     return 0;
 }
 

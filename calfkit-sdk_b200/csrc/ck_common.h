@@ -28,7 +28,9 @@ enum {
     CK_ACT_TAILCALL = 5,     // TailCall: pop + push inheriting callback
     CK_ACT_FANOUT = 6,       // list[Call]: one publish per pending tool call; handler return = input
     CK_ACT_HOST_TOOL = 7,    // tool result must come from the host (tool is not a device template)
-    CK_ACT_REPLY = 8         // client reply: the payload is the output value (DataPart.data / TextPart.text as JSON)
+    CK_ACT_REPLY = 8,        // client reply: the payload is the output value (DataPart.data / TextPart.text as JSON)
+    CK_ACT_GATE_COMPLETE = 9,// aggregation gate: this arrival completed its fan-out; payload = envelope carrying the merged state
+    CK_ACT_GATE_PASS = 10    // aggregation gate: no pending fan-out for this correlation id
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -1024,5 +1024,6 @@ ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
 }
 
 #include "ck_plan2.cuh"
+#include "ck_gate.cuh"
 
 #endif  // CK_KERNELS_CUH

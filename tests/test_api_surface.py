@@ -347,6 +347,9 @@ def test_agent_per_request_registry_switch_and_restore():
             assert all(t in self.topic_ids for t in registry.values())
             self.calls.append(("set_agent_node", tuple(sorted(registry.items()))))
 
+        def gate_create(self, **kw):               # the device gate is created once per engine, not per registry switch
+            self.gate_created = getattr(self, "gate_created", 0) + 1
+
     agent = Agent("planner", subscribe_topics="planner.input", publish_topic="planner.output", tools=[own],
                   model_client=FunctionModelClient(lambda m, t: None))
     eng = Rec()
