@@ -215,6 +215,8 @@ def _fit(offsets, max_records: int, max_bytes: int | None) -> int:
     """how many leading records of a batch fit the limits (at least one)"""
     n = len(offsets) - 1
     k = min(n, max_records)
+    if n and (max_bytes is None or int(offsets[k] - offsets[0]) <= max_bytes):
+        return k                                            # the common case: no array work at all
     if max_bytes is not None and n:
         import numpy as np
         k = min(k, int(np.searchsorted(offsets - offsets[0], max_bytes, side="right")) - 1)

@@ -58,6 +58,22 @@ class Publish:
     partition: int
 
 
+class _SpanOffsets:
+    """offsets[i], offsets[i+1] of records that do NOT lie back to back (values inside raw Kafka frames): indexing i gives
+    the start, and BatchOutput takes the end from `end(i)`"""
+    def __init__(self, off: np.ndarray, ln: np.ndarray):
+        self.off, self.ln = off, ln
+
+    def __getitem__(self, i):
+        return self.off[i]
+
+    def end(self, i):
+        return int(self.off[i]) + int(self.ln[i])
+
+    def __len__(self):
+        return len(self.off) + 1
+
+
 class BatchOutput:
     """Result of one plan+emit: unique payloads + the publish table that references them."""
 
@@ -72,6 +88,8 @@ class BatchOutput:
         if self.overlay is not None and self.overlay[1][r] >= 0:
             o = int(self.overlay[1][r])
             return self.overlay[0][o:o + int(self.overlay[2][r])]
+        if isinstance(self.in_off, _SpanOffsets):
+            return self.in_data[int(self.in_off[r]):self.in_off.end(r)]
         return self.in_data[self.in_off[r]:self.in_off[r + 1]]
 
     def payload(self, i: int) -> bytes:
@@ -240,9 +258,9 @@ class BatchEngine:
         self._check(self.lib.ck_gate_create(self.h, max_entries, max_slots if max_slots is not None else 16 * max_entries, arena_bytes))
         self.gate_arena_bytes = arena_bytes
 
-    def gate_register(self) -> None:
+    def gate_register(self, min_pending: int = 2) -> None:
         """after fanout_plan: every record that went out as list[Call] becomes a pending entry of the gate"""
-        self._check(self.lib.ck_gate_register(self.h))
+        self._check(self.lib.ck_gate_register(self.h, min_pending))
 
     def gate_arrive(self, stamp_base: int) -> None:
         """run the gate over the submitted batch of arrivals; ACTION afterwards: SILENT / GATE_COMPLETE / GATE_PASS"""
@@ -266,6 +284,39 @@ class BatchEngine:
         self.n = len(offsets) - 1
         self._in_data, self._in_off = data, offsets
         self._check(self.lib.ck_submit(self.h, ptr(data), ptr(offsets), self.n))
+
+    def submit_recordbatch(self, buf: np.ndarray) -> int:
+        """H2D + CRC32C check + record split + field decode + walk of a fetch response's record set (concatenated Kafka
+        RecordBatch v2 frames, uncompressed); returns the number of records.  Column spans are relative to each VALUE."""
+        assert buf.dtype == np.uint8
+        n = C.c_uint32(0)
+        self._check(self.lib.ck_submit_recordbatch(self.h, ptr(buf), buf.nbytes, C.byref(n)))
+        self.n = n.value
+        idx = self.rb_index()
+        # the host-side view of the batch for result decoding: record i = buf[val_off[i] : val_off[i] + val_len[i]]
+        self._in_data, self._in_off = buf, _SpanOffsets(idx["val_off"], idx["val_len"])
+        self._rb = idx
+        return self.n
+
+    def rb_index(self) -> dict[str, np.ndarray]:
+        """where value / key / the correlation_id header of every record lie in the submitted buffer (len -1 = absent)"""
+        n = self.n
+        out = {"val_off": np.zeros(n, np.int64), "val_len": np.zeros(n, np.uint32), "key_off": np.zeros(n, np.int64),
+               "key_len": np.zeros(n, np.int32), "corr_off": np.zeros(n, np.int64), "corr_len": np.zeros(n, np.int32),
+               "bad": np.zeros(n, np.uint32)}
+        if n:
+            self._check(self.lib.ck_fetch_rb_index(self.h, *[ptr(out[k]) for k in ("val_off", "val_len", "key_off", "key_len", "corr_off", "corr_len", "bad")]))
+        return out
+
+    def encode_recordbatch(self, pub_indices: np.ndarray, base_offset: int = 0, timestamp_ms: int = 0) -> np.ndarray:
+        """one Kafka RecordBatch v2 frame holding the publishes `pub_indices` of the current plan (one topic-partition, in
+        send order), built on the device"""
+        idx = np.ascontiguousarray(pub_indices, dtype=np.uint32)
+        cap = self.max_out + 256 * self.max_payloads + 4096
+        buf = np.empty(cap, dtype=np.uint8)
+        used = C.c_uint64(0)
+        self._check(self.lib.ck_encode_recordbatch(self.h, ptr(idx), len(idx), base_offset, timestamp_ms, ptr(buf), cap, C.byref(used)))
+        return buf[:used.value]
 
     def submit_device(self, dev_data, dev_off, n: int, host_data: np.ndarray | None = None,
                       host_off: np.ndarray | None = None) -> None:

@@ -129,10 +129,15 @@ class PublishBatch:
     view of the lane's landing buffers; nothing per record is materialised until a consumer asks for one topic."""
     def __init__(self, out: np.ndarray, out_off: np.ndarray, out_len: np.ndarray, pubs: np.ndarray, topic_names: dict[int, str],
                  source: Arena | None, key_spans: np.ndarray | None, status: np.ndarray | None, action: np.ndarray | None,
-                 on_release: Callable[[], None] | None = None, overlay=None):
+                 on_release: Callable[[], None] | None = None, overlay=None, order: np.ndarray | None = None,
+                 key_counts: np.ndarray | None = None):
         self.out, self.out_off, self.out_len, self.pubs, self.topic_names = out, out_off, out_len, pubs, topic_names
         self.source, self.key_spans, self.status, self.action = source, key_spans, status, action
         self.overlay = overlay          # (bytes, off[n], len[n]) canonical re-emissions: column / topic spans of those records refer to them
+        # device-side grouping (ck_group_publishes): `order` = publish indices grouped by key (0 = topic without a registered
+        # id, 1 + id = registered topic, 4095 = unused slot), send order kept inside a group; key_counts[4096]
+        self.order, self.key_counts = order, key_counts
+        self._starts = None if key_counts is None else np.concatenate(([0], np.cumsum(key_counts, dtype=np.int64)))
         self._on_release = on_release
         self._refs = 1
         self._live = None
@@ -151,6 +156,8 @@ class PublishBatch:
     # -- vectorised views
     @property
     def n_publishes(self) -> int:
+        if self.key_counts is not None:
+            return int(self.key_counts[:-1].sum())
         return int(self.live_mask().sum())
 
     def live_mask(self) -> np.ndarray:
@@ -160,6 +167,9 @@ class PublishBatch:
 
     def topic_counts(self) -> dict[int, int]:
         """registered topic id -> publishes (id -1 = topic named by a span of the source record, e.g. a client reply topic)"""
+        if self.key_counts is not None:                      # grouped on the device: no scan of the table
+            nz = np.nonzero(self.key_counts[:-1])[0]
+            return {int(k) - 1: int(self.key_counts[k]) for k in nz}
         ids = np.ascontiguousarray(self.pubs["topic_id"][self.live_mask()])
         if ids.size == 0:
             return {}
@@ -168,6 +178,8 @@ class PublishBatch:
 
     def select(self, topic_id: int) -> np.ndarray:
         """indices into the publish table of the live publishes to `topic_id`, in order"""
+        if self.order is not None and -1 <= topic_id < 4093:
+            return self.order[int(self._starts[topic_id + 1]):int(self._starts[topic_id + 2])]
         return np.nonzero(self.live_mask() & (self.pubs["topic_id"] == topic_id))[0]
 
     def payload(self, pub_index: int) -> bytes:
@@ -248,25 +260,31 @@ class Lane:
         eng, pool, n = self.eng, self.pool, self.arena.n
         nb, npay, npub = eng.out_size()
         self._b_out = b_out = pool.take(nb + 64)
-        self._b_meta = b_meta = pool.take(8 * (npay + 1) + 4 * npay + PUB_DTYPE.itemsize * npub + 16 * n + 256)
+        self._b_meta = b_meta = pool.take(8 * (npay + 1) + 4 * npay + PUB_DTYPE.itemsize * npub + 16 * n + 4 * npub + 4 * 4096 + 512)
         off = b_meta.view(np.int64, npay + 1)
         ln = b_meta.view(np.uint32, npay, 8 * (npay + 1))
         p0 = (8 * (npay + 1) + 4 * npay + 31) & ~31
         pubs = b_meta.view(PUB_DTYPE, npub, p0)
-        rows = b_meta.view(np.uint32, 4 * n, p0 + PUB_DTYPE.itemsize * npub).reshape(4, n)
+        r0 = p0 + PUB_DTYPE.itemsize * npub
+        rows = b_meta.view(np.uint32, 4 * n, r0).reshape(4, n)
+        g0 = (r0 + 16 * n + 31) & ~31
+        order = b_meta.view(np.uint32, npub, g0)
+        key_counts = b_meta.view(np.uint32, 4096, (g0 + 4 * npub + 31) & ~31)
+        eng._check(eng.lib.ck_group_publishes(eng.h))       # per-topic split on the device, before the copies are queued
         eng._check(eng.lib.ck_fetch_output_async(eng.h, ptr(b_out.array), b_out.array.nbytes, ptr(off) if npay else None,
                                                  ptr(ln) if npay else None, ptr(pubs) if npub else None))
         if n:
             eng._check(eng.lib.ck_fetch_cols_async(eng.h, ptr(_FAST_COLS), 4, ptr(rows)))
-        self._views = (b_out.array[:nb], off, ln, pubs, rows)
+        eng._check(eng.lib.ck_fetch_groups(eng.h, ptr(order), ptr(key_counts), 0))
+        self._views = (b_out.array[:nb], off, ln, pubs, rows, order, key_counts)
         self.collecting = True
 
     def finish_collect(self) -> PublishBatch:
         eng, pool = self.eng, self.pool
         eng.sync()
-        out, off, ln, pubs, rows = self._views
+        out, off, ln, pubs, rows, order, key_counts = self._views
         b_out, b_meta = self._b_out, self._b_meta
-        self.d2h_bytes = int(out.nbytes + off.nbytes + ln.nbytes + pubs.nbytes + rows.nbytes)
+        self.d2h_bytes = int(out.nbytes + off.nbytes + ln.nbytes + pubs.nbytes + rows.nbytes + order.nbytes + key_counts.nbytes)
         listed = C.c_uint32(0)
         eng._check(eng.lib.ck_canon_stats(eng.h, C.byref(listed), None))
         overlay = eng.overlay() if listed.value else None       # rare: some records arrived in a non-canonical spelling
@@ -277,7 +295,8 @@ class Lane:
             pool.give(b_out)
             pool.give(b_meta)
             arena.release()
-        return PublishBatch(out, off, ln, pubs, eng.topic_names, arena, rows[2:4], rows[0], rows[1], on_release=done, overlay=overlay)
+        return PublishBatch(out, off, ln, pubs, eng.topic_names, arena, rows[2:4], rows[0], rows[1], on_release=done, overlay=overlay,
+                            order=order, key_counts=key_counts)
 
     def collect(self) -> PublishBatch:
         if not self.collecting:

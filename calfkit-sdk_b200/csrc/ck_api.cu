@@ -36,6 +36,16 @@ struct ck_handle {
     u32* d_topic_hist = nullptr;
     // aggregation gate (allocated by ck_gate_create)
     ck_gate gate{}; bool gate_set = false; u32* d_rec_entry = nullptr;
+    // peer exchange (ck_comm_create)
+    u8* d_recv = nullptr; ck_xpeers peers{}; void* peer_opened[CK_X_MAXWORLD] = {nullptr}; u32 comm_rank = 0, comm_world = 0, max_fwd = 0, x_nb = 0;
+    unsigned long long region_stride = 0, region_data_cap = 0; u32* d_x_overflow = nullptr; bool comm_ready = false;
+    // publish grouping (allocated on first use)
+    u32 *d_g_hist = nullptr, *d_g_o1 = nullptr, *d_g_o2 = nullptr, *d_g_keys = nullptr; long long* d_g_base = nullptr; unsigned long long *d_g_tile = nullptr, *d_g_grand = nullptr;
+    bool grouped = false;
+    // Kafka record-batch framing (allocated on first use)
+    long long *d_rb_batch_off = nullptr, *d_rb_rec_pos = nullptr, *d_rb_key_off = nullptr, *d_rb_corr_off = nullptr, *d_rb_rec_off = nullptr, *d_rb_frame_len = nullptr;
+    u32 *d_rb_rec_base = nullptr, *d_rb_batch_bad = nullptr, *d_rb_rec_batch = nullptr, *d_rb_val_len = nullptr, *d_rb_rec_bad = nullptr, *d_rb_idx = nullptr, *d_rb_sizes = nullptr, *d_rb_partial = nullptr;
+    int *d_rb_key_len = nullptr, *d_rb_corr_len = nullptr; u8* d_rb_frame = nullptr; uint64_t rb_frame_cap = 0; uint32_t rb_n = 0;
     // exchange planning (allocated on first use)
     u32* d_x_hist = nullptr; long long* d_x_base = nullptr; unsigned long long* d_x_nbytes = nullptr;
     long long *d_x_src_off = nullptr, *d_x_len = nullptr, *d_x_dst_off = nullptr; u32 *d_x_len32 = nullptr, *d_x_pub = nullptr;
@@ -44,7 +54,7 @@ struct ck_handle {
     ck_topic_table tab{}; u32 *d_tab_hash = nullptr, *d_tab_off = nullptr, *d_tab_len = nullptr; int32_t* d_tab_id = nullptr; u8* d_tab_names = nullptr;
     uint32_t num_partitions = 0, hist_cap = 0;
     // current batch
-    const u8* cur_in = nullptr; const long long* cur_in_off = nullptr;
+    const u8* cur_in = nullptr; const long long* cur_in_off = nullptr; const u32* cur_len = nullptr;
     uint32_t n = 0, n_payloads = 0, n_pubs = 0;
     bool tool_set = false; ck_tool_cfg h_tool_cfg{};
     unsigned long long n_launch = 0;
@@ -156,8 +166,14 @@ extern "C" void ck_destroy(ck_handle* h) {
                     h->d_tab_len, h->d_tab_id, h->d_tab_names, h->d_x_hist, h->d_x_base, h->d_x_nbytes, h->d_x_src_off, h->d_x_len, h->d_x_dst_off,
                     h->d_x_len32, h->d_x_pub, h->d_x_tile, h->d_x_grand};
     for (void* p : ptrs) if (p) cudaFree(p);
-    void* gptrs[] = {h->gate.keys, h->gate.vals, h->gate.entries, h->gate.slots, h->gate.arena, h->gate.ctr, h->d_rec_entry};
+    void* gptrs[] = {h->gate.keys, h->gate.vals, h->gate.entries, h->gate.slots, h->gate.arena, h->gate.ctr, h->d_rec_entry,
+                     h->d_rb_batch_off, h->d_rb_rec_pos, h->d_rb_key_off, h->d_rb_corr_off, h->d_rb_rec_off, h->d_rb_frame_len, h->d_rb_rec_base, h->d_rb_batch_bad,
+                     h->d_g_hist, h->d_g_o1, h->d_g_o2, h->d_g_keys, h->d_g_base, h->d_g_tile, h->d_g_grand,
+                     h->d_rb_rec_batch, h->d_rb_val_len, h->d_rb_rec_bad, h->d_rb_idx, h->d_rb_sizes, h->d_rb_partial, h->d_rb_key_len, h->d_rb_corr_len, h->d_rb_frame};
     for (void* p : gptrs) if (p) cudaFree(p);
+    for (u32 d = 0; d < CK_X_MAXWORLD; d++) if (h->peer_opened[d]) cudaIpcCloseMemHandle(h->peer_opened[d]);
+    if (h->d_recv) cudaFree(h->d_recv);
+    if (h->d_x_overflow) cudaFree(h->d_x_overflow);
     if (h->h_grand) cudaFreeHost(h->h_grand);
     if (h->h_x) cudaFreeHost(h->h_x);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -232,7 +248,7 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
 
 static ck_view view_of(ck_handle* h) {
     ck_view v; v.in = h->cur_in; v.off = h->cur_in_off; v.ovl = h->d_ovl; v.ovl_off = h->d_ovl_off; v.ovl_len = h->d_ovl_len;
-    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list;
+    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list; v.len = h->cur_len;
     return v;
 }
 
@@ -276,14 +292,14 @@ extern "C" int ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* ho
     CUDA_TRY(h, cudaMemcpyAsync(h->d_in, host_in, nbytes, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_in_off, host_off, sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->d_in + nbytes, 0, 16, h->stream));
-    h->cur_in = h->d_in; h->cur_in_off = h->d_in_off; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
+    h->cur_in = h->d_in; h->cur_in_off = h->d_in_off; h->cur_len = nullptr; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
     return launch_decode(h);
 }
 
 extern "C" int ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n) {
     cudaSetDevice(h->device);
     if (n > h->max_records) return fail(h, "ck_submit_device: batch has more records than max_records");
-    h->cur_in = dev_in; h->cur_in_off = (const long long*)dev_off; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
+    h->cur_in = dev_in; h->cur_in_off = (const long long*)dev_off; h->cur_len = nullptr; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
     return launch_decode(h);
 }
 
@@ -509,6 +525,181 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     return 0;
 }
 
+// ---- grouping the publish table by topic (csrc/ck_group.cuh) ---------------------------------------------------------------
+extern "C" int ck_group_publishes(ck_handle* h) {
+    cudaSetDevice(h->device);
+    u32 nb_max = (h->max_pubs + CK_G_BLOCK - 1) / CK_G_BLOCK;
+    if (!h->d_g_hist) {
+        size_t nh = 64 * (size_t)nb_max;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_hist, sizeof(u32) * nh));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_base, sizeof(long long) * (nh + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_o1, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_o2, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_keys, sizeof(u32) * CK_G_KEYS));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_tile, sizeof(unsigned long long) * (nh / CK_SCAN_TILE + 2)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_grand, sizeof(unsigned long long)));
+    }
+    u32 n = h->n_pubs;
+    h->grouped = true;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_g_keys, 0, sizeof(u32) * CK_G_KEYS, h->stream));
+    if (!n) return 0;
+    u32 nb = (n + CK_G_BLOCK - 1) / CK_G_BLOCK;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        CKL(h) ck_group_count_kernel<0><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, nullptr, n, h->d_g_hist, h->d_g_keys);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_g_hist, 64 * nb, h->d_g_base, 0, h->d_g_tile, h->d_g_grand)) return 1;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        CKL(h) ck_group_scatter_kernel<0><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, nullptr, n, h->d_g_base, h->d_g_o1);
+        CKL(h) ck_group_count_kernel<6><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, h->d_g_o1, n, h->d_g_hist, h->d_g_keys);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_g_hist, 64 * nb, h->d_g_base, 0, h->d_g_tile, h->d_g_grand)) return 1;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        CKL(h) ck_group_scatter_kernel<6><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, h->d_g_o1, n, h->d_g_base, h->d_g_o2);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+// order[n_publishes]: publish indices grouped by key (0 = unregistered topic, 1 + id = registered topic id, 4095 = unused
+// slot), send order kept inside a group; key_counts[4096].  wait = 0: copies queued only (page-locked destinations).
+extern "C" int ck_fetch_groups(ck_handle* h, uint32_t* host_order, uint32_t* host_key_counts, int wait) {
+    cudaSetDevice(h->device);
+    if (!h->grouped) return fail(h, "ck_fetch_groups: call ck_group_publishes first");
+    if (h->n_pubs) CUDA_TRY(h, cudaMemcpyAsync(host_order, h->d_g_o2, sizeof(u32) * (size_t)h->n_pubs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(host_key_counts, h->d_g_keys, sizeof(u32) * CK_G_KEYS, cudaMemcpyDeviceToHost, h->stream));
+    if (wait) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- Kafka RecordBatch v2 framing (csrc/ck_kafka.cuh) -------------------------------------------------------------------
+static int rb_alloc(ck_handle* h) {
+    if (h->d_rb_batch_off) return 0;
+    size_t mr = (size_t)h->max_records + 1;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_batch_off, sizeof(long long) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_rec_base, sizeof(u32) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_batch_bad, sizeof(u32) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_rec_pos, sizeof(long long) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_rec_batch, sizeof(u32) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_val_len, sizeof(u32) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_key_off, sizeof(long long) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_key_len, sizeof(int) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_corr_off, sizeof(long long) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_corr_len, sizeof(int) * mr));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_rec_bad, sizeof(u32) * mr));
+    return 0;
+}
+static inline uint32_t host_be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+// A fetch response's record set (concatenated RecordBatch v2 frames, as it came off the socket) goes to HBM in one copy;
+// CRC32C check, record split and varint field decode run on the device and the walker reads every value where it lies.
+// The host only chains through the frame headers (12 + batchLength bytes each) to index the frames.
+extern "C" int ck_submit_recordbatch(ck_handle* h, const uint8_t* host_buf, uint64_t nbytes, uint32_t* n_records) {
+    cudaSetDevice(h->device);
+    if (nbytes > h->max_in) return fail(h, "ck_submit_recordbatch: buffer larger than max_in_bytes");
+    if (rb_alloc(h)) return 1;
+    std::vector<long long> boff; std::vector<u32> rbase;
+    uint64_t pos = 0; uint64_t total = 0;
+    while (pos + 12 <= nbytes) {
+        uint32_t blen = host_be32(host_buf + pos + 8);
+        uint64_t end = pos + 12 + (uint64_t)blen;
+        if ((int32_t)blen < (int32_t)(CK_RB_HEADER - 12) || end > nbytes) break;         // truncated trailing frame: legal in a fetch response
+        uint32_t cnt = host_be32(host_buf + pos + 57);
+        if (total + cnt > h->max_records) return fail(h, "ck_submit_recordbatch: more records than max_records");
+        boff.push_back((long long)pos); rbase.push_back((u32)total);
+        total += cnt; pos = end;
+    }
+    boff.push_back((long long)pos); rbase.push_back((u32)total);
+    u32 nb = (u32)boff.size() - 1, n = (u32)total;
+    if (n_records) *n_records = n;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_in, host_buf, pos, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_in + pos, 0, 16, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_rb_batch_off, boff.data(), sizeof(long long) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_rb_rec_base, rbase.data(), sizeof(u32) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));           // the two index vectors are pageable stack objects
+    h->rb_n = n;
+    if (nb) {
+        KTimer t(h, CK_K_WALK);
+        CKL(h) ck_rb_crc_kernel<<<(nb + 7) / 8, 256, 0, h->stream>>>(h->d_in, h->d_rb_batch_off, nb, h->d_rb_batch_bad);
+        CKL(h) ck_rb_split_kernel<<<(nb + 127) / 128, 128, 0, h->stream>>>(h->d_in, h->d_rb_batch_off, h->d_rb_rec_base, nb, h->d_rb_batch_bad,
+                                                                        h->d_rb_rec_pos, h->d_rb_rec_batch);
+        if (n) CKL(h) ck_rb_fields_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_in, (long long)pos, h->d_rb_rec_pos, h->d_rb_rec_batch, h->d_rb_batch_bad, n,
+            h->d_in_off, h->d_rb_val_len, h->d_rb_key_off, h->d_rb_key_len, h->d_rb_corr_off, h->d_rb_corr_len, h->d_rb_rec_bad);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    h->cur_in = h->d_in; h->cur_in_off = h->d_in_off; h->cur_len = h->d_rb_val_len; h->n = n; h->n_payloads = 0; h->n_pubs = 0;
+    if (launch_decode(h)) return 1;
+    if (n) { CKL(h) ck_rb_mark_bad_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_rb_rec_bad, n, h->d_cols, n); CUDA_TRY(h, cudaGetLastError()); }
+    return 0;
+}
+
+// per record of the last ck_submit_recordbatch: where value / key / correlation_id header lie in the submitted buffer
+// (key_len / corr_len = -1: absent), and whether its frame failed the CRC / framing check
+extern "C" int ck_fetch_rb_index(ck_handle* h, int64_t* val_off, uint32_t* val_len, int64_t* key_off, int32_t* key_len,
+                                 int64_t* corr_off, int32_t* corr_len, uint32_t* bad) {
+    cudaSetDevice(h->device);
+    u32 n = h->rb_n;
+    if (!n) return 0;
+    if (val_off) CUDA_TRY(h, cudaMemcpyAsync(val_off, h->d_in_off, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (val_len) CUDA_TRY(h, cudaMemcpyAsync(val_len, h->d_rb_val_len, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (key_off) CUDA_TRY(h, cudaMemcpyAsync(key_off, h->d_rb_key_off, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (key_len) CUDA_TRY(h, cudaMemcpyAsync(key_len, h->d_rb_key_len, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (corr_off) CUDA_TRY(h, cudaMemcpyAsync(corr_off, h->d_rb_corr_off, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (corr_len) CUDA_TRY(h, cudaMemcpyAsync(corr_len, h->d_rb_corr_len, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (bad) CUDA_TRY(h, cudaMemcpyAsync(bad, h->d_rb_rec_bad, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// produce side: the publishes host_idx[0..n) of the current plan (one topic-partition, in send order) become ONE
+// RecordBatch v2 frame — varint record headers, key = correlation id when keyed, calfkit's two headers, CRC32C — built
+// on the device from the payloads where they lie in the output buffer, then copied to host_frame.
+extern "C" int ck_encode_recordbatch(ck_handle* h, const uint32_t* host_idx, uint32_t n, int64_t base_offset, int64_t timestamp_ms,
+                                     uint8_t* host_frame, uint64_t cap, uint64_t* frame_len) {
+    cudaSetDevice(h->device);
+    if (!n || n > h->n_pubs) return fail(h, "ck_encode_recordbatch: index list empty or longer than the publish table");
+    if (!h->d_rb_idx) {
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_idx, sizeof(u32) * (size_t)h->max_pubs));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_sizes, sizeof(u32) * (size_t)h->max_pubs));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_rec_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_frame_len, sizeof(long long)));
+        h->rb_frame_cap = h->max_out + 256ull * h->max_payloads + 4096;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_frame, h->rb_frame_cap + CK_PAD));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_rb_partial, sizeof(u32) * (h->rb_frame_cap / CK_RB_CRC_CHUNK + 2)));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_rb_idx, host_idx, sizeof(u32) * n, cudaMemcpyHostToDevice, h->stream));
+    {
+        KTimer t(h, CK_K_EMIT);
+        CKL(h) ck_rb_size_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_pubs, h->d_rb_idx, n, h->d_pay_len, h->d_cols, h->n, h->d_rb_sizes);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_rb_sizes, n, h->d_rb_rec_off, 0)) return 1;
+    // the frame's size is known on the device only; bound it on the host to size the launches and the copy
+    uint64_t out_total = 0;
+    { unsigned long long g = 0; CUDA_TRY(h, cudaMemcpyAsync(&g, h->d_grand, sizeof g, cudaMemcpyDeviceToHost, h->stream)); CUDA_TRY(h, cudaStreamSynchronize(h->stream)); out_total = g; }
+    uint64_t total = CK_RB_HEADER + out_total;
+    if (total > h->rb_frame_cap) return fail(h, "ck_encode_recordbatch: frame larger than the frame buffer");
+    if (total > cap) return fail(h, "ck_encode_recordbatch: host buffer too small");
+    {
+        KTimer t(h, CK_K_EMIT);
+        CKL(h) ck_rb_write_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(view_of(h), h->d_pubs, h->d_rb_idx, n, h->d_pay_len, h->d_out_off, h->d_out, h->d_cols, h->n,
+                                                                h->d_rb_rec_off, h->d_rb_frame);
+        CKL(h) ck_rb_header_kernel<<<1, 32, 0, h->stream>>>(h->d_rb_frame, h->d_rb_rec_off, n, base_offset, timestamp_ms, h->d_rb_frame_len);
+        u32 nchunks = (u32)((total - CK_RB_CRC_FROM + CK_RB_CRC_CHUNK - 1) / CK_RB_CRC_CHUNK);
+        CKL(h) ck_rb_crc_chunks_kernel<<<(nchunks + 7) / 8, 256, 0, h->stream>>>(h->d_rb_frame, h->d_rb_frame_len, h->d_rb_partial);
+        CKL(h) ck_rb_crc_fold_kernel<<<1, 32, 0, h->stream>>>(h->d_rb_frame, h->d_rb_frame_len, h->d_rb_partial);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(host_frame, h->d_rb_frame, total, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (frame_len) *frame_len = total;
+    return 0;
+}
+
 // ---- aggregation gate (csrc/ck_gate.cuh) ------------------------------------------------------------------------------
 extern "C" int ck_gate_create(ck_handle* h, uint32_t max_entries, uint32_t max_slots, uint64_t arena_bytes) {
     cudaSetDevice(h->device);
@@ -548,13 +739,13 @@ extern "C" int ck_gate_stats(ck_handle* h, uint64_t* out5) {
 }
 
 // after ck_fanout_plan on a batch of post-LLM envelopes: every record that went out as list[Call] becomes a pending entry
-extern "C" int ck_gate_register(ck_handle* h) {
+extern "C" int ck_gate_register(ck_handle* h, uint32_t min_pending) {
     cudaSetDevice(h->device);
     if (!h->gate_set) return fail(h, "ck_gate_register: call ck_gate_create first");
     u32 n = h->n;
     if (!n) return 0;
     KTimer t(h, CK_K_FANOUT);
-    CKL(h) ck_gate_register_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->gate, h->d_rec_entry);
+    CKL(h) ck_gate_register_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->gate, min_pending, h->d_rec_entry);
     CKL(h) ck_gate_copy_base_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(view_of(h), n, h->gate, h->d_rec_entry);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -583,6 +774,125 @@ extern "C" int ck_gate_arrive(ck_handle* h, uint64_t stamp_base) {
     return 0;
 }
 
+// ---- cross-partition forward over peer memory (csrc/ck_xsend.cuh) --------------------------------------------------------
+static int x_alloc(ck_handle* h) {
+    if (h->d_x_hist) return 0;
+    u32 nb_max = (h->max_pubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
+    size_t nh = (size_t)CK_X_MAXWORLD * nb_max;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_hist, sizeof(u32) * nh));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_base, sizeof(long long) * (nh + 1)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_nbytes, sizeof(unsigned long long) * CK_X_MAXWORLD));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_src_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_len, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_dst_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_len32, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_pub, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+    size_t nt = (nh > h->max_pubs ? nh : h->max_pubs) / CK_SCAN_TILE + 2;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_tile, sizeof(unsigned long long) * nt));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_grand, sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMallocHost((void**)&h->h_x, sizeof(long long) * (2 * CK_X_MAXWORLD + 2)));
+    return 0;
+}
+
+// receive buffer of this rank: `world` regions (one per source rank), each max_fwd meta entries + data_cap payload bytes.
+// ipc_handle_out (64 bytes): give it to every peer (any side channel: the Python binding all-gathers it).
+extern "C" int ck_comm_create(ck_handle* h, uint32_t rank, uint32_t world, uint32_t max_fwd, uint64_t data_cap, uint8_t* ipc_handle_out) {
+    cudaSetDevice(h->device);
+    if (world < 1 || world > CK_X_MAXWORLD || rank >= world) return fail(h, "ck_comm_create: world must be 1..16 and rank < world");
+    if (h->d_recv) return fail(h, "ck_comm_create: already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    h->comm_rank = rank; h->comm_world = world; h->max_fwd = max_fwd;
+    h->region_data_cap = (data_cap + 15) & ~15ull;
+    h->region_stride = (CK_X_HDR + (unsigned long long)max_fwd * sizeof(ck_xmeta) + h->region_data_cap + 255) & ~255ull;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_recv, h->region_stride * world + CK_PAD));
+    CUDA_TRY(h, cudaMemset(h->d_recv, 0, h->region_stride * world));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_overflow, sizeof(u32) * CK_X_MAXWORLD));
+    CUDA_TRY(h, cudaMemset(h->d_x_overflow, 0, sizeof(u32) * CK_X_MAXWORLD));
+    cudaIpcMemHandle_t ih;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&ih, h->d_recv));
+    memcpy(ipc_handle_out, &ih, 64);
+    return 0;
+}
+
+// handles[world][64]: every rank's ck_comm_create output, in rank order (this rank's own entry is ignored)
+extern "C" int ck_comm_connect(ck_handle* h, const uint8_t* handles) {
+    cudaSetDevice(h->device);
+    if (!h->d_recv) return fail(h, "ck_comm_connect: call ck_comm_create first");
+    for (u32 d = 0; d < h->comm_world; d++) {
+        if (d == h->comm_rank) { h->peers.recv[d] = h->d_recv; continue; }
+        cudaIpcMemHandle_t ih; memcpy(&ih, handles + 64 * (size_t)d, 64);
+        void* p = nullptr;
+        CUDA_TRY(h, cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_opened[d] = p; h->peers.recv[d] = (u8*)p;
+    }
+    h->comm_ready = true;
+    return 0;
+}
+
+// plan + pack + transfer of the keyed publishes of the current plan whose partition another rank owns: queued on the
+// handle's stream, no host synchronisation.  The caller brackets it with two barriers (peers consumed the previous
+// contents / every peer's stores have landed).
+extern "C" int ck_exchange_send(ck_handle* h, uint64_t step) {
+    cudaSetDevice(h->device);
+    if (!h->comm_ready) return fail(h, "ck_exchange_send: call ck_comm_create / ck_comm_connect first");
+    if (x_alloc(h)) return 1;
+    u32 rank = h->comm_rank, world = h->comm_world, npubs = h->n_pubs;
+    u32 nb = (npubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
+    if (!nb) nb = 1;
+    h->x_nb = nb;
+    u32 nh = world * nb;
+    {
+        KTimer t(h, CK_K_ROUTE);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_x_nbytes, 0, sizeof(unsigned long long) * CK_X_MAXWORLD, h->stream));
+        CKL(h) ck_xplan_count_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, rank, world, h->d_x_hist, h->d_x_nbytes);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_x_hist, nh, h->d_x_base, 0, h->d_x_tile, h->d_x_grand)) return 1;       // d_x_grand = payloads selected
+    {
+        KTimer t(h, CK_K_ROUTE);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_x_len32, 0, sizeof(u32) * ((size_t)npubs + 1), h->stream));
+        CKL(h) ck_xplan_scatter_kernel<<<nb, CK_X_BLOCK, 0, h->stream>>>(h->d_pubs, npubs, h->d_pay_len, h->d_out_off, rank, world, h->d_x_base,
+                                                                  h->d_x_src_off, h->d_x_len, h->d_x_len32, h->d_x_pub);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    // byte offsets of the (16-byte padded) payloads in destination order; scanned over all publish slots so that the
+    // launch does not need the selected count on the host (unselected tail entries are zero)
+    if (run_scan(h, h->d_x_len32, npubs ? npubs : 1, h->d_x_dst_off, 15, h->d_x_tile, h->d_g_grand ? h->d_g_grand : h->d_grand)) return 1;
+    {
+        KTimer t(h, CK_K_EMIT);
+        if (npubs) CKL(h) ck_xsend_kernel<<<(npubs + 7) / 8, 256, 0, h->stream>>>(h->d_pubs, h->d_x_pub, h->d_x_src_off, h->d_x_len32, h->d_x_dst_off, h->d_x_base, nb,
+            h->d_x_grand, h->d_out, h->peers, rank, world, h->region_stride, h->max_fwd, h->region_data_cap, h->d_x_overflow);
+        CKL(h) ck_xhdr_kernel<<<1, 32, 0, h->stream>>>(h->d_x_dst_off, h->d_x_base, nb, h->d_x_grand, h->peers, rank, world, h->region_stride, step, h->d_x_overflow);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+// what this rank received (after the caller's closing barrier): per source rank the header {step, count, overflow, bytes};
+// ck_recv_buffer gives the device address and layout for in-place use, ck_fetch_received copies region `src` to the host
+extern "C" int ck_recv_info(ck_handle* h, void** dev_recv, uint64_t* region_stride, uint32_t* max_fwd, uint64_t* data_cap) {
+    if (!h->d_recv) return fail(h, "ck_recv_info: call ck_comm_create first");
+    if (dev_recv) *dev_recv = h->d_recv;
+    if (region_stride) *region_stride = h->region_stride;
+    if (max_fwd) *max_fwd = h->max_fwd;
+    if (data_cap) *data_cap = h->region_data_cap;
+    return 0;
+}
+extern "C" int ck_fetch_received(ck_handle* h, uint32_t src, uint64_t* hdr4 /* step, count, overflow, nbytes */, uint8_t* host_meta, uint8_t* host_data, uint64_t data_cap) {
+    cudaSetDevice(h->device);
+    if (!h->d_recv || src >= h->comm_world) return fail(h, "ck_fetch_received: no such region");
+    const u8* region = h->d_recv + (size_t)src * h->region_stride;
+    ck_xregion_hdr hd{};
+    CUDA_TRY(h, cudaMemcpyAsync(&hd, region, sizeof hd, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    hdr4[0] = hd.step; hdr4[1] = hd.count; hdr4[2] = hd.overflow; hdr4[3] = hd.nbytes;
+    if (hd.nbytes > data_cap) return fail(h, "ck_fetch_received: host buffer too small");
+    if (host_meta && hd.count) CUDA_TRY(h, cudaMemcpyAsync(host_meta, region + CK_X_HDR, sizeof(ck_xmeta) * (size_t)hd.count, cudaMemcpyDeviceToHost, h->stream));
+    if (host_data && hd.nbytes) CUDA_TRY(h, cudaMemcpyAsync(host_data, region + CK_X_HDR + (size_t)h->max_fwd * sizeof(ck_xmeta), hd.nbytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // multi-GPU exchange planning: see ck_xplan_*_kernel.  One host synchronisation (the all-to-all needs the split
 // sizes on the host); the scatter and the offset scan are queued behind it.
 extern "C" int ck_exchange_plan(ck_handle* h, uint32_t rank, uint32_t world, const int64_t** dev_src_off, const int64_t** dev_len,
@@ -590,22 +900,7 @@ extern "C" int ck_exchange_plan(ck_handle* h, uint32_t rank, uint32_t world, con
                                 uint32_t* n_sel) {
     cudaSetDevice(h->device);
     if (world < 1 || world > CK_X_MAXWORLD || rank >= world) return fail(h, "ck_exchange_plan: world must be 1..16 and rank < world");
-    u32 nb_max = (h->max_pubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
-    if (!h->d_x_hist) {
-        size_t nh = (size_t)CK_X_MAXWORLD * nb_max;
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_hist, sizeof(u32) * nh));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_base, sizeof(long long) * (nh + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_nbytes, sizeof(unsigned long long) * CK_X_MAXWORLD));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_src_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_len, sizeof(long long) * ((size_t)h->max_pubs + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_dst_off, sizeof(long long) * ((size_t)h->max_pubs + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_len32, sizeof(u32) * ((size_t)h->max_pubs + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_pub, sizeof(u32) * ((size_t)h->max_pubs + 1)));
-        size_t nt = (nh > h->max_pubs ? nh : h->max_pubs) / CK_SCAN_TILE + 2;
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_tile, sizeof(unsigned long long) * nt));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_x_grand, sizeof(unsigned long long)));
-        CUDA_TRY(h, cudaMallocHost((void**)&h->h_x, sizeof(long long) * (2 * CK_X_MAXWORLD + 2)));
-    }
+    if (x_alloc(h)) return 1;
     u32 npubs = h->n_pubs;
     u32 nb = (npubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
     for (u32 d = 0; d < world; d++) { host_counts[d] = 0; host_nbytes[d] = 0; }

@@ -82,12 +82,15 @@ __device__ __forceinline__ int ck_gate_find(const ck_gate& g, Rd& r, u32 coff, u
 // (ACTION == FANOUT) becomes a pending entry: base_state = its `state` object, expected ids = its pending tool calls.
 // (a) thread per record: allocate entry, slots and arena space, insert into the table, fill the slots
 __global__ void __launch_bounds__(128)
-ck_gate_register_kernel(ck_view v, u32 n, const u32* __restrict__ cols, u32 stride, ck_gate g, u32* __restrict__ rec_entry) {
+ck_gate_register_kernel(ck_view v, u32 n, const u32* __restrict__ cols, u32 stride, ck_gate g, u32 min_pending, u32* __restrict__ rec_entry) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
 #define COL(k) cols[(size_t)(k) * stride + i]
     rec_entry[i] = 0xffffffffu;
-    if (COL(CK_COL_STATUS) != CK_OK || COL(CK_COL_ACTION) != CK_ACT_FANOUT) return;
+    // the reference registers a PendingToolBatch only for list[Call] (more than one pending call, agent.py:178,194-209);
+    // min_pending = 1 also takes single Calls (tests of the gate itself: the golden cases include a one-id batch)
+    u32 act = COL(CK_COL_ACTION);
+    if (COL(CK_COL_STATUS) != CK_OK || !(act == CK_ACT_FANOUT || (min_pending <= 1 && act == CK_ACT_CALL))) return;
     u32 rlen; const u8* rec = ck_rec(v, i, rlen);
     Rd r; r.init(rec, rlen);
     u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF), trl = COL(CK_COL_TR_LEN);
@@ -98,7 +101,7 @@ ck_gate_register_kernel(ck_view v, u32 n, const u32* __restrict__ cols, u32 stri
     u32 pending = 0;
     { u32 pos = tc + 1; while (pos < r.n && r.at(pos) != '}') { Span k; ck_string(r, pos, k); pos++; ck_skip_value(r, pos);
         if (ck_dict_find(r, tr, k.off, k.len).len == 0) pending++; if (pos < r.n && r.at(pos) == ',') pos++; } }
-    if (pending < 2) return;
+    if (pending < min_pending || pending == 0) return;
     u32 e = (u32)atomicAdd(&g.ctr[0], 1ull);
     u32 s0 = (u32)atomicAdd(&g.ctr[1], (unsigned long long)pending);
     unsigned long long need = (unsigned long long)((base_len + 15u) & ~15u) + ((clen + 15u) & ~15u);

@@ -24,13 +24,17 @@ struct ck_view {
     const u8* in; const long long* off;
     const u8* ovl; const long long* ovl_off; const u32* ovl_len;     // ovl_off[i] < 0: record i has no overlay
     ck_canon_ctl* canon_ctl; u32* canon_list;                        // records the walker left to the canonicaliser
-};
+    const u32* len;                                                  // NULL: record i = [off[i], off[i+1]); else off[i] .. + len[i]
+};                                                                   //       (values inside raw Kafka record batches are not contiguous)
+__device__ __forceinline__ const u8* ck_rec_in(const ck_view& v, u32 i, u32& len) {     // the submitted bytes of record i
+    long long a = v.off[i];
+    len = v.len ? v.len[i] : (u32)(v.off[i + 1] - a);
+    return v.in + a;
+}
 __device__ __forceinline__ const u8* ck_rec(const ck_view& v, u32 i, u32& len) {
     long long o = v.ovl_off[i];
     if (o >= 0) { len = v.ovl_len[i]; return v.ovl + o; }
-    long long a = v.off[i];
-    len = (u32)(v.off[i + 1] - a);
-    return v.in + a;
+    return ck_rec_in(v, i, len);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,7 +93,7 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 len; const u8* rec;
-    if (mode == 0) { long long a = v.off[i]; len = (u32)(v.off[i + 1] - a); rec = v.in + a; }      // the submitted spelling
+    if (mode == 0) rec = ck_rec_in(v, i, len);                                                       // the submitted spelling
     else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }                                  // re-walk of canonicalised records
     WalkOut o; o.base = cols + i; o.stride = stride;
     u32 status, stop = 0;
@@ -131,14 +135,14 @@ ck_canon_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u8* __rest
     u32 cnt = v.canon_ctl->count;
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
         u32 i = v.canon_list[k];
-        long long a = v.off[i];
-        u32 len = (u32)(v.off[i + 1] - a), out_len = 0;
-        u32 st = ck_canonicalise(v.in + a, len, nullptr, 0, out_len);
+        u32 len, out_len = 0;
+        const u8* src = ck_rec_in(v, i, len);
+        u32 st = ck_canonicalise(src, len, nullptr, 0, out_len);
         if (st != CK_OK) { cols[(size_t)CK_COL_STATUS * stride + i] = st; continue; }
         u32 need = (out_len + 15u) & ~15u;
         long long o0 = (long long)atomicAdd(&v.canon_ctl->cursor, (unsigned long long)need);
         if (o0 + need > ovl_cap) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; continue; }   // overlay buffer full
-        st = ck_canonicalise(v.in + a, len, ovl + o0, need, out_len);
+        st = ck_canonicalise(src, len, ovl + o0, need, out_len);
         if (st != CK_OK) { cols[(size_t)CK_COL_STATUS * stride + i] = CK_UNSUPPORTED; continue; }
         for (u32 b = out_len; b < need; b++) ovl[o0 + b] = 0;
         ovl_len[i] = out_len;
@@ -1025,5 +1029,8 @@ ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
 
 #include "ck_plan2.cuh"
 #include "ck_gate.cuh"
+#include "ck_kafka.cuh"
+#include "ck_group.cuh"
+#include "ck_xsend.cuh"
 
 #endif  // CK_KERNELS_CUH

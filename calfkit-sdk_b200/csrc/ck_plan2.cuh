@@ -24,8 +24,23 @@ extern __shared__ uint4 ck_win_smem[];   // nvcc's host pass parses the device c
 #define CK_P2_THREADS 128
 #define CK_P2_WIN 64u                 // window bytes per thread
 #define CK_P2_WSTRIDE 80u             // slot stride (the pad spreads the slots over the banks)
-#define CK_P2_GLUE 288u               // glue bytes per record assembled in shared memory
-#define CK_P2_GSTRIDE 304u
+#define CK_P2_GLUE 256u               // glue bytes per record assembled in shared memory (more: global-memory planner)
+#define CK_P2_GSTRIDE 272u
+#define CK_P2_SEGS 8u                 // segments per record staged in shared memory (more: global-memory planner)
+
+// out of line and by value: a member function taking `this` would pin the reader (and everything that points to it) in
+// local memory — the first version of this kernel made 307 local-memory loads per warp that way
+__device__ __noinline__ u32 ck_p2_refill(const u8* gb, u32 ap, u32 lim) {
+    u32 wb = ap & ~15u;
+    wb = wb >= 16u ? wb - 16u : 0u;
+    u32 dst = (u32)__cvta_generic_to_shared((const u8*)ck_win_smem + threadIdx.x * CK_P2_WSTRIDE);
+    const u8* src = gb + wb;
+#pragma unroll
+    for (u32 k = 0; k < CK_P2_WIN; k += 16)
+        if (wb + k < lim) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + k), "l"(src + k) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return wb;
+}
 
 struct PRd {
     static const bool kWindow = true;
@@ -38,18 +53,7 @@ struct PRd {
     __device__ __forceinline__ u32 st() const { return wbase; }
     __device__ __forceinline__ void set_st(u32 s) { wbase = s; }
     __device__ __forceinline__ void invalidate() { wbase = CK_WIN_NONE; }
-    __device__ __noinline__ void refill(u32 ap) {
-        u32 wb = ap & ~15u;
-        wb = wb >= 16u ? wb - 16u : 0u;
-        u32 lim = (m + n + 15u) & ~15u;
-        u32 dst = (u32)__cvta_generic_to_shared(wp);
-        const u8* src = g - m + wb;
-#pragma unroll
-        for (u32 k = 0; k < CK_P2_WIN; k += 16)
-            if (wb + k < lim) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + k), "l"(src + k) : "memory");
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        wbase = wb;
-    }
+    __device__ __forceinline__ void refill(u32 ap) { wbase = ck_p2_refill(g - m, ap, (m + n + 15u) & ~15u); }
     __device__ __forceinline__ u8 at(u32 pos) {
         u32 ap = pos + m, o = ap - wbase;
         if (o >= CK_P2_WIN) { refill(ap); o = ap - wbase; }
@@ -65,23 +69,23 @@ struct PRd {
     __device__ __forceinline__ void load16(u32 pos, u64& x0, u64& x1) { x0 = load8(pos); x1 = load8(pos + 8); }
 };
 
+struct ck_p2_desc { u32 nseg, record, total_len, pad; u32 seg[CK_P2_SEGS][2]; };     // leading part of ck_out_desc
 struct ck_p2_stage {                   // one per warp
     u8 glue[32][CK_P2_GSTRIDE];
-    ck_out_desc desc[32];
-    ck_pub pubs[64];
+    ck_p2_desc desc[32];
 };
 #define CK_P2_SMEM (CK_P2_THREADS * CK_P2_WSTRIDE + (CK_P2_THREADS / 32) * sizeof(ck_p2_stage))
 
 // SegWriter over shared-memory staging (same layout rules as SegWriter: every segment starts at a 16-byte aligned
 // output offset, all but the last are multiples of 16 bytes long)
 struct SegWriter2 {
-    ck_out_desc* d; PRd* r; const u8* lit; const u8* aux; u8* slot;
+    ck_p2_desc* d; PRd* r; const u8* lit; const u8* aux; u8* slot;
     u32 n, total; bool in_glue, overflow; u32 gfill, grun; unsigned long long acc; u32 cnt;
-    __device__ __forceinline__ void init(ck_out_desc* dd, PRd* rr, const u8* l, const u8* a, u8* s) {
+    __device__ __forceinline__ void init(ck_p2_desc* dd, PRd* rr, const u8* l, const u8* a, u8* s) {
         d = dd; r = rr; lit = l; aux = a; slot = s; n = 0; total = 0; in_glue = false; overflow = false; gfill = 0; grun = 0; acc = 0; cnt = 0;
     }
     __device__ __forceinline__ void seg(u32 src, u32 off, u32 len) {
-        if (n < CK_MAX_SEGS) { *(uint2*)d->seg[n] = make_uint2(off, (len << 2) | src); n++; } else overflow = true;
+        if (n < CK_P2_SEGS) { *(uint2*)d->seg[n] = make_uint2(off, (len << 2) | src); n++; } else overflow = true;
     }
     __device__ __forceinline__ void put8(unsigned long long chunk, u32 nb) {
         if (gfill + nb > CK_P2_GLUE) { overflow = true; return; }
@@ -239,7 +243,7 @@ struct ck_p2_res { u32 action, nout, status, pay_len, glue_len, desc_len; };
 __device__ __forceinline__ bool
 ck_plan_tool2_one(ck_view v, u32 i, const u32* __restrict__ cols, u32 stride, const ck_tool_cfg& cfg, const u8* __restrict__ lit,
                   const long long* __restrict__ aux_off, const u8* __restrict__ aux, int mode,
-                  ck_out_desc* d, u8* gslot, ck_pub* pb /* [2] */, const ck_topic_table& tab, u32 num_partitions, ck_p2_res& out) {
+                  ck_p2_desc* d, u8* gslot, ck_pub* pb /* [2] */, const ck_topic_table& tab, u32 num_partitions, ck_p2_res& out) {
 #define COL(k) cols[(size_t)(k) * stride + i]
     ck_pub none; none.payload = 0xffffffffu; none.topic_id = -1; none.topic_off = none.topic_len = 0; none.record = i;
     none.has_key = 0; none.partition = -1; none.pad = 0;
@@ -363,25 +367,30 @@ ck_plan_tool2_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
     u32 i0 = i - lane;                                   // first record of this warp
     ck_p2_res res; res.action = CK_ACT_NONE; res.nout = 0; res.status = CK_OK; res.pay_len = 0; res.glue_len = 0; res.desc_len = 0;
     bool live = i < n, staged = false;
+    ck_pub pb[2];
+    pb[0].payload = pb[1].payload = 0xffffffffu; pb[0].topic_id = pb[1].topic_id = -1;
     if (live) {
-        staged = ck_plan_tool2_one(v, i, cols, stride, *cfgp, lit, aux_off, aux, mode, &st->desc[lane], st->glue[lane], &st->pubs[2 * lane],
-                                   tab, num_partitions, res);
+        staged = ck_plan_tool2_one(v, i, cols, stride, *cfgp, lit, aux_off, aux, mode, &st->desc[lane], st->glue[lane], pb, tab, num_partitions, res);
         if (!staged) {
             // rare: splice too large for the staging slot -> the global-memory planner, then route its two publishes
             ck_plan_tool_one(v, i, cols, stride, cfgp, lit, aux_off, aux, glue, mode, descs, pay_len, pubs);
             ck_route_one_global(v, cols, stride, pubs + 2 * i, tab, num_partitions);
             ck_route_one_global(v, cols, stride, pubs + 2 * i + 1, tab, num_partitions);
-            st->pubs[2 * lane] = pubs[2 * i]; st->pubs[2 * lane + 1] = pubs[2 * i + 1];     // for the histogram below
+            pb[0] = pubs[2 * i]; pb[1] = pubs[2 * i + 1];                                   // for the histogram below
             res.glue_len = 0; res.desc_len = 0;
         } else {
             pay_len[i] = res.pay_len;
             cols[(size_t)CK_COL_ACTION * stride + i] = res.action;
             cols[(size_t)CK_COL_NOUT * stride + i] = res.nout;
             if (res.status != CK_OK) cols[(size_t)CK_COL_STATUS * stride + i] = res.status;
+            // the two publishes: 64 contiguous bytes per record, four 16-byte stores (adjacent lanes fill adjacent sectors)
+            uint4* gp = (uint4*)(pubs + 2 * (size_t)i);
+            const uint4* sp = (const uint4*)pb;
+            gp[0] = sp[0]; gp[1] = sp[1]; gp[2] = sp[2]; gp[3] = sp[3];
         }
     }
     __syncwarp();
-    // ---- coalesced write-out: two records per store instruction, 16 bytes per lane
+    // ---- coalesced write-out of descriptors and glue: two records per store instruction, 16 bytes per lane
     u32 half = lane >> 4, hl = lane & 15;
 #pragma unroll 1
     for (u32 it = 0; it < 16; it++) {
@@ -390,25 +399,14 @@ ck_plan_tool2_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
         if (hl * 16 < dl) *(uint4*)((u8*)(descs + i0 + rr) + hl * 16) = *(const uint4*)((const u8*)&st->desc[rr] + hl * 16);
         for (u32 k = hl * 16; k < gl; k += 256) *(uint4*)(glue + (size_t)(i0 + rr) * CK_GLUE_STRIDE + k) = *(const uint4*)(&st->glue[rr][k]);
     }
-    u32 stg = __ballot_sync(0xffffffffu, staged);
-    {   // the warp's 64 publishes are contiguous in HBM: 2 KB, 4 x 16 bytes per lane (slow-path records wrote theirs already)
-        const uint4* sp = (const uint4*)st->pubs;
-        uint4* gp = (uint4*)(pubs + 2 * (size_t)i0);
-#pragma unroll
-        for (u32 k = 0; k < 4; k++) {
-            u32 q = k * 32 + lane;                       // 16-byte chunk index: record = q / 4
-            if ((stg >> (q >> 2)) & 1u) gp[q] = sp[q];
-        }
-    }
     // ---- per-topic histogram, aggregated inside the warp (one atomic per distinct topic)
 #pragma unroll
     for (u32 k = 0; k < 2; k++) {
-        ck_pub p = st->pubs[2 * lane + k];
-        bool cnt = live && p.payload != 0xffffffffu && p.topic_id >= 0 && (u32)p.topic_id < hist_cap;
+        bool cnt = live && pb[k].payload != 0xffffffffu && pb[k].topic_id >= 0 && (u32)pb[k].topic_id < hist_cap;
         u32 active = __ballot_sync(0xffffffffu, cnt);
         if (cnt) {
-            u32 peers = __match_any_sync(active, p.topic_id);
-            if (lane == (u32)(__ffs(peers) - 1)) atomicAdd(topic_hist + p.topic_id, __popc(peers));
+            u32 peers = __match_any_sync(active, pb[k].topic_id);
+            if (lane == (u32)(__ffs(peers) - 1)) atomicAdd(topic_hist + pb[k].topic_id, __popc(peers));
         }
     }
 }

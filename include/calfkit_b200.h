@@ -69,6 +69,29 @@ int  ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t nparts, c
 int  ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* host_off, uint32_t n);
 int  ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n);
 
+/* group the publish table of the current plan by destination topic on the device (stable two-pass radix sort over 12-bit
+ * keys: 0 = topic without a registered id, 1 + id = registered topic, 4095 = unused slot) — the per-topic split a producer
+ * needs (reference: one broker.publish per topic, nodes/base.py:82-87) without any host-side scan of the table.
+ * ck_fetch_groups: order[n_publishes] = publish indices grouped by key (send order kept inside a group) and
+ * key_counts[4096]; wait = 0 queues the copies only (page-locked destinations, ck_sync before reading). */
+int  ck_group_publishes(ck_handle* h);
+int  ck_fetch_groups(ck_handle* h, uint32_t* host_order, uint32_t* host_key_counts, int wait);
+
+/* Kafka RecordBatch v2 framing on the device (reference: aiokafka under broker.subscriber / broker.publish,
+ * calfkit/worker/worker.py:45-53, calfkit/nodes/base.py:82-87).  ck_submit_recordbatch takes a fetch response's record set
+ * (concatenated v2 frames, uncompressed) as it came off the socket: one H2D copy, then CRC32C verification, record split and
+ * zig-zag varint field decode on the device; the walker reads each value where it lies.  Records of a frame that fails the
+ * CRC / framing check get status 6 (bad frame); a truncated trailing frame is ignored.  *n_records = records decoded.
+ * ck_fetch_rb_index: per record, where value / key / the `correlation_id` header lie in the submitted buffer (-1 = absent).
+ * ck_encode_recordbatch: the publishes host_idx[0..n) of the current plan (one topic-partition, in send order) -> one
+ * uncompressed v2 frame (offsetDelta = position in the list, key = correlation id when keyed, headers content-type and
+ * correlation_id, CRC32C), built on the device and copied to host_frame. */
+int  ck_submit_recordbatch(ck_handle* h, const uint8_t* host_buf, uint64_t nbytes, uint32_t* n_records);
+int  ck_fetch_rb_index(ck_handle* h, int64_t* val_off, uint32_t* val_len, int64_t* key_off, int32_t* key_len,
+                       int64_t* corr_off, int32_t* corr_len, uint32_t* bad);
+int  ck_encode_recordbatch(ck_handle* h, const uint32_t* host_idx, uint32_t n, int64_t base_offset, int64_t timestamp_ms,
+                           uint8_t* host_frame, uint64_t cap, uint64_t* frame_len);
+
 /* tool node, host tools only: gather every record's tool-call `args` JSON into the output buffer
  * (payload i = args of record i, empty when the record does not reach the tool). */
 int  ck_tool_args(ck_handle* h);
@@ -116,7 +139,7 @@ int  ck_tailcall_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed);
  *   ck_gate_stats     out5 = {entries used, slots used, arena bytes used, live entries, capacity failures}
  *   ck_gate_reset     forget everything (e.g. when live == 0 and the arena is mostly used) */
 int  ck_gate_create(ck_handle* h, uint32_t max_entries, uint32_t max_slots, uint64_t arena_bytes);
-int  ck_gate_register(ck_handle* h);
+int  ck_gate_register(ck_handle* h, uint32_t min_pending /* 2 = the reference's rule; 1 also registers single Calls */);
 int  ck_gate_arrive(ck_handle* h, uint64_t stamp_base);
 int  ck_gate_stats(ck_handle* h, uint64_t* out5);
 int  ck_gate_reset(ck_handle* h);

