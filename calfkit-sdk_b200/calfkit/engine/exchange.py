@@ -4,9 +4,11 @@ payloads whose partition (murmur2(correlation_id) % num_partitions, computed by 
 owned by another rank.  Reference analogue: the record would simply be produced to a topic-partition
 that a different worker process consumes (calfkit/nodes/base.py:82-87 key=correlation_id).
 
-The planning below is plain tensor bookkeeping (device-agnostic torch ops: it runs on CUDA tensors in
-production and on CPU tensors under the gloo tests); the byte movement is ck_gather_spans (CUDA) and
-torch.distributed.all_to_all_single (NCCL over NVLink)."""
+Production path (`PeerExchange`): every rank maps its peers' receive buffers (CUDA IPC over NVSwitch) and
+`ck_exchange_send` plans, packs and transfers in one pass on the device — a warp per forwarded payload stores it straight
+into the owner's region — with no host synchronisation; torch.distributed is used for the one-off handle exchange and for
+two 4-byte barriers per step.  The tensor-level `plan_exchange` / `exchange` below is the device-agnostic statement of the
+same plan (CPU tensors under the gloo tests; the kernels are pinned to it on the GPU)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -87,3 +89,74 @@ def exchange(plan: ExchangePlan, gather: Callable[[ExchangePlan, torch.Tensor], 
     rlens = torch.empty(sum(rc), dtype=torch.int64, device=plan.lens.device)
     dist.all_to_all_single(rlens, plan.lens.contiguous(), rc, sc)
     return sum(rc), sum(rb), rlens
+
+
+META_DTYPE = None
+
+
+def _meta_dtype():
+    global META_DTYPE
+    if META_DTYPE is None:
+        import numpy as np
+        META_DTYPE = np.dtype([("len", "<u4"), ("topic_id", "<i4"), ("partition", "<i4"), ("src_pub", "<u4")])
+    return META_DTYPE
+
+
+class PeerExchange:
+    """One per engine (lane).  create -> all-gather the 64-byte IPC handles -> connect; then per step `send(step)` after
+    the plan.  The receive regions stay in HBM for the next hop; `received()` copies them out for a host-side consumer."""
+
+    def __init__(self, engine, rank: int, world: int, max_fwd: int, data_cap: int, group=None):
+        import ctypes as C
+        import numpy as np
+        self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        self.max_fwd, self.data_cap = max_fwd, data_cap
+        handle = np.zeros(64, dtype=np.uint8)
+        engine._check(engine.lib.ck_comm_create(engine.h, rank, world, max_fwd, data_cap, handle.ctypes.data))
+        mine = torch.from_numpy(handle).to(torch.device("cuda", torch.cuda.current_device()))
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        handles = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
+        engine._check(engine.lib.ck_comm_connect(engine.h, handles.ctypes.data))
+        self._token = torch.zeros(1, dtype=torch.int32, device=mine.device)
+        dist.barrier(group=group)
+        _ = C
+
+    def barrier(self) -> None:
+        """4-byte all-reduce on the current stream: a device-side barrier, the host does not wait"""
+        dist.all_reduce(self._token, group=self.group)
+
+    def send(self, step: int) -> None:
+        """forward the foreign-partition payloads of the engine's current plan.  Stream-ordered, asynchronous:
+        barrier (peers have consumed last step's regions) -> ck_exchange_send -> barrier (all stores have landed)."""
+        self.barrier()
+        self.engine._check(self.engine.lib.ck_exchange_send(self.engine.h, step))
+        self.barrier()
+
+    def received(self, step: int | None = None):
+        """[(source rank, meta records, payload bytes)] for every other rank; raises if a sender overflowed a region"""
+        import numpy as np
+        out = []
+        for src in range(self.world):
+            if src == self.rank:
+                continue
+            hdr = np.zeros(4, dtype=np.uint64)
+            meta = np.zeros(self.max_fwd, dtype=_meta_dtype())
+            data = np.empty(self.data_cap, dtype=np.uint8)
+            self.engine._check(self.engine.lib.ck_fetch_received(self.engine.h, src, hdr.ctypes.data, meta.ctypes.data, data.ctypes.data, data.nbytes))
+            if hdr[2]:
+                raise RuntimeError(f"rank {src} could not fit {int(hdr[2])} payloads into its region here: raise max_fwd / data_cap")
+            if step is not None and int(hdr[0]) != step:
+                raise RuntimeError(f"region of rank {src} holds step {int(hdr[0])}, expected {step}")
+            out.append((src, meta[:int(hdr[1])], data[:int(hdr[3])]))
+        return out
+
+    @staticmethod
+    def payloads(meta, data) -> list[bytes]:
+        """split a region's data into payloads (16-byte aligned starts)"""
+        res, pos = [], 0
+        for ln in meta["len"]:
+            ln = int(ln)
+            res.append(data[pos:pos + ln].tobytes())
+            pos += (ln + 15) & ~15
+        return res

@@ -143,6 +143,22 @@ int  ck_gate_register(ck_handle* h, uint32_t min_pending /* 2 = the reference's 
 int  ck_gate_arrive(ck_handle* h, uint64_t stamp_base);
 int  ck_gate_stats(ck_handle* h, uint64_t* out5);
 int  ck_gate_reset(ck_handle* h);
+/* cross-partition forward over NVLink peer memory (records shard by Kafka partition across the GPUs of a box; reference
+ * analogue: producing to a topic-partition another worker process consumes, nodes/base.py:82-87 key=correlation_id).
+ *   ck_comm_create    this rank's receive buffer: one region per source rank (max_fwd payloads, data_cap bytes each);
+ *                     ipc_handle_out[64] is handed to every peer (any side channel)
+ *   ck_comm_connect   handles[world][64] in rank order: maps the peers' receive buffers (CUDA IPC, same box)
+ *   ck_exchange_send  plan + pack + transfer in one pass on the handle's stream, no host synchronisation: the keyed
+ *                     publishes of the current plan whose partition % world != rank are written straight into the owner's
+ *                     region for this rank (payload bytes 16-byte aligned + {len, topic_id, partition, source publish}),
+ *                     then the region header {step, count, overflow, bytes}.  The caller brackets it with two barriers:
+ *                     before (every peer has consumed what it received last time) and after (all stores have landed).
+ *   ck_recv_info / ck_fetch_received: where the regions are / one region copied to the host */
+int  ck_comm_create(ck_handle* h, uint32_t rank, uint32_t world, uint32_t max_fwd, uint64_t data_cap, uint8_t* ipc_handle_out);
+int  ck_comm_connect(ck_handle* h, const uint8_t* handles);
+int  ck_exchange_send(ck_handle* h, uint64_t step);
+int  ck_recv_info(ck_handle* h, void** dev_recv, uint64_t* region_stride, uint32_t* max_fwd, uint64_t* data_cap);
+int  ck_fetch_received(ck_handle* h, uint32_t src, uint64_t* hdr4, uint8_t* host_meta, uint8_t* host_data, uint64_t data_cap);
 /* multi-GPU exchange planning (records shard by Kafka partition across the GPUs of a box; reference analogue:
  * producing to a topic-partition another worker process consumes, nodes/base.py:82-87 key=correlation_id).  Selects the
  * keyed publishes whose partition % world != rank, ordered by destination rank (stable), into library-owned device
