@@ -566,7 +566,7 @@ def main() -> None:
     in_bytes = int(batch.data.nbytes)
     topics = ["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"]
     import ctypes as C
-    from calfkit.engine.exchange import exchange as run_exchange, plan_exchange_device
+    from calfkit.engine.exchange import PeerExchange
     launches = [0]
 
     all_lanes = []
@@ -588,9 +588,16 @@ def main() -> None:
             self.t_out_len = torch.as_tensor(CudaArray(p_len.value, (n,), "<i4"), device=dev)
             self.out_cap = eng.max_out
             self.t_out = torch.as_tensor(CudaArray(bufs["out"], (self.out_cap,), "|u1"), device=dev)
+            self.px, self.step_no = None, 0
             if world > 1:
-                self.send_buf = torch.empty(int(self.out_cap * min(1.0, args.cross * 2 + 0.05)) + (1 << 20), dtype=torch.uint8, device=dev)
-                self.recv_buf = torch.empty_like(self.send_buf)
+                # receive regions for what the other ranks forward here: one per source, sized for 2 x the expected share
+                fwd = int(n * min(1.0, args.cross * 2 + 0.05) / (world - 1)) + 1024
+                self.px = PeerExchange(eng, rank, world, max_fwd=fwd, data_cap=fwd * (int(in_bytes / n) + 64))
+                rp, rs, rmf, rdc = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint64()
+                eng.lib.ck_recv_info(eng.h, C.byref(rp), C.byref(rs), C.byref(rmf), C.byref(rdc))
+                self.region_stride, self.region_hdr = rs.value, 64 + 16 * rmf.value
+                self.t_recv = torch.as_tensor(CudaArray(rp.value, (world * rs.value,), "|u1"), device=dev)
+                self.h_recv = torch.empty(world * rs.value, dtype=torch.uint8).pin_memory()
             self.h_out = torch.empty(self.out_cap, dtype=torch.uint8).pin_memory()
             self.h_out_np = self.h_out.numpy()
             # pinned landing buffers for the offsets / lengths / publish table as well
@@ -601,22 +608,15 @@ def main() -> None:
             self.rbytes = 0
 
         def close(self):
-            self.t_pubs = self.t_out_off = self.t_out_len = self.t_out = self.stream = None
+            self.t_pubs = self.t_out_off = self.t_out_len = self.t_out = self.stream = self.t_recv = None
             self.eng.close()
 
-        def gather(self, plan, buf):
-            eng = self.eng
-            eng._check(eng.lib.ck_gather_spans(eng.h, self.t_out.data_ptr(), plan.src_off.data_ptr(), plan.lens.data_ptr(),
-                                               int(plan.sel.numel()), buf.data_ptr(), plan.dst_off.data_ptr()))
-            launches[0] += 1
-
         def exchange(self):
-            """forward keyed payloads whose partition is owned by another GPU: one variable-size all-to-all"""
+            """forward keyed payloads whose partition is owned by another GPU: the library's kernels plan, pack and store
+            them straight into the owners' receive regions over NVLink (no host synchronisation); two 4-byte barriers"""
+            self.step_no += 1
             with torch.cuda.stream(self.stream):
-                nrecv, rbytes, _ = run_exchange(plan_exchange_device(self.eng, rank, world, dev), self.gather, self.send_buf, self.recv_buf)
-            launches[0] += 8            # exchange plan: count, 3 x scan, scatter, 3 x scan
-            self.rbytes = rbytes
-            return nrecv, rbytes
+                self.px.send(self.step_no)
 
         def enqueue_device(self, d_in, d_off):
             self.eng.submit_device(d_in, d_off, n)
@@ -628,13 +628,22 @@ def main() -> None:
             self.eng.tool_plan()
 
         def exchange_host(self):
-            """N > 1: forward foreign-partition payloads and land what this rank received in pinned memory.
-            Called after the other lane's D2H so that its host-side wait does not stall the copy pipeline."""
+            """N > 1: forward foreign-partition payloads and land what this rank received in pinned memory (headers first: they
+            say how many bytes each source sent).  Called after the other lane's D2H so that the wait does not stall the copies."""
             if world > 1:
                 self.exchange()
-                if self.rbytes:
-                    with torch.cuda.stream(self.stream):
-                        self.h_out[self.out_cap - self.rbytes:].copy_(self.recv_buf[:self.rbytes], non_blocking=True)
+                with torch.cuda.stream(self.stream):
+                    hdrs = self.t_recv.view(world, self.region_stride)[:, :32].contiguous().cpu().view(torch.int64)    # waits for the closing barrier
+                    self.rbytes = 0
+                    for s_ in range(world):
+                        if s_ == rank:
+                            continue
+                        if int(hdrs[s_, 1]) >> 32:
+                            raise RuntimeError("exchange region overflow: raise max_fwd / data_cap")
+                        nbytes = self.region_hdr + int(hdrs[s_, 2])
+                        a = s_ * self.region_stride
+                        self.h_recv[a:a + nbytes].copy_(self.t_recv[a:a + nbytes], non_blocking=True)
+                        self.rbytes += nbytes
 
         def fetch_host(self):
             out, off, ln, pubs = self.eng._fetch(out_buf=self.h_out_np, off_buf=self.h_off, len_buf=self.h_len,
@@ -752,6 +761,34 @@ def main() -> None:
     e2e_ms = float(t[0].item()) / e2e_steps
     e2e_value = world * n / (e2e_ms / 1e3)
     d2h_bytes = [lanes[0].d2h]
+
+    # ---- N > 1: the bytes each rank RECEIVED against what their senders planned (outside all timed regions) ---------------
+    x_parity = None
+    if world > 1:
+        ln0 = lanes[0]
+        ln0.eng.submit(h_in_np, h_off_np)
+        ln0.eng.tool_plan()
+        ln0.step_no += 1
+        with torch.cuda.stream(ln0.stream):
+            ln0.px.send(ln0.step_no)
+        recv = ln0.px.received(ln0.step_no)
+        out_b, off_b, len_b, pubs_b = ln0.eng._fetch()
+        keyed = (pubs_b["payload"] != 0xFFFFFFFF) & (pubs_b["has_key"] == 1)
+        mine = {}
+        for d_ in range(world):
+            if d_ != rank:
+                idx_ = np.nonzero(keyed & (pubs_b["partition"] % world == d_))[0]
+                mine[d_] = (len(idx_), [out_b[off_b[p_]:off_b[p_] + len_b[p_]].tobytes() for p_ in pubs_b["payload"][idx_[:64]]])
+        allm = [None] * world
+        dist.all_gather_object(allm, mine)
+        okx = True
+        for src_, meta_, data_ in recv:
+            cnt_, first_ = allm[src_][rank]
+            okx = okx and cnt_ == len(meta_) and PeerExchange.payloads(meta_[:64], data_) == first_ \
+                and bool(((meta_["partition"] % world) == rank).all())
+        tx = torch.tensor([1 if okx else 0], device=dev)
+        dist.all_reduce(tx, op=dist.ReduceOp.MIN)
+        x_parity = bool(tx.item())
 
     # ---- end to end through the product API: Worker.run() over a batch-native broker -----------------------------------
     # the same pinned batch is produced `w_steps` times to the node's input topic; Worker.run polls it as arenas, drives its
@@ -880,7 +917,8 @@ def main() -> None:
         "data": "synthetic",
         "config": bench_config(args, world),
         "workload_stats": {"record_bytes_mean": in_bytes / n, "out_bytes_mean": out_payload_bytes / max(npay, 1), "publishes_per_event": 2,
-                           "accepted_fraction": ok_frac, "parity_spot_check_256": parity_ok, "in_gb_per_step": in_bytes / 1e9},
+                           "accepted_fraction": ok_frac, "parity_spot_check_256": parity_ok, "in_gb_per_step": in_bytes / 1e9,
+                           "exchange_parity": x_parity},
         "clocks": sampler.summary(),
         "e2e": {"value": w_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": w_d2h,
                 "ms_per_step": w_ms, "steps": w_steps, "gpu_launches": w_launches, "all_publishes_seen_by_sinks": w_ok,

@@ -119,12 +119,15 @@ class PeerExchange:
         handles = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
         engine._check(engine.lib.ck_comm_connect(engine.h, handles.ctypes.data))
         self._token = torch.zeros(1, dtype=torch.int32, device=mine.device)
+        # the barriers must be ordered with the engine's kernels: they are issued with the engine's stream current
+        self._stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=mine.device)
         dist.barrier(group=group)
         _ = C
 
     def barrier(self) -> None:
-        """4-byte all-reduce on the current stream: a device-side barrier, the host does not wait"""
-        dist.all_reduce(self._token, group=self.group)
+        """4-byte all-reduce ordered on the engine's stream: a device-side barrier, the host does not wait"""
+        with torch.cuda.stream(self._stream):
+            dist.all_reduce(self._token, group=self.group)
 
     def send(self, step: int) -> None:
         """forward the foreign-partition payloads of the engine's current plan.  Stream-ordered, asynchronous:

@@ -432,7 +432,7 @@ extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const u
     puts("{\"target_topic\":\"" + cb + "\",\"callback_topic\":\"", c.lit_tc_head);
     puts("\",\"input_args\":null,\"frame_id\":\"", c.lit_tc_mid);
     c.self_topic_id = -1;
-    std::vector<u32> tab(5 * (size_t)ntools);
+    std::vector<u32> tab(6 * (size_t)ntools);
     for (u32 k = 0; k < ntools; k++) {
         std::string nm((const char*)tool_names + tool_name_off[k], tool_name_off[k + 1] - tool_name_off[k]);
         std::string tp((const char*)tool_topics + tool_topic_off[k], tool_topic_off[k + 1] - tool_topic_off[k]);
@@ -443,6 +443,7 @@ extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const u
         // registered id of the tool's topic, if any (host-side probe of the same table the device uses is
         // not needed: ids are resolved by the route kernel when this is 0xffffffff)
         tab[4 * ntools + k] = 0xffffffffu;
+        { u32 hh = 2166136261u ^ (u32)nm.size(); for (unsigned char ch : nm) hh = (hh ^ ch) * 16777619u; tab[5 * ntools + k] = hh; }   // = ck_hash_span of the name
     }
     if (pool.size() > CK_LIT_CAP) return fail(h, "ck_set_agent_node: literal pool overflow");
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -498,7 +499,8 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     u32 n = h->n;
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) CKL(h) ck_fanout_count_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, max_fanout, sequential, h->d_counts);
+        if (n) CKL(h) ck_fanout2_count_kernel<<<(n + CK_F2_WARPS - 1) / CK_F2_WARPS, 32 * CK_F2_WARPS, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg,
+                                                                                                             max_fanout, sequential, h->d_counts);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (run_scan(h, h->d_counts, n, h->d_slot_base, 0)) return 1;
@@ -509,8 +511,8 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
     if (slots > h->max_payloads) return fail(h, "ck_fanout_plan: more payloads than max_payloads");
     {
         KTimer t(h, CK_K_FANOUT);
-        if (n) CKL(h) ck_fanout_plan_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
-            h->d_slot_base, unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
+        if (n) CKL(h) ck_fanout2_plan_kernel<<<(n + CK_F2_WARPS - 1) / CK_F2_WARPS, 32 * CK_F2_WARPS, 0, h->stream>>>(view_of(h), n, h->d_cols, n, h->d_agent_cfg, h->d_lit,
+            h->d_agent_tables + 5 * (size_t)h->h_agent_cfg.ntools, h->d_slot_base, unix_ms, seed, h->d_aux, h->d_glue, h->d_descs, h->d_pay_len, h->d_pubs);
         CUDA_TRY(h, cudaGetLastError());
     }
     if (scan_emit(h, (u32)slots, h->d_aux)) return 1;

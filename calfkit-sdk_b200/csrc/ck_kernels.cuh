@@ -520,114 +520,7 @@ __device__ __forceinline__ void SegWriter::hex_uuid7(unsigned long long unix_ms,
     total += 32;
 }
 
-// pass 1: how many payloads does each record produce (pending + 1 for the handler return)
-__global__ void __launch_bounds__(128)
-ck_fanout_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
-                       const ck_agent_cfg* __restrict__ cfgp, u32 max_fanout, u32 sequential, u32* __restrict__ counts) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-#define COL(k) cols[(size_t)(k) * stride + i]
-    counts[i] = 0;
-    COL(CK_COL_NOUT) = 0;
-    if (COL(CK_COL_STATUS) != CK_OK) { COL(CK_COL_ACTION) = CK_ACT_NONE; return; }
-    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
-    Rd r; r.init(rec, rlen);
-    if (COL(CK_COL_NFRAMES) == 0) { COL(CK_COL_ACTION) = CK_ACT_RAISES; return; }
-    u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF);
-    u32 pos = tc + 1, pending = 0;
-    while (pos < r.n && r.at(pos) != '}') {
-        Span k; ck_string(r, pos, k); pos++;
-        ck_skip_value(r, pos);
-        if (ck_dict_find(r, tr, k.off, k.len).len == 0) pending++;
-        if (pos < r.n && r.at(pos) == ',') pos++;
-    }
-    // sequential_only_mode (agent.py:94-108,179-192): only the first pending call goes out, as a single Call
-    if (sequential && pending > 1) pending = 1;
-    if (pending == 0 || pending > max_fanout) { COL(CK_COL_ACTION) = CK_ACT_RAISES; COL(CK_COL_STATUS) = CK_UNSUPPORTED; return; }
-    u32 extra = (cfgp->publish_topic_id >= 0 && pending > 1) ? 1u : 0u;   // list[Call]: the input envelope is the return value
-    counts[i] = pending + extra;
-    COL(CK_COL_ACTION) = pending == 1 ? CK_ACT_CALL : CK_ACT_FANOUT;
-    COL(CK_COL_NOUT) = pending + ((cfgp->publish_topic_id >= 0) ? 1u : 0u);
-#undef COL
-}
-
-// pass 2: descriptors.  slot_base = exclusive scan of counts (payload slots), one publish per payload
-// except a single Call whose payload is published twice (target + publish_topic): pubs are sized 2/slot.
-__global__ void __launch_bounds__(128)
-ck_fanout_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride,
-                      const ck_agent_cfg* __restrict__ cfgp, const u8* __restrict__ lit, const long long* __restrict__ slot_base,
-                      unsigned long long unix_ms, unsigned long long seed, const u8* __restrict__ aux, u8* __restrict__ glue,
-                      ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-#define COL(k) cols[(size_t)(k) * stride + i]
-    u32 action = COL(CK_COL_ACTION);
-    if (COL(CK_COL_STATUS) != CK_OK || (action != CK_ACT_CALL && action != CK_ACT_FANOUT)) return;
-    const ck_agent_cfg& cfg = *cfgp;
-    u32 rlen; const u8* rec = ck_rec(v, i, rlen);
-    Rd r; r.init(rec, rlen);
-    u32 slot = (u32)slot_base[i];
-    u32 tc = COL(CK_COL_TC_OFF), tr = COL(CK_COL_TR_OFF);
-    u32 frames_off = COL(CK_COL_FRAMES_OFF), frames_len = COL(CK_COL_FRAMES_LEN), nframes = COL(CK_COL_NFRAMES);
-    u32 fov_off = COL(CK_COL_FOV_OFF), fov_len = COL(CK_COL_FOV_LEN), sov_off = COL(CK_COL_SOV_OFF), sov_len = COL(CK_COL_SOV_LEN);
-    bool ov = r.at(fov_off) != 'n';
-    u32 list_end = frames_off + frames_len - 1;            // position of the closing ']'
-    ck_pub none; none.payload = 0xffffffffu; none.topic_id = -1; none.topic_off = none.topic_len = 0; none.record = i;
-    none.has_key = 0; none.partition = -1; none.pad = 0;
-    u32 pos = tc + 1, j = 0;
-    bool bad = false;
-    while (pos < r.n && r.at(pos) != '}') {
-        Span k; ck_string(r, pos, k); pos++;
-        u32 v = pos;
-        ck_skip_value(r, pos);
-        if (ck_dict_find(r, tr, k.off, k.len).len == 0) {
-            // tool_name of this ToolCallPart -> registry
-            u32 p2 = v + 13; Span tn; ck_string(r, p2, tn);
-            u32 tool = 0xffffffffu;
-            for (u32 t = 0; t < cfg.ntools; t++) {
-                if (cfg.tool_name_len[t] != tn.len) continue;
-                bool eq = true;
-                for (u32 b = 0; b < tn.len; b++) if (lit[cfg.tool_name_off[t] + b] != r.at(tn.off + b)) { eq = false; break; }
-                if (eq) { tool = t; break; }
-            }
-            u32 s = slot + j;
-            ck_out_desc* d = descs + s;
-            SegWriter w; w.init(d, &r, lit, aux, glue + (size_t)s * CK_GLUE_STRIDE);
-            if (tool == 0xffffffffu) { bad = true; w.finish(i); pay_len[s] = 0; pubs[2 * s] = none; pubs[2 * s + 1] = none; j++; }
-            else {
-                u32 cur = 0;
-                if (ov) { w.add(CK_SRC_INPUT, 0, sov_off); w.add(CK_SRC_INPUT, fov_off, fov_len); cur = sov_off + sov_len; }
-                w.add(CK_SRC_INPUT, cur, list_end - cur);
-                if (nframes > 0) w.add(CK_SRC_LIT, cfg.lit_comma[0], cfg.lit_comma[1]);
-                w.add(CK_SRC_LIT, cfg.tool_lit_off[tool], cfg.tool_lit_len[tool]);
-                w.add(CK_SRC_INPUT, k.off, k.len);                       // tool_call_id (raw JSON string content)
-                w.add(CK_SRC_LIT, cfg.lit_mid[0], cfg.lit_mid[1]);
-                w.hex_uuid7(unix_ms, seed, (unsigned long long)s);
-                w.add(CK_SRC_LIT, cfg.lit_tail[0], cfg.lit_tail[1]);
-                w.add(CK_SRC_INPUT, list_end, r.n - list_end);
-                w.finish(i);
-                pay_len[s] = w.total;
-                ck_pub p = none; p.payload = s; p.topic_id = (int32_t)cfg.tool_topic_id[tool]; p.has_key = 1;
-                pubs[2 * s] = p; pubs[2 * s + 1] = none;
-                if (action == CK_ACT_CALL && cfg.publish_topic_id >= 0) { ck_pub q = none; q.payload = s; q.topic_id = cfg.publish_topic_id; pubs[2 * s + 1] = q; }
-                j++;
-            }
-        }
-        if (action == CK_ACT_CALL && j) break;                           // single Call: first pending only
-        if (pos < r.n && r.at(pos) == ',') pos++;
-    }
-    if (action == CK_ACT_FANOUT && cfg.publish_topic_id >= 0) {
-        // handler return value of the list[Call] branch: the original envelope (nodes/base.py:88)
-        u32 s = slot + j;
-        SegWriter w; w.init(descs + s, &r, lit, aux, glue + (size_t)s * CK_GLUE_STRIDE);
-        w.add(CK_SRC_INPUT, 0, r.n); w.finish(i);
-        pay_len[s] = r.n;
-        ck_pub q = none; q.payload = s; q.topic_id = cfg.publish_topic_id; pubs[2 * s] = q; pubs[2 * s + 1] = none;
-    }
-    if (bad) { COL(CK_COL_STATUS) = CK_UNSUPPORTED; }
-#undef COL
-}
-
+// (the count / plan kernels of the fan-out are in ck_fanout2.cuh: one warp per record)
 
 // TailCall to self (reference nodes/agent.py:171-175 -> nodes/base.py:120-136): the current frame is
 // replaced by {target_topic: self.subscribe_topics[0], callback_topic: <popped frame's callback>,
@@ -1028,6 +921,7 @@ ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
 }
 
 #include "ck_plan2.cuh"
+#include "ck_fanout2.cuh"
 #include "ck_gate.cuh"
 #include "ck_kafka.cuh"
 #include "ck_group.cuh"
