@@ -340,6 +340,25 @@ def run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -
     kern = {k: {"ms_per_launch": ms / c, "launches": c} for k, (ms, c) in prof.items() if c}
     emit_ms = kern["emit"]["ms_per_launch"]
     algo_emit = in_bytes + payload_bytes            # every input byte read at least once + every payload byte written
+    # parity spot check (byte-exact, outside the timed regions): the first events' F Call envelopes + handler return vs the oracle
+    from oracle import port
+    from calfkit import _ids
+    from calfkit.engine.batch import device_uuid7_hex
+    small = synth.pack(recs[:4])
+    eng.submit(small.data, small.offsets)
+    eng.fanout_plan(ms0, 99, max_fanout=256)
+    chk = list(eng.fetch().publishes())
+    parity_ok, kk, slot = True, 0, 0
+    for rec in recs[:4]:
+        it = iter([device_uuid7_hex(ms0, 99, slot + j) for j in range(F)])
+        _ids.set_id_source(lambda: next(it))
+        try:
+            want = port.agent_fanout("planner", "planner.input", "planner.output", registry, rec)
+        finally:
+            _ids.set_id_source(None)
+        parity_ok = parity_ok and [(p.topic, p.key, p.payload) for p in chk[kk:kk + len(want)]] == [(t, k2, pl) for (t, k2, _c, pl) in want]
+        kk += len(want)
+        slot += F + 1
     cores = os.cpu_count() or 1
     sample = recs[: max(cores * 2, 64)]
     if all_cpus:
@@ -355,15 +374,18 @@ def run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"fanout: 1 Agent node -> {F} @agent_tool nodes (BASELINE.json configs[2]), post-LLM agent-stage envelopes",
-                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "payloads_per_event": npay / n,
-                   "out_bytes_per_event": payload_bytes / n, "l2": "outputs (%.1f GB/step) far larger than L2" % (payload_bytes / 1e9)},
+        "config": dict(bench_config(args, world), fanout=F, events_per_gpu_per_step=n),
+        "workload_stats": {"record_bytes_mean": in_bytes / n, "payloads_per_event": npay / n, "out_bytes_per_event": payload_bytes / n,
+                           "out_gb_per_step": payload_bytes / 1e9, "parity_spot_check_4_events": parity_ok},
         "clocks": sampler.summary(),
         "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "BatchEngine.submit(pinned host) + fanout_plan + fetch(pinned host)"},
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "ck_emit_kernel", "bound": "hbm", "achieved": algo_emit / emit_ms / 1e6, "peak": peak, "unit": "GB/s",
-                     "frac": algo_emit / emit_ms / 1e6 / peak, "traffic": None, "share_of_step": emit_ms / ms_step, "kernels": kern},
+                     "frac": algo_emit / emit_ms / 1e6 / peak, "traffic": None, "share_of_step": emit_ms / ms_step, "kernels": kern,
+                     "dominant_by_time": max(kern, key=lambda k_: kern[k_]["ms_per_launch"] * (2 if k_ == "fanout" else 1)),
+                     "pipeline": {"algo_bytes_per_event": (in_bytes + payload_bytes) / n, "achieved": (in_bytes + payload_bytes) / ms_step / 1e6,
+                                  "frac": (in_bytes + payload_bytes) / ms_step / 1e6 / peak}},
         "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} events in {cpu_dt:.1f} s over {min(cores, len(sample))} processes (oracle/port.py agent_fanout)"},
     }
@@ -488,11 +510,9 @@ def run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) ->
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "reply: client-side projection of final reply envelopes to NodeResult.output (SURVEY 8f row 3; "
-                               "reference client/deserialize.py:15-89), auto output type",
-                   "events_per_gpu_per_step": n, "record_bytes_mean": in_bytes / n, "out_bytes_per_event": out_bytes / n,
-                   "ok_fraction": float((cols[_COL["STATUS"]] == 0).mean()), "parity_vs_oracle_256": ok,
-                   "l2": "inputs (%.2f GB/step) larger than L2" % (in_bytes / 1e9)},
+        "config": bench_config(args, world),
+        "workload_stats": {"record_bytes_mean": in_bytes / n, "out_bytes_per_event": out_bytes / n,
+                           "ok_fraction": float((cols[_COL["STATUS"]] == 0).mean()), "parity_vs_oracle_256": ok, "in_gb_per_step": in_bytes / 1e9},
         "clocks": sampler.summary(),
         "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "BatchEngine.submit(pinned host) + reply_plan + fetch(pinned host)"},
@@ -501,6 +521,128 @@ def run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) ->
                      "frac": algo_walk / walk_ms / 1e6 / peak, "traffic": None, "share_of_step": walk_ms / ms_step, "kernels": kern},
         "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} replies in {cpu_dt:.1f} s over {cores} processes (oracle/port.py reply_output)"},
+    }
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    torch.cuda.synchronize()
+    del stream
+    eng.close()
+    teardown(world)
+
+
+def _cpu_mixed_worker(chunk):
+    return _cpu_worker(chunk)
+
+
+def run_mixed(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) -> None:
+    """BASELINE.json configs[4]: mixed-size event stream (128 B - 64 KB JSON: multi-turn histories with escapes and multi-byte
+    UTF-8), callbacks spread over 256 subscribe_topics; the tool-node path (decode -> run -> publish plan -> encode -> route)."""
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from calfkit import synth
+    from calfkit.engine import BatchEngine, ToolTemplate
+    n = args.events if args.events != 1_000_000 else 65536
+    base = synth.mixed_events(4096, seed=5000 + rank, hi=65536, n_agents=256)
+    recs = [base[i % len(base)] for i in range(n)]
+    batch = synth.pack(recs)
+    in_bytes = int(batch.data.nbytes)
+    topics = [f"agent_{k:03d}.input" for k in range(256)] + ["tool.get_weather.input", "tool.get_weather.output"]
+    eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096)
+    eng.register_topics(topics, num_partitions=NUM_PARTITIONS)
+    eng.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))
+    d_in = torch.from_numpy(batch.data.copy()).to(dev)
+    d_off = torch.from_numpy(batch.offsets.copy()).to(dev)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+
+    def step():
+        eng.submit_device(d_in, d_off, n)
+        eng.tool_plan()
+
+    for _ in range(args.warmup):
+        step()
+    eng.sync()
+    eng.profile(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    gpu_launches = eng.launch_count() - l0
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    prof = eng.profile_read()
+    eng.profile(False)
+    out_bytes, npay, npub = eng.out_size()
+    value = world * n / (ms_step / 1e3)
+    from calfkit.engine.lane import Arena, LanePipeline
+    pipe = LanePipeline(local_rank, lambda e_: (e_.register_topics(topics, num_partitions=NUM_PARTITIONS),
+                                                e_.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))),
+                        lanes=3, max_records=n, max_in_bytes=in_bytes + 4096)
+    h_in = torch.from_numpy(batch.data.copy()).pin_memory()
+    h_off = torch.from_numpy(batch.offsets.copy()).pin_memory()
+    arena = Arena(h_in.numpy(), h_off.numpy())
+    d2h, e2e_steps = 0, 8
+    for k in range(3 + e2e_steps):
+        if k == 3:
+            for pb in pipe.drain():
+                pb.release()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        pb = pipe.push(arena)
+        if pb is not None:
+            pb.release()
+    for pb in pipe.drain():
+        d2h = max(d2h, max(l_.d2h_bytes for l_ in pipe.lanes))
+        pb.release()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    pipe.close()
+    cols = eng.columns()
+    peak, _peak_src = hbm_peak_gbs()
+    kern = {k: {"ms_per_launch": ms / c, "launches": c} for k, (ms, c) in prof.items() if c}
+    walk_ms = kern["walk"]["ms_per_launch"]
+    from calfkit.engine._lib import COL as _COL, NUM_COLS as _NC
+    algo_walk = in_bytes + 8 * (n + 1) + 4 * (_NC - 10) * n
+    from oracle import port
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tools_def
+    small = synth.pack(recs[:128])
+    chk = eng.run_tool_batch(small.data, small.offsets)
+    node = port.ToolNode.of(tools_def.get_weather)
+    parity_ok = [(p.topic, p.key, p.payload) for p in chk.publishes()] == \
+        [(tp, k, pl) for r in recs[:128] for (tp, k, _c, pl) in port.tool_node_event(node, r)]
+    cores = os.cpu_count() or 1
+    sample = recs[: max(cores * 16, 256)]
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)
+    rpool = ReferencePool(cores)
+    rpool.run(sample[: max(cores, 16)])
+    cpu_value, cpu_dt, cpu_n = rpool.run(sample)
+    cpu_kind, cpu_desc = rpool.kind, rpool.describe()
+    rpool.close()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": dict(bench_config(args, world), events_per_gpu_per_step=n, topics=len(topics)),
+        "workload_stats": {"record_bytes_mean": in_bytes / n, "record_bytes_max": int(np.diff(batch.offsets).max()), "in_gb_per_step": in_bytes / 1e9,
+                           "input_gbs": in_bytes / ms_step / 1e6, "ok_fraction": float((cols[_COL["STATUS"]] == 0).mean()),
+                           "parity_spot_check_128": parity_ok, "out_bytes_per_event": out_bytes / n},
+        "clocks": sampler.summary(),
+        "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "calfkit.engine.lane.LanePipeline.push(pinned Arena) -> PublishBatch (3 lanes)"},
+        "gpu_launches": gpu_launches,
+        "roofline": {"kernel": "ck_walk_kernel", "bound": "hbm", "achieved": algo_walk / walk_ms / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": algo_walk / walk_ms / 1e6 / peak, "traffic": None, "share_of_step": walk_ms / ms_step, "kernels": kern,
+                     "pipeline": {"algo_bytes_per_event": (in_bytes + out_bytes) / n, "achieved": (in_bytes + out_bytes) / ms_step / 1e6,
+                                  "frac": (in_bytes + out_bytes) / ms_step / 1e6 / peak}},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": cpu_kind,
+                         "sample": f"{cpu_n} events of the same batch in {cpu_dt:.1f} s over {cores} processes; " + cpu_desc},
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -520,7 +662,7 @@ def main() -> None:
     ap.add_argument("--events", type=int, default=1_000_000, help="events per GPU per step (config 2: 1M)")
     ap.add_argument("--cross", type=float, default=0.125, help="fraction of records on a foreign partition (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="events for the cpu_baseline leg (0 = auto)")
-    ap.add_argument("--workload", default="tool_event_1k", choices=["tool_event_1k", "fanout", "reply"],
+    ap.add_argument("--workload", default="tool_event_1k", choices=["tool_event_1k", "fanout", "reply", "mixed"],
                     help="tool_event_1k = BASELINE.json configs[1] (the headline); fanout = configs[2]: 1 Agent -> 64 tools")
     ap.add_argument("--fanout", type=int, default=64)
     args = ap.parse_args()
@@ -551,13 +693,18 @@ def main() -> None:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner / logs must not land on stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True          # the per-step barriers must not queue behind the big kernels
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     if args.workload == "fanout":
         run_fanout(args, rank, world, local_rank, dev, real_stdout, all_cpus)
         return
     if args.workload == "reply":
         run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus)
+        return
+    if args.workload == "mixed":
+        run_mixed(args, rank, world, local_rank, dev, real_stdout, all_cpus)
         return
     n = args.events
     recs = synth.tool_events(n, seed=1000 + rank)
@@ -608,7 +755,15 @@ def main() -> None:
             self.rbytes = 0
 
         def close(self):
-            self.t_pubs = self.t_out_off = self.t_out_len = self.t_out = self.stream = self.t_recv = None
+            # every torch object that touched this engine's stream goes first (the caching allocators record an event on a
+            # tensor's streams when it is freed: the stream must still exist), then the engine (stream + HBM buffers)
+            import gc
+            self.t_pubs = self.t_out_off = self.t_out_len = self.t_out = self.t_recv = self.h_recv = None
+            self.h_out = self.h_out_np = self.h_off = self.h_len = self.h_pubs = None
+            self.px = None
+            gc.collect()
+            torch.cuda.synchronize()
+            self.stream = None
             self.eng.close()
 
         def exchange(self):

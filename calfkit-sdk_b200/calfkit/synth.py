@@ -107,10 +107,11 @@ def pack(records: list[bytes]) -> Batch:
 
 def tool_events(n: int, seed: int = 0, *, size: int | None = 1152, jitter: int = 16, full_history: bool = False,
                 tool_name: str = "get_weather", agent_topic: str = "weather_agent.input",
-                agent_name: str = "weather_agent", n_tools: int = 1, compact: bool | None = None) -> list[bytes]:
+                agent_name: str = "weather_agent", n_tools: int = 1, compact: bool | None = None, n_agents: int = 1) -> list[bytes]:
     """config-2 records.  `size`=None leaves records unpadded; otherwise provided_deps carries a
     pad string so that len(record) = size + U[-jitter, +jitter] (clamped to the unpadded size).
-    With n_tools > 1 records are spread over tools tool_00..tool_{n-1} (config 5 routing)."""
+    With n_tools > 1 records are spread over tools tool_00..tool_{n-1}; with n_agents > 1 their callback topics are spread
+    over agent_000.input .. (config 5 routing: the route step resolves among that many destination topics)."""
     if compact is None:
         compact = size is not None and size <= 1200   # short ids: smallest valid record ~1130 B
     rng = np.random.default_rng(seed)
@@ -122,11 +123,14 @@ def tool_events(n: int, seed: int = 0, *, size: int | None = 1152, jitter: int =
     city_i = rng.integers(0, len(CITIES), size=n)
     prompt_i = rng.integers(0, 2 if compact else len(PROMPT_BITS), size=n)
     tool_i = rng.integers(0, n_tools, size=n)
+    agent_i = rng.integers(0, n_agents, size=n) if n_agents > 1 else None
+    agent_topic0 = agent_topic
     jit = rng.integers(-jitter, jitter + 1, size=n) if jitter else np.zeros(n, dtype=np.int64)
     out: list[bytes] = []
     for i in range(n):
         city = CITIES[city_i[i]]
         tname = tool_name if n_tools == 1 else f"tool_{int(tool_i[i]):02d}"
+        agent_topic = agent_topic0 if agent_i is None else f"agent_{int(agent_i[i]):03d}.input"
         # OpenAI-style short ids in the 1 KB class, pydantic-ai generated ids otherwise
         call_id = ("call_" + tcid[i][:12]) if compact else ("pyd_ai_" + tcid[i])
         args = '{"location":' + jstr(city) + '}'
@@ -177,12 +181,12 @@ def fanout_events(n: int, seed: int = 0, *, fanout: int = 64, agent_topic: str =
     return out
 
 
-def mixed_events(n: int, seed: int = 0, *, lo: int = 128, hi: int = 65536, n_tools: int = 256) -> list[bytes]:
+def mixed_events(n: int, seed: int = 0, *, lo: int = 128, hi: int = 65536, n_tools: int = 256, n_agents: int = 1) -> list[bytes]:
     """config-5 records: log-uniform sizes; long records get long multi-turn histories with
     escapes and multi-byte UTF-8, short ones are stripped to the minimum envelope."""
     rng = np.random.default_rng(seed)
     sizes = np.exp(rng.uniform(np.log(lo), np.log(hi), size=n)).astype(np.int64)
-    base = tool_events(n, seed + 1, size=None, n_tools=n_tools)
+    base = tool_events(n, seed + 1, size=None, n_tools=n_tools, n_agents=n_agents)
     out: list[bytes] = []
     filler = "The quick brown fox — «jumps» over\tthe lazy dog.\n\"quoted\" back\\slash ünïcödé 漢字 🙂 "
     for i in range(n):

@@ -19,6 +19,7 @@ static thread_local std::string g_create_error;
 struct ck_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t xstream = nullptr; cudaEvent_t x_ev0 = nullptr, x_ev1 = nullptr;   // high-priority side stream of the exchange
     std::string err;
     uint64_t max_in = 0, max_out = 0, max_aux = 0;
     uint32_t max_records = 0, max_payloads = 0, max_pubs = 0;
@@ -177,6 +178,9 @@ extern "C" void ck_destroy(ck_handle* h) {
     if (h->h_grand) cudaFreeHost(h->h_grand);
     if (h->h_x) cudaFreeHost(h->h_x);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->xstream) { cudaStreamSynchronize(h->xstream); cudaStreamDestroy(h->xstream); }
+    if (h->x_ev0) cudaEventDestroy(h->x_ev0);
+    if (h->x_ev1) cudaEventDestroy(h->x_ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -814,6 +818,13 @@ extern "C" int ck_comm_create(ck_handle* h, uint32_t rank, uint32_t world, uint3
     cudaIpcMemHandle_t ih;
     CUDA_TRY(h, cudaIpcGetMemHandle(&ih, h->d_recv));
     memcpy(ipc_handle_out, &ih, 64);
+    // the exchange is a dozen small dependent kernels: on a highest-priority stream their blocks are scheduled as soon as
+    // any SM slot frees up instead of queueing behind the other lane's million-record kernels
+    int lo = 0, hi = 0;
+    CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(h, cudaStreamCreateWithPriority(&h->xstream, cudaStreamNonBlocking, hi));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->x_ev0, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->x_ev1, cudaEventDisableTiming));
     return 0;
 }
 
@@ -835,10 +846,25 @@ extern "C" int ck_comm_connect(ck_handle* h, const uint8_t* handles) {
 // plan + pack + transfer of the keyed publishes of the current plan whose partition another rank owns: queued on the
 // handle's stream, no host synchronisation.  The caller brackets it with two barriers (peers consumed the previous
 // contents / every peer's stores have landed).
+static int exchange_send_on_stream(ck_handle* h, uint64_t step);
 extern "C" int ck_exchange_send(ck_handle* h, uint64_t step) {
     cudaSetDevice(h->device);
     if (!h->comm_ready) return fail(h, "ck_exchange_send: call ck_comm_create / ck_comm_connect first");
     if (x_alloc(h)) return 1;
+    // fork: everything below runs on the high-priority side stream, after what is queued on the handle's stream so far
+    CUDA_TRY(h, cudaEventRecord(h->x_ev0, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->xstream, h->x_ev0, 0));
+    cudaStream_t main_stream = h->stream;
+    h->stream = h->xstream;
+    int rc = exchange_send_on_stream(h, step);
+    h->stream = main_stream;
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->x_ev1, h->xstream));                  // join
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->x_ev1, 0));
+    return 0;
+}
+
+static int exchange_send_on_stream(ck_handle* h, uint64_t step) {
     u32 rank = h->comm_rank, world = h->comm_world, npubs = h->n_pubs;
     u32 nb = (npubs + CK_X_BLOCK - 1) / CK_X_BLOCK;
     if (!nb) nb = 1;

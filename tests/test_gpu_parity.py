@@ -486,3 +486,97 @@ def test_long_floats_on_device(engine):
     assert (out.cols[0] == 0).all(), np.bincount(out.cols[0])
     want = [(tp, k, pl) for r in recs for (tp, k, _c, pl) in port.tool_node_event(node, r)]
     assert _pubs(out) == want
+
+
+def test_fanout_64_matches_oracle_config3(engine):
+    """BASELINE.json configs[2]: 1 Agent node -> 64 @agent_tool nodes.  Every one of the 64 Call envelopes of every event
+    (and the handler-return publish) byte-exact against the oracle, ids injected from the device generator; plus records with
+    some results already present (partial fan-out) and one whose tool the registry does not know."""
+    from oracle import port
+    from calfkit import _ids, synth
+    from calfkit.engine.batch import device_uuid7_hex
+    from calfkit.engine import BatchEngine
+    F = 64
+    recs = synth.fanout_events(24, seed=19, fanout=F)
+    # partial: give record 3 results for a third of its calls (they are no longer pending)
+    env = json.loads(recs[3])
+    ids = list(env["context"]["state"]["tool_calls"])
+    for cid in ids[::3]:
+        env["context"]["state"]["tool_results"][cid] = {"return_value": "done", "content": None, "metadata": {"tool_call_id": cid}, "kind": "tool-return"}
+    recs[3] = port.encode(port.decode(json.dumps(env).encode()))
+    registry = {f"tool_{j:02d}": f"tool.tool_{j:02d}.input" for j in range(F)}
+    e = BatchEngine(0, max_records=64, max_in_bytes=8 << 20, max_out_bytes=256 << 20, max_payloads=64 * (F + 1))
+    try:
+        e.register_topics(list(registry.values()) + ["planner.input", "planner.output"], num_partitions=8)
+        e.set_agent_node("planner", "planner.input", "planner.output", registry)
+        b = synth.pack(recs)
+        ms, seed = 1767225600000, 4321
+        e.submit(b.data, b.offsets)
+        e.fanout_plan(ms, seed, max_fanout=64)
+        out = e.fetch()
+        assert (out.cols[0] == 0).all()
+        pubs = list(out.publishes())
+        slot = k = 0
+        for i, rec in enumerate(recs):
+            st = port.decode(rec).context.state
+            npend = len([c for c in st.tool_calls if c not in st.tool_results])
+            it = iter([device_uuid7_hex(ms, seed, slot + j) for j in range(npend)])
+            _ids.set_id_source(lambda: next(it))
+            try:
+                want = port.agent_fanout("planner", "planner.input", "planner.output", registry, rec)
+            finally:
+                _ids.set_id_source(None)
+            got = [(p.topic, p.key, p.payload) for p in pubs[k:k + len(want)]]
+            assert len(want) == npend + 1 and got == [(t, kk, pl) for (t, kk, c, pl) in want], i
+            k += len(want)
+            slot += npend + 1
+        assert k == len(pubs)
+    finally:
+        e.close()
+
+
+def test_mixed_sizes_256_topics_config5(engine):
+    """BASELINE.json configs[4] shape: sizes log-uniform 128 B - 64 KB (multi-turn histories with escapes and multi-byte
+    UTF-8), callbacks spread over 256 registered topics: every publish (topic, key, partition, payload) against the oracle."""
+    import tools_def
+    from oracle import port
+    from calfkit import synth
+    from calfkit.engine import BatchEngine, ToolTemplate
+    recs = synth.mixed_events(700, seed=41, hi=65536, n_agents=256)
+    assert max(len(r) for r in recs) > 40000 and min(len(r) for r in recs) < 1500
+    topics = [f"agent_{k:03d}.input" for k in range(256)] + ["tool.get_weather.input", "tool.get_weather.output"]
+    e = BatchEngine(0, max_records=1024, max_in_bytes=32 << 20)
+    try:
+        e.register_topics(topics, num_partitions=8)
+        e.set_tool_node("tool.get_weather.output", ToolTemplate.from_format("It's sunny in {location}"))
+        b = synth.pack(recs)
+        e.submit(b.data, b.offsets)
+        e.tool_plan()
+        out = e.fetch()
+        assert (out.cols[0] == 0).all()
+        assert (out.live()["topic_id"] >= 0).all()            # all 256 callback topics resolved on the device
+        node = port.ToolNode.of(tools_def.get_weather)
+        got = [(p.topic, p.key, p.payload, p.partition) for p in out.publishes()]
+        want = []
+        for r in recs:
+            for (t, k, _c, pl) in port.tool_node_event(node, r):
+                want.append((t, k, pl, -1 if k is None else (_murmur2(k) & 0x7FFFFFFF) % 8))
+        assert got == want
+        assert len({t for t, *_ in got}) == 257
+    finally:
+        e.close()
+
+
+def _murmur2(data: bytes) -> int:
+    m, h = 0x5BD1E995, (0x9747B28C ^ len(data)) & 0xFFFFFFFF
+    n4 = len(data) // 4
+    for i in range(n4):
+        k = int.from_bytes(data[4 * i:4 * i + 4], "little")
+        k = (k * m) & 0xFFFFFFFF; k ^= k >> 24; k = (k * m) & 0xFFFFFFFF
+        h = (h * m) & 0xFFFFFFFF; h ^= k
+    t = data[4 * n4:]
+    if len(t) == 3: h ^= t[2] << 16
+    if len(t) >= 2: h ^= t[1] << 8
+    if len(t) >= 1: h ^= t[0]; h = (h * m) & 0xFFFFFFFF
+    h ^= h >> 13; h = (h * m) & 0xFFFFFFFF; h ^= h >> 15
+    return h
