@@ -1,4 +1,7 @@
-"""Client-side request / reply machinery in ONE module, in dependency order: NodeResult -> reply projection ->
+"""Largely a TRANSCRIPTION of the reference's client package (same names, arguments, error behaviour: the API surface);
+only `_ReplyDispatcher.drain` (the batch worker's stand-in for FastStream's consume task) is new.
+
+Client-side request / reply machinery in ONE module, in dependency order: NodeResult -> reply projection ->
 InvocationHandle -> correlation-id future table -> BaseClient.  Same names, arguments and error behaviour as the
 reference's calfkit/client/{node_result,deserialize,invocation_handle,reply_dispatcher,base}.py (those module paths
 re-export from here).  This is the per-request user-API edge of the path: objects in,

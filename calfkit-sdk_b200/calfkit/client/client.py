@@ -1,4 +1,7 @@
-"""Client (mirrors reference calfkit/client/client.py:20-218): invoke_node / execute_node."""
+"""TRANSCRIPTION: signatures and bodies restate the reference's calfkit/client/client.py (the user-facing API of the drop-in
+boundary) — not original work.
+
+Client (mirrors reference calfkit/client/client.py:20-218): invoke_node / execute_node."""
 from __future__ import annotations
 
 from collections.abc import Sequence

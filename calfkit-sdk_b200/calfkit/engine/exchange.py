@@ -76,6 +76,8 @@ def exchange(plan: ExchangePlan, gather: Callable[[ExchangePlan, torch.Tensor], 
              recv_buf: torch.Tensor) -> tuple[int, int, torch.Tensor]:
     """gather(plan, send_buf) packs the selected payloads; returns (n received payloads, received bytes,
     their lengths)."""
+    if int(plan.nbytes.sum()) > send_buf.numel():
+        raise RuntimeError("exchange send buffer too small")          # before the pack kernel writes anything
     gather(plan, send_buf)
     meta_out = torch.stack([plan.counts, plan.nbytes], 1).contiguous().to(plan.lens.device)
     meta_in = torch.empty_like(meta_out)

@@ -5,7 +5,7 @@ from calfkit.models import wire as _wire
 from calfkit.models.tool_context import ToolContext
 
 _EXPORTS = {
-    _actions: ("Call", "Delegate", "Emit", "NodeResult", "Parallel", "Reply", "ReturnCall", "Sequential", "Silent", "TailCall", "_Call"),
+    _actions: ("Call", "NodeResult", "ReturnCall", "Silent", "TailCall", "_Call"),
     _wire: ("Envelope", "ContentPart", "DataPart", "FilePart", "TextPart", "ToolCallPart", "BaseSessionRunContext", "CallFrame",
             "CallFrameStack", "Deps", "SessionRunContext", "Stack", "WorkflowState", "BaseAgentActivityState", "CoreMessageState",
             "InFlightToolsState", "OverridesState", "State", "PendingToolBatch"),

@@ -1,6 +1,9 @@
-"""What a node's run() may return (reference calfkit/models/actions.py:10-122).  The batch
-engine maps each onto a call-stack operation: Call = push, ReturnCall = pop, TailCall = pop+push,
-list[Call] = fan-out of pushes, Silent = nothing (nodes/base.py:70-147)."""
+"""What a node's run() may return.  TRANSCRIPTION, not original work: these dataclasses restate the declarations of the
+reference's calfkit/models/actions.py (:26-49 _Call / Call / TailCall / ReturnCall, :68-70 Silent, :73-80 NodeResult) because
+their names and fields are the user-facing API of the drop-in boundary.  The reference's other action
+types (Reply, Delegate, Sequential, Emit, Parallel, :14-66) are not produced by any node on this path and are not mirrored.
+The batch engine maps each kept type onto a call-stack operation: Call = push, ReturnCall = pop, TailCall = pop+push,
+list[Call] = fan-out of pushes, Silent = nothing (reference nodes/base.py:70-147)."""
 from collections.abc import Sequence
 from dataclasses import dataclass
 from typing import Any, Generic
@@ -8,18 +11,6 @@ from typing import Any, Generic
 from typing_extensions import TypeAliasType, TypeVar
 
 from calfkit._types import StateT
-
-
-@dataclass
-class Reply(Generic[StateT]):
-    value: StateT
-
-
-@dataclass
-class Delegate(Generic[StateT]):
-    topic: str
-    value: StateT | None = None
-    input_args: Sequence[Any] | None = None
 
 
 @dataclass(init=False)
@@ -45,23 +36,6 @@ class TailCall(Generic[StateT], _Call[StateT]):
 @dataclass
 class ReturnCall(Generic[StateT]):
     state: StateT
-
-
-@dataclass
-class Sequential(Generic[StateT]):
-    topics: list[str]
-    value: StateT | None = None
-
-
-@dataclass
-class Emit(Generic[StateT]):
-    value: StateT
-    topic: str
-
-
-@dataclass
-class Parallel(Generic[StateT]):
-    delegates: list[Delegate[StateT] | Call[StateT]]
 
 
 @dataclass

@@ -1,4 +1,8 @@
-"""Wire-format models of the hot path in ONE module, in dependency order: content parts -> node routing schema ->
+"""TRANSCRIPTION of the reference's model declarations (field names, order, defaults, config = the byte contract), with the
+helper bodies the reference gives them (commit_message_to_history, Stack.push/pop/peek, invoke_frame / unwind_frame) restated
+as they are — not original work; the product's own work is the CUDA path that implements this schema.
+
+Wire-format models of the hot path in ONE module, in dependency order: content parts -> node routing schema ->
 agent state -> call stack / session context -> Envelope.  Field names, order, defaults and config are the byte
 contract (`Envelope.model_dump_json()`); the reference spreads the same declarations over
 calfkit/models/{payload,node_schema,state,session_context,envelope}.py — those module paths still exist here and

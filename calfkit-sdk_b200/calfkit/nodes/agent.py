@@ -116,6 +116,13 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
                                "(e.g. partition rebalance or process restart).")
         if state.uncommitted_message is not None:
             state.commit_message_to_history()
+        # instructions as the reference's agent loop composes them (_vendor/pydantic_ai/agent/__init__.py:1465-1487,
+        # 638-650): the literals — Agent(instructions=system_prompt) and run(instructions=state.temp_instructions),
+        # nodes/agent.py:54,126 — joined by "\n", then that and the outputs of the @agent.instructions functions joined by
+        # "\n\n"; the ModelRequest that carries the tool returns records the same string
+        literal = "\n".join(x for x in (self.system_prompt, state.temp_instructions) if isinstance(x, str)).strip() or None
+        inst_parts = [x for x in [literal, *[fn() for fn in self._instruction_fns]] if x]
+        instructions = "\n\n".join(inst_parts).strip() if inst_parts else None
         messages = list(state.message_history)
         if latest:                                           # tool returns go back to the model as a request
             parts = []
@@ -126,16 +133,10 @@ class BaseAgentNodeDef(Generic[AgentOutputT], BaseNodeDef):
                 else:
                     value = getattr(res, "return_value", res)
                     parts.append(ToolReturnPart(tool_name=tc.tool_name, content=value, tool_call_id=tc.tool_call_id))
-            request = ModelRequest(parts=parts)
+            request = ModelRequest(parts=parts, instructions=instructions)
             messages.append(request)
             state.message_history.append(request)
-        instructions = state.temp_instructions
-        for fn in self._instruction_fns:
-            extra = fn()
-            if extra:
-                instructions = f"{instructions}\n{extra}" if instructions else extra
-        response = self.model_client(messages, instructions or self.system_prompt,
-                                     [t.tool_schema for t in registry.values()], deps)
+        response = self.model_client(messages, instructions, [t.tool_schema for t in registry.values()], deps)
         state.message_history.append(response)
         calls = [p for p in response.parts if isinstance(p, ToolCallPart)]
         if calls:

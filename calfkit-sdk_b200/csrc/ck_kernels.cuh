@@ -14,16 +14,24 @@
 #include "ck_walk.cuh"
 #include "ck_canon.cuh"
 
+#if !defined(__CUDA_ARCH__)
+extern __shared__ uint4 ck_win_smem[];   // nvcc's host pass parses the device code too; ck_walk.cuh declares it for the device pass
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // A batch as the kernels see it: the submitted records (concatenated bytes + offsets) plus an overlay —
 // the canonical re-emission of the records that arrived in a non-canonical spelling (ck_canon.cuh).
 // Every stage after decode reads a record through ck_rec(), i.e. its canonical bytes.
 // ------------------------------------------------------------------------------------------------
-struct ck_canon_ctl { unsigned long long cursor; u32 count; u32 pad; };   // overlay bytes handed out, records listed
+#ifndef CK_LONG_MIN
+#define CK_LONG_MIN 4096u        // records at least this long are walked one per warp (ck_walk_long.cuh)
+#endif
+struct ck_canon_ctl { unsigned long long cursor; u32 count; u32 pad; };   // overlay bytes handed out, records listed; pad = long records listed
 struct ck_view {
     const u8* in; const long long* off;
     const u8* ovl; const long long* ovl_off; const u32* ovl_len;     // ovl_off[i] < 0: record i has no overlay
     ck_canon_ctl* canon_ctl; u32* canon_list;                        // records the walker left to the canonicaliser
+    u32* long_list;                                                  // records of CK_LONG_MIN bytes or more: walked one per warp (ck_walk_long.cuh)
     const u32* len;                                                  // NULL: record i = [off[i], off[i+1]); else off[i] .. + len[i]
 };                                                                   //       (values inside raw Kafka record batches are not contiguous)
 __device__ __forceinline__ const u8* ck_rec_in(const ck_view& v, u32 i, u32& len) {     // the submitted bytes of record i
@@ -95,6 +103,11 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
     u32 len; const u8* rec;
     if (mode == 0) rec = ck_rec_in(v, i, len);                                                       // the submitted spelling
     else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }                                  // re-walk of canonicalised records
+    if (mode == 0 && len >= CK_LONG_MIN && v.long_list) {            // long record: a whole warp takes it (ck_walk_long_kernel)
+        u32 k = atomicAdd(&v.canon_ctl->pad, 1u);
+        v.long_list[k] = i;
+        return;
+    }
     WalkOut o; o.base = cols + i; o.stride = stride;
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
@@ -920,6 +933,7 @@ ck_route_kernel(ck_view vw, const u32* __restrict__ cols, u32 stride,
     }
 }
 
+#include "ck_walk_long.cuh"
 #include "ck_plan2.cuh"
 #include "ck_fanout2.cuh"
 #include "ck_gate.cuh"

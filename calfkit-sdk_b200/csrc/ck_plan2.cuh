@@ -17,10 +17,6 @@
 #ifndef CK_PLAN2_CUH
 #define CK_PLAN2_CUH
 
-#if !defined(__CUDA_ARCH__)
-extern __shared__ uint4 ck_win_smem[];   // nvcc's host pass parses the device code below; ck_walk.cuh declares it for the device pass
-#endif
-
 #define CK_P2_THREADS 128
 #define CK_P2_WIN 64u                 // window bytes per thread
 #define CK_P2_WSTRIDE 80u             // slot stride (the pad spreads the slots over the banks)

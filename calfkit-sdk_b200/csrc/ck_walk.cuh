@@ -34,6 +34,60 @@ struct uint4 { u32 x, y, z, w; };        // host test build of the device source
 struct Span { u32 off, len; };
 
 // -------------------------------------------------------------------------------------------------
+// Long records (ck_walk_long.cuh): one WARP walks a record.  All lanes run the walker in lockstep on the same bytes (reader
+// URd: kWarp); where the schema has a long list — the entries of tool_calls / tool_results, the messages of message_history,
+// the parts of a message — the lanes take one element each and validate it with the unchanged recognisers through their
+// own reader.  The element boundaries come from a data-parallel structural pre-scan of the record (string mask by prefix
+// XOR of the quote bits, nesting depth by prefix sums of the bracket bits: positions of the commas and closers at depths 4
+// and 6).  The pre-scan only PROPOSES boundaries: element e must start right after the opener / the previous comma and its
+// walk must end exactly at the next proposed comma / the closer, so the element walks chain into exactly the cover the
+// sequential walker would produce — a wrong proposal fails a walk and the record goes to the canonicaliser path.
+// The helpers below have single-lane stand-ins so that the host (g++) build of this file parses the hooks.
+// -------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+extern __shared__ uint4 ck_win_smem[];       // dynamic shared memory of the walk kernels (per-thread windows / per-warp indexes)
+#endif
+#define CK_LX_SEP 640u               // commas indexed per depth
+#define CK_LX_CLOSE 320u             // closers indexed per depth
+#define CK_LX_MIN 4u                 // lists shorter than this are walked sequentially
+#define CK_LX_KEYS 128u              // = CK_DICT_KEYS
+struct ck_long_index {
+    u32 n_sep[2], n_close[2], ok, pad[3];
+    u32 sep[2][CK_LX_SEP];           // [0]: depth 4, [1]: depth 6 — record-relative positions of commas outside strings
+    u32 close_[2][CK_LX_CLOSE];      // closers that end a container of that depth
+    u32 kh[2][CK_LX_KEYS], koff[2][CK_LX_KEYS];      // key hash / offset of the entries of tool_calls [0], tool_results [1]
+};
+#if defined(__CUDA_ARCH__)
+CK_HD u32 ck_lane() { return threadIdx.x & 31u; }
+CK_HD bool ck_all(bool p) { return __all_sync(0xffffffffu, p); }
+CK_HD u32 ck_bcast(u32 v, u32 src) { return __shfl_sync(0xffffffffu, v, src); }
+CK_HD u32 ck_or_reduce(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
+CK_HD void ck_warp_sync() { __syncwarp(); }
+#else
+CK_HD u32 ck_lane() { return 0; }
+CK_HD bool ck_all(bool p) { return p; }
+CK_HD u32 ck_bcast(u32 v, u32) { return v; }
+CK_HD u32 ck_or_reduce(u32 v) { return v; }
+CK_HD void ck_warp_sync() {}
+#endif
+// elements of the list whose content starts at `pos` (just after its opener) at depth index di (0: depth 4, 1: depth 6):
+// closer position q, index of the first separator inside and the number of separators; false = no usable proposal
+CK_HD bool ck_lx_range(const ck_long_index* lx, u32 di, u32 pos, u32& q, u32& s0, u32& k) {
+    if (!lx || !lx->ok) return false;
+    u32 lo = 0, hi = lx->n_close[di];
+    while (lo < hi) { u32 mid = (lo + hi) >> 1; if (lx->close_[di][mid] < pos) lo = mid + 1; else hi = mid; }
+    if (lo >= lx->n_close[di]) return false;
+    q = lx->close_[di][lo];
+    lo = 0; hi = lx->n_sep[di];
+    while (lo < hi) { u32 mid = (lo + hi) >> 1; if (lx->sep[di][mid] < pos) lo = mid + 1; else hi = mid; }
+    s0 = lo;
+    u32 a = lo; hi = lx->n_sep[di];
+    while (a < hi) { u32 mid = (a + hi) >> 1; if (lx->sep[di][mid] < q) a = mid + 1; else hi = mid; }
+    k = a - s0;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Reader: byte access to one record through aligned 8-byte global loads (one 32 B sector serves
 // four consecutive loads of a lane; L1 keeps the line for the next three).  The input buffer is
 // allocated with >= 16 bytes of tail padding and a 256 B aligned base, so aligned-down / +8 loads
@@ -41,6 +95,7 @@ struct Span { u32 off, len; };
 // -------------------------------------------------------------------------------------------------
 struct GRd {
     static const bool kWindow = false;
+    static const bool kWarp = false;          // see URd (ck_walk_long.cuh)
     static const bool kTrustFloats = false;   // see WRdT
     const u8* g;     // record start
     u32 n;           // record length
@@ -92,6 +147,20 @@ struct GRd {
 
 typedef GRd Rd;        // the plan / fan-out kernels read a few scattered spots of a record: plain global loads
 
+// the reader of a warp that walks ONE record in lockstep: plain global loads (every lane reads the same address: one
+// transaction, broadcast), plus the record's structural index in shared memory
+struct URd : GRd {
+    static const bool kWarp = true;
+    CK_HD const ck_long_index* lx() const {
+#if defined(__CUDA_ARCH__)
+        return (const ck_long_index*)ck_win_smem + (threadIdx.x >> 5);
+#else
+        return nullptr;
+#endif
+    }
+    CK_HD ck_long_index* lxw() const { return (ck_long_index*)lx(); }
+};
+
 // -------------------------------------------------------------------------------------------------
 // Window reader (the walker's): each thread stages CK_WIN_BYTES of its record in shared memory with
 // 16-byte asynchronous copies (cp.async, no data registers, all chunks of a refill in flight at once)
@@ -135,6 +204,7 @@ CK_HD_NOINLINE u32 ck_win_refill(const u8* gb, u32 ap, u32 lim) {
 
 struct WRd {
     static const bool kWindow = true;
+    static const bool kWarp = false;
     static const bool kTrustFloats = false;
     const u8* g;     // record start
     u32 n;           // record length
@@ -774,12 +844,38 @@ CK_HD_NOINLINE u64 ck_message_core(const u8* g, u32 n, u32 pos, u32 st, u32 d, A
     if (!M("{\"parts\":[")) return 0;
     u32 seen = 0;
     if (!PEEK(']')) {
+        bool par = false;
+        if constexpr (R::kWarp) {
+            // a message of message_history (d == 5): its parts are list elements at depth 6 — one lane each
+            u32 q, s0, k;
+            if (d == 5 && ck_lx_range(r.lx(), 1, pos, q, s0, k) && k + 1 >= CK_LX_MIN) {
+                par = true;
+                const ck_long_index* lx = r.lx();
+                bool good = true;
+                for (u32 base = 0; base <= k; base += 32) {
+                    u32 e = base + ck_lane(), kind = 0;
+                    bool ok = true;
+                    if (e <= k) {
+                        u32 p = e ? lx->sep[1][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[1][s0 + e];
+                        GRd lr; lr.init(r.g, r.n);
+                        kind = ck_message_part(lr, p, d + 2, cx);
+                        ok = kind != 0 && p == tend;
+                    }
+                    good = ck_all(ok) && good;
+                    seen |= ck_or_reduce(kind);
+                }
+                if (!good) return 0;
+                pos = q;
+            }
+        }
+        if (!par) {
         for (;;) {
             u32 k = ck_message_part(r, pos, d + 2, cx);
             if (!k) return 0;
             seen |= k;
             if (PEEK(',')) { pos++; continue; }
             break;
+        }
         }
     }
     if (!M("]")) return 0;
@@ -986,8 +1082,8 @@ CK_HD bool ck_tool_result_value(R& r, u32& pos, u32 d, AnyCtx& cx) {
 // column sink: device = the SoA table in HBM (lane i of a warp owns element i of every column, so
 // a convergent warp writes 128 contiguous bytes per column); host tests = a plain array (stride 1)
 struct WalkOut {
-    u32* base; size_t stride;
-    CK_HD void set(u32 col, u32 v) { base[(size_t)col * stride] = v; }
+    u32* base; size_t stride; bool active = true;       // a warp walking one record: only lane 0 stores
+    CK_HD void set(u32 col, u32 v) { if (active) base[(size_t)col * stride] = v; }
 };
 
 #define SETSPAN(COL, a, b) do { o.set(COL, (a)); o.set(COL + 1, (b) - (a)); } while (0)
@@ -1000,8 +1096,13 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     // keys of the two id-keyed dicts: 32-bit hash (uniqueness check: the reference holds Python dicts)
     // + span, so that tool_calls[input_args[0]] / tool_results[...] can be resolved at the end of the
     // walk without scanning the dicts again
-    u32 tc_kh[CK_DICT_KEYS], tc_koff[CK_DICT_KEYS], tc_n = 0;     // key length is re-derived from the closing quote
-    u32 tr_kh[CK_DICT_KEYS], tr_koff[CK_DICT_KEYS], tr_n = 0;
+    u32 tc_kh_l[CK_DICT_KEYS], tc_koff_l[CK_DICT_KEYS], tc_n = 0;     // key length is re-derived from the closing quote
+    u32 tr_kh_l[CK_DICT_KEYS], tr_koff_l[CK_DICT_KEYS], tr_n = 0;
+    u32 *tc_kh = tc_kh_l, *tc_koff = tc_koff_l, *tr_kh = tr_kh_l, *tr_koff = tr_koff_l;
+    if constexpr (R::kWarp) {          // a warp on one record: the lanes share the key tables (shared memory)
+        ck_long_index* lw = r.lxw();
+        tc_kh = lw->kh[0]; tc_koff = lw->koff[0]; tr_kh = lw->kh[1]; tr_koff = lw->koff[1];
+    }
     ToolCallSpans first_tc = {{0, 0}, {0, 0}, {0, 0}};
     u32 first_tc0 = 0, first_tc1 = 0, first_tr0 = 0, first_tr1 = 0;
 #define FAIL do { stop = pos; return false; } while (0)
@@ -1009,6 +1110,45 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M("{\"context\":{\"state\":{\"tool_calls\":{")) FAIL;
     u32 a = pos - 1;
     if (!PEEK('}')) {
+        bool par = false;
+        if constexpr (R::kWarp) {
+            u32 q, s0, k;
+            if (ck_lx_range(r.lx(), 0, pos, q, s0, k) && k + 1 >= CK_LX_MIN) {
+                par = true;
+                if (k + 1 > CK_DICT_KEYS) FAIL;
+                const ck_long_index* lx = r.lx();
+                bool good = true;
+                for (u32 base = 0; base <= k; base += 32) {
+                    u32 e = base + ck_lane(), v0 = 0, v1 = 0;
+                    bool ok = true;
+                    ToolCallSpans tc = {{0, 0}, {0, 0}, {0, 0}};
+                    if (e <= k) {
+                        u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
+                        GRd lr; lr.init(r.g, r.n);
+                        Span key;
+                        ok = ck_string(lr, p, key) && ck_match(lr, p, ":", 1);
+                        v0 = p;
+                        ok = ok && ck_tool_call_part(lr, p, 5, cx, tc) == 1 && p == tend;
+                        v1 = p;
+                        if (ok) { tc_kh[e] = ck_hash_span(lr, key.off, key.len); tc_koff[e] = key.off; }
+                    }
+                    good = ck_all(ok) && good;
+                    if (base == 0) {       // entry 0 (lane 0 of the first round): the common single-call case needs no second look
+                        first_tc.tool_name.off = ck_bcast(tc.tool_name.off, 0); first_tc.tool_name.len = ck_bcast(tc.tool_name.len, 0);
+                        first_tc.args.off = ck_bcast(tc.args.off, 0); first_tc.args.len = ck_bcast(tc.args.len, 0);
+                        first_tc.tool_call_id.off = ck_bcast(tc.tool_call_id.off, 0); first_tc.tool_call_id.len = ck_bcast(tc.tool_call_id.len, 0);
+                        first_tc0 = ck_bcast(v0, 0); first_tc1 = ck_bcast(v1, 0);
+                    }
+                }
+                if (!good) FAIL;
+                ck_warp_sync();
+                bool dup = false;
+                for (u32 e = ck_lane(); e <= k; e += 32) for (u32 j = 0; j < e; j++) dup |= (tc_kh[j] == tc_kh[e]);
+                if (!ck_all(!dup)) FAIL;
+                tc_n = k + 1; pos = q;
+            }
+        }
+        if (!par) {
         // dict[str, ToolCallPart]; keys must be unique (a Python dict on the reference side):
         // 32-bit hashes of the raw key bytes, a (vanishingly rare) collision only costs the fast path
         for (;;) {
@@ -1024,6 +1164,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             if (tc_n == 1) { first_tc = tc; first_tc0 = v0; first_tc1 = pos; }      // the common single-call case needs no second look
             if (PEEK(',')) { pos++; continue; }
             break;
+        }
         }
     }
     if (!M("}")) FAIL;
@@ -1041,6 +1182,39 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     if (!M(",\"tool_results\":{")) FAIL;
     a = pos - 1;
     if (!PEEK('}')) {
+        bool par = false;
+        if constexpr (R::kWarp) {
+            u32 q, s0, k;
+            if (ck_lx_range(r.lx(), 0, pos, q, s0, k) && k + 1 >= CK_LX_MIN) {
+                par = true;
+                if (k + 1 > CK_DICT_KEYS) FAIL;
+                const ck_long_index* lx = r.lx();
+                bool good = true;
+                for (u32 base = 0; base <= k; base += 32) {
+                    u32 e = base + ck_lane(), v0 = 0, v1 = 0;
+                    bool ok = true;
+                    if (e <= k) {
+                        u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
+                        GRd lr; lr.init(r.g, r.n);
+                        Span key;
+                        ok = ck_string(lr, p, key) && ck_match(lr, p, ":", 1);
+                        v0 = p;
+                        ok = ok && ck_tool_result_value(lr, p, 5, cx) && p == tend;
+                        v1 = p;
+                        if (ok) { tr_kh[e] = ck_hash_span(lr, key.off, key.len); tr_koff[e] = key.off; }
+                    }
+                    good = ck_all(ok) && good;
+                    if (base == 0) { first_tr0 = ck_bcast(v0, 0); first_tr1 = ck_bcast(v1, 0); }
+                }
+                if (!good) FAIL;
+                ck_warp_sync();
+                bool dup = false;
+                for (u32 e = ck_lane(); e <= k; e += 32) for (u32 j = 0; j < e; j++) dup |= (tr_kh[j] == tr_kh[e]);
+                if (!ck_all(!dup)) FAIL;
+                tr_n = k + 1; pos = q;
+            }
+        }
+        if (!par) {
         for (;;) {
             if (!ck_string(r, pos, t)) FAIL;
             u32 h = ck_hash_span(r, t.off, t.len);
@@ -1053,6 +1227,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             if (tr_n == 1) { first_tr0 = v0; first_tr1 = pos; }
             if (PEEK(',')) { pos++; continue; }
             break;
+        }
         }
     }
     if (!M("}")) FAIL;
@@ -1069,10 +1244,33 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
 #endif
     a = pos - 1;
     if (!PEEK(']')) {
+        bool par = false;
+        if constexpr (R::kWarp) {
+            u32 q, s0, k;
+            if (ck_lx_range(r.lx(), 0, pos, q, s0, k) && k + 1 >= CK_LX_MIN) {
+                par = true;
+                const ck_long_index* lx = r.lx();
+                bool good = true;
+                for (u32 base = 0; base <= k; base += 32) {
+                    u32 e = base + ck_lane();
+                    bool ok = true;
+                    if (e <= k) {
+                        u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
+                        GRd lr; lr.init(r.g, r.n);
+                        ok = ck_message(lr, p, 5, cx) != 0 && p == tend;
+                    }
+                    good = ck_all(ok) && good;
+                }
+                if (!good) FAIL;
+                pos = q;
+            }
+        }
+        if (!par) {
         for (;;) {
             if (!ck_message(r, pos, 5, cx)) FAIL;
             if (PEEK(',')) { pos++; continue; }
             break;
+        }
         }
     }
     if (!M("]")) FAIL;

@@ -406,3 +406,33 @@ def test_a_raising_tool_fails_only_its_record():
     args = [b'{"x":2}', b'{"x":3}', b"", b'{"x":4}']
     results, failed = picky._host_results(4, lambda i: args[i], lambda i: memoryview(b""), cols)
     assert results == [b"20", b"null", b"", b"40"] and failed == {1}
+
+
+def test_agent_instructions_are_composed_like_the_reference():
+    """reference _vendor/pydantic_ai/agent/__init__.py:1465-1487,638-650 with nodes/agent.py:54,126: literals (system prompt,
+    temp_instructions) joined by a newline, then the @agent.instructions function outputs joined by a blank line; the request
+    that carries the tool returns records the composed string."""
+    from calfkit.models import State
+    from calfkit.models.messages import ModelRequest, ModelResponse, TextPart, ToolCallPart, ToolReturn, UserPromptPart
+    from calfkit.nodes import Agent, FunctionModelClient
+    seen = {}
+
+    class Client:
+        def __call__(self, messages, instructions, tools, deps):
+            seen["instructions"], seen["last"] = instructions, messages[-1]
+            return ModelResponse(parts=[TextPart(content="ok")])
+    agent = Agent("planner", system_prompt="You plan.", subscribe_topics="planner.input", model_client=Client())
+    agent.instructions(lambda: "Dynamic A.")
+    agent.instructions(lambda: None)
+    agent.instructions(lambda: "Dynamic B.")
+    st = State(message_history=[ModelRequest(parts=[UserPromptPart(content="hi")])], temp_instructions="Only today.")
+    agent._llm_step("c" * 32, st, {})
+    assert seen["instructions"] == "You plan.\nOnly today.\n\nDynamic A.\n\nDynamic B."
+    # no temp instructions, no functions: just the system prompt; and the tool-return request records it
+    agent2 = Agent("planner", system_prompt="You plan.", subscribe_topics="planner.input", model_client=Client())
+    tc = ToolCallPart(tool_name="t", args={}, tool_call_id="id1")
+    st2 = State(message_history=[ModelRequest(parts=[UserPromptPart(content="hi")]), ModelResponse(parts=[tc])],
+                tool_calls={"id1": tc}, tool_results={"id1": ToolReturn(return_value="r", metadata={"tool_call_id": "id1"})})
+    _a, new = agent2._llm_step("d" * 32, st2, {})
+    assert seen["instructions"] == "You plan." and seen["last"].instructions == "You plan."
+    assert new.message_history[-2].instructions == "You plan."
