@@ -340,9 +340,73 @@ struct CJ {                                   // one canonicalisation in flight
     u32 hs[CJ_HS]; u32 hsp;                   // key hashes of the dict scopes being checked for duplicates (LIFO)
 };
 
+// decoded strings equal?
+CK_HD bool cj_keys_equal(const CIn& in, u32 a, u32 b) {
+    a++; b++;
+    for (;;) {
+        bool ea = in.p[a] == '"', eb = in.p[b] == '"';
+        if (ea || eb) return ea && eb;
+        if (cj_next_cp(in, a) != cj_next_cp(in, b)) return false;
+    }
+}
+
+CK_HD int cj_emit_scalar(const CIn& in, u32 p, COut& o) {       // string / number / literal token at p
+    u8 c = in.p[p];
+    if (c == '"') { cj_emit_string(in, p, o); return CE_OK; }
+    u32 e = cj_scalar_end(in, p);
+    if (c == 't' || c == 'f' || c == 'n') { o.copy(in, p, e); return CE_OK; }
+    if (c == 'N' || c == 'I' || (c == '-' && in.p[p + 1] == 'I')) { CPUTS(o, "null"); return CE_OK; }
+    return cj_emit_number(in, p, e, o, false);
+}
+
+// generic value with duplicate keys somewhere inside: the reference holds Python dicts, so a repeated key keeps its FIRST
+// position and takes the LAST value (dict assignment).  Recursive, bounded: <= CJ_DD_KEYS members per object with
+// duplicates in play, <= CJ_DD_DEPTH levels; beyond that the record stays undecided.
+#define CJ_DD_KEYS 32
+#define CJ_DD_DEPTH 16
+CK_HDR int cj_emit_any_dedup(CJ& cj, u32 pos, u32 depth) {
+    const CIn& in = cj.in; COut& o = cj.o;
+    if (depth > CJ_DD_DEPTH) return CE_UNSUP;
+    u8 c = in.p[pos];
+    if (c == '[') {
+        o.put('[');
+        u32 q = cj_skip_ws(in, pos + 1);
+        bool first = true;
+        while (in.p[q] != ']') {
+            if (!first) o.put(',');
+            first = false;
+            int rc = cj_emit_any_dedup(cj, q, depth + 1); if (rc) return rc;
+            q = cj_skip_ws(in, cj_skip_value(in, q));
+            if (in.p[q] == ',') q = cj_skip_ws(in, q + 1);
+        }
+        o.put(']');
+        return CE_OK;
+    }
+    if (c != '{') return cj_emit_scalar(in, pos, o);
+    u32 kp[CJ_DD_KEYS], vp[CJ_DD_KEYS], n = 0;
+    u32 q = cj_skip_ws(in, pos + 1);
+    while (in.p[q] != '}') {
+        u32 key = q;
+        q = cj_skip_ws(in, cj_skip_value(in, q)); q++; q = cj_skip_ws(in, q);
+        u32 j = 0;
+        for (; j < n; j++) if (cj_keys_equal(in, kp[j], key)) break;
+        if (j == n) { if (n >= CJ_DD_KEYS) return CE_UNSUP; kp[n] = key; n++; }
+        vp[j] = q;
+        q = cj_skip_ws(in, cj_skip_value(in, q));
+        if (in.p[q] == ',') q = cj_skip_ws(in, q + 1);
+    }
+    o.put('{');
+    for (u32 j = 0; j < n; j++) {
+        if (j) o.put(',');
+        cj_emit_string(in, kp[j], o);
+        o.put(':');
+        int rc = cj_emit_any_dedup(cj, vp[j], depth + 1); if (rc) return rc;
+    }
+    o.put('}');
+    return CE_OK;
+}
+
 // generic value ("Any"): whitespace stripped, strings / numbers canonical, NaN / +-Infinity -> null.
-// Objects with duplicate keys (decoded) are UNSUPPORTED (the reference keeps the first position with the
-// last value).
 CK_HDR int cj_emit_any(CJ& cj, u32 pos) {
     const CIn& in = cj.in; COut& o = cj.o;
     // iterative: the text is valid JSON, so emitting tokens in order minus whitespace reproduces the structure
@@ -360,7 +424,7 @@ CK_HDR int cj_emit_any(CJ& cj, u32 pos) {
                 u32 base = cj.hsp, nh = 0;
                 while (in.p[q] != '}') {
                     u32 h = cj_str_hash(in, q);
-                    for (u32 k = 0; k < nh; k++) if (cj.hs[base + k] == h) return CE_UNSUP;
+                    for (u32 k = 0; k < nh; k++) if (cj.hs[base + k] == h) return cj_emit_any_dedup(cj, pos, 0);   // (or a hash collision: same result)
                     if (base + nh >= CJ_HS) return CE_UNSUP;
                     cj.hs[base + nh++] = h;
                     q = cj_skip_value(in, q);                 // key
@@ -587,17 +651,39 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
     case T_OBJN: if (is_null) { CPUTS(o, "null"); return CE_OK; } /* fall through */
     case T_OBJ: if (ch != '{') return CE_SCHEMA; return cj_emit_any(c, pos);
     case T_INT: {
-        if (ch == '"' || ch == 't' || ch == 'f') return CE_UNSUP;              // lax coercions of str / bool
+        if (ch == '"') {
+            // lax mode: a string holding a plain canonical integer, "-?(0|[1-9][0-9]*)", is that integer; every other string
+            // (signs, underscores, whitespace, "5.0" ...: pydantic has its own rules for them) stays undecided
+            u32 a = pos + 1, b = a;
+            if (in.p[b] == '-') b++;
+            u32 d0 = b;
+            while (cj_isdigit(in.p[b])) b++;
+            if (in.p[b] != '"' || b == d0 || b - d0 > 18 || (in.p[d0] == '0' && b - d0 > 1) || (in.p[a] == '-' && in.p[d0] == '0')) return CE_UNSUP;
+            o.copy(in, a, b);
+            return CE_OK;
+        }
+        if (ch == 't' || ch == 'f') return CE_UNSUP;                           // bool -> int: undecided
         if (!(ch == '-' || cj_isdigit(ch))) return CE_SCHEMA;
         u32 e = cj_scalar_end(in, pos);
-        for (u32 i = pos; i < e; i++) if (in.p[i] == '.' || in.p[i] == 'e' || in.p[i] == 'E') return CE_UNSUP;   // 7.0 -> 7
+        for (u32 i = pos; i < e; i++) if (in.p[i] == '.' || in.p[i] == 'e' || in.p[i] == 'E') {
+            // lax mode: a float literal with an all-zero fraction (7.0, 12.000) is the integer; other float spellings undecided
+            u32 j = i;
+            if (in.p[j] != '.' || j + 1 >= e || i - pos > 15) return CE_UNSUP;
+            for (j = i + 1; j < e; j++) if (in.p[j] != '0') return CE_UNSUP;
+            if (in.p[pos] == '-' && i == pos + 2 && in.p[pos + 1] == '0') { o.put('0'); return CE_OK; }      // -0.0 -> 0
+            return cj_emit_number(in, pos, i, o, false);
+        }
         return cj_emit_number(in, pos, e, o, false);
     }
     case T_BOOLN: if (is_null) { CPUTS(o, "null"); return CE_OK; } /* fall through */
     case T_BOOL:
         if (ch == 't') { CPUTS(o, "true"); return CE_OK; }
         if (ch == 'f') { CPUTS(o, "false"); return CE_OK; }
-        return (ch == '{' || ch == '[' || is_null) ? CE_SCHEMA : CE_UNSUP;     // "true", 1, 0 ... coerce in lax mode
+        // lax mode, the unambiguous spellings only: 1 / 0 and "true" / "false"; the rest of pydantic's table stays undecided
+        if ((ch == '1' || ch == '0') && cj_scalar_end(in, pos) == pos + 1) { if (ch == '1') CPUTS(o, "true"); else CPUTS(o, "false"); return CE_OK; }
+        if (ch == '"' && cj_str_is(in, pos, "true", 4)) { CPUTS(o, "true"); return CE_OK; }
+        if (ch == '"' && cj_str_is(in, pos, "false", 5)) { CPUTS(o, "false"); return CE_OK; }
+        return (ch == '{' || ch == '[' || is_null) ? CE_SCHEMA : CE_UNSUP;
     case T_FLTN:
         if (is_null) { CPUTS(o, "null"); return CE_OK; }
         if (!(ch == '-' || cj_isdigit(ch))) return (ch == '{' || ch == '[') ? CE_SCHEMA : CE_UNSUP;
@@ -654,7 +740,16 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
         bool first = true;
         while (in.p[q] != '}') {
             u32 h = cj_str_hash(in, q);
-            for (u32 k = 0; k < nh; k++) if (c.hs[base + k] == h) return CE_UNSUP;   // duplicate keys: first position, last value
+            bool seen = false;
+            u32 cont = 0;
+            for (u32 k = 0; k < nh; k++) if (c.hs[base + k] == h) seen = true;
+            if (seen) {
+                // a key that occurred before: it keeps its first position and took its last value there (below)
+                q = cj_skip_value(in, q); q = cj_skip_ws(in, q); q++; q = cj_skip_ws(in, q);
+                q = cj_skip_value(in, q); q = cj_skip_ws(in, q);
+                if (in.p[q] == ',') q = cj_skip_ws(in, q + 1);
+                continue;
+            }
             if (base + nh >= CJ_HS) return CE_UNSUP;
             c.hs[base + nh++] = h;
             c.hsp = base + nh;                                                    // nested scopes stack above this one
@@ -662,7 +757,20 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
             first = false;
             cj_emit_string(in, q, o);
             o.put(':');
+            u32 key0 = q;
             q = cj_skip_value(in, q); q = cj_skip_ws(in, q); q++; q = cj_skip_ws(in, q);
+            {   // dict assignment: the value of the LAST member with this key (a 32-bit hash hit is verified on the decoded bytes)
+                u32 scan = cj_skip_ws(in, cj_skip_value(in, q)), lastv = 0;
+                while (in.p[scan] == ',') {
+                    scan = cj_skip_ws(in, scan + 1);
+                    u32 k2 = scan;
+                    scan = cj_skip_ws(in, cj_skip_value(in, scan)); scan++; scan = cj_skip_ws(in, scan);
+                    if (cj_str_hash(in, k2) == h) { if (!cj_keys_equal(in, key0, k2)) return CE_UNSUP; lastv = scan; }
+                    scan = cj_skip_ws(in, cj_skip_value(in, scan));
+                }
+                cont = q;
+                if (lastv) q = lastv;
+            }
             int rc;
             if (type == T_DICT_INT) rc = cj_emit_value(c, q, T_INT, 0);
             else if (type == T_DICT_TCP) rc = cj_emit_value(c, q, T_MODEL, M_TOOLCALL);
@@ -680,17 +788,19 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
                         else if (cj_str_is(in, tv, "retry-prompt", 12)) m = M_RETRYPART;
                     }
                     if (m >= 0) {
-                        u32 save = o.len, sd = c.depth;
+                        u32 save = o.len, sd = c.depth, sh = c.hsp;
+                        bool sovf = o.ovf;
                         rc = cj_emit_model(c, q, (u32)m);
-                        // tagged but not a valid instance: the reference keeps it as plain data (smart union).  That text
-                        // is not a fixed point the fast path can recognise, so it is left undecided here.
-                        if (rc == CE_SCHEMA) { (void)save; (void)sd; return CE_UNSUP; }
+                        // tagged but not a valid instance: the reference keeps it as plain data (`| Any` of the smart union).
+                        // The second walk accepts such a value only from here (trusting reader): it cannot re-derive that
+                        // the tagged model does not validate.
+                        if (rc == CE_SCHEMA) { o.len = save; o.ovf = sovf; c.depth = sd; c.hsp = sh; rc = -1; }
                     }
                 }
                 if (rc < 0) rc = cj_emit_any(c, q);
             }
             if (rc) return rc;
-            q = cj_skip_value(in, q); q = cj_skip_ws(in, q);
+            q = cj_skip_value(in, cont); q = cj_skip_ws(in, q);
             if (in.p[q] == ',') q = cj_skip_ws(in, q + 1);
         }
         o.put('}');
@@ -764,7 +874,9 @@ CK_HDR int cj_emit_model(CJ& c, u32 pos, u32 model) {
         if (fpos[k]) {
             // DataPart.schema_ given through its alias survives one dump but not the next (the emitted key
             // `schema_` is ignored on validation): such a record has no stable canonical form
-            if (f.no_primary && in.p[fpos[k]] != 'n') return CE_UNSUP;
+            // (DataPart.schema_ arrives through its alias `schema`: the reference dumps the value under `schema_`; that text
+            // is no fixed point of the codec — a second validation would ignore the key — so only the trusting second walk
+            // accepts it, from here)
             int rc = cj_emit_value(c, fpos[k], f.type, f.arg); if (rc) return rc; continue;
         }
         switch (f.dflt) {
