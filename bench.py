@@ -917,6 +917,33 @@ def main() -> None:
     e2e_value = world * n / (e2e_ms / 1e3)
     d2h_bytes = [lanes[0].d2h]
 
+    # ---- host-copy ceiling: the same bytes per step as plain concurrent H2D + D2H copies, no kernels, all ranks at once -------
+    c_h2d = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
+    c_d2h = torch.empty(lanes[0].d2h or in_bytes, dtype=torch.uint8).pin_memory()
+    c_din = torch.empty(in_bytes, dtype=torch.uint8, device=dev)
+    c_dout = torch.empty(c_d2h.numel(), dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    c_steps = 6
+    for k_ in range(2 + c_steps):
+        if k_ == 2:
+            barrier()
+            t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            c_din.copy_(c_h2d, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            c_d2h.copy_(c_dout, non_blocking=True)
+    torch.cuda.synchronize()
+    c_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    tc_ = torch.tensor([c_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc_, op=dist.ReduceOp.MAX)
+    c_ms = float(tc_.item()) / c_steps
+    ceiling = {"events_per_s": world * n / (c_ms / 1e3), "ms_per_step": c_ms, "h2d_gbs_per_gpu": in_bytes / c_ms / 1e6,
+               "d2h_gbs_per_gpu": c_d2h.numel() / c_ms / 1e6,
+               "what": "plain cudaMemcpyAsync of one step's bytes in both directions at once from/to pinned host memory on every rank, no kernels"}
+    del c_h2d, c_d2h, c_din, c_dout, s_up, s_dn
+
     # ---- N > 1: the bytes each rank RECEIVED against what their senders planned (outside all timed regions) ---------------
     x_parity = None
     if world > 1:
@@ -1080,6 +1107,7 @@ def main() -> None:
                 "api": "calfkit.Worker.run(until_idle=True): MemoryBroker.poll_arena (pinned batch) -> LanePipeline (3 lanes) -> "
                        "MemoryBroker.produce_publishes -> per-topic sinks; no exchange step inside Worker yet (N > 1: ranks run independent shards)",
                 "timing": "host wall clock around Worker.run, synchronised on both sides, max over ranks",
+                "ceiling": ceiling, "frac_of_ceiling": w_value / ceiling["events_per_s"],
                 "engine_level": {"value": e2e_value, "ms_per_step": e2e_ms, "steps": e2e_steps, "d2h_bytes_per_step": d2h_bytes[0],
                                  "api": "BatchEngine.submit(pinned host) + tool_plan + fetch(pinned host), %d engines pipelined%s"
                                         % (len(lanes), " + cross-partition exchange" if world > 1 else "")}},

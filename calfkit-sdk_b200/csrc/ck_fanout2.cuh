@@ -7,11 +7,16 @@
 // indexes the two dicts once into shared memory (key span, value span, 32-bit key hash), then the lanes take one tool
 // call each: pending test against the hashed tool_results keys, registry lookup by name hash, and the splice descriptor
 // of their own Call envelope (same SegWriter, same bytes as before).
+// The index itself is built by the whole warp too: the structural pre-scan of ck_walk_long.cuh proposes the entry
+// boundaries of both dicts, every lane parses its own entry and checks that it ends exactly where the next one starts and
+// that the dict closes where the walker's column says; only if that chain does not hold does lane 0 index sequentially
+// (a 20 KB record: 1.9 ms per kernel that way, measured).
 #ifndef CK_FANOUT2_CUH
 #define CK_FANOUT2_CUH
 
 #define CK_F2_WARPS 4
 #define CK_F2_MAX 256u              // tool calls / results indexed per record (more: CK_UNSUPPORTED, as before beyond max_fanout)
+#define CK_F2_SMEM (CK_F2_WARPS * (sizeof(ck_long_index) + sizeof(ck_f2_index)))
 
 struct ck_f2_index {                // per warp, shared memory
     u32 k_off[CK_F2_MAX], k_len[CK_F2_MAX], v_off[CK_F2_MAX], k_hash[CK_F2_MAX];     // tool_calls entries (v_off = the ToolCallPart)
@@ -45,15 +50,51 @@ __device__ __forceinline__ bool ck_f2_pending(const ck_f2_index* ix, Rd& r, u32 
     return true;
 }
 
+// warp-parallel index of one dict (entries at nesting depth 4) from the pre-scan's proposals; false = chain broken
+__device__ __forceinline__ bool ck_f2_index_dict(const ck_long_index* lx, Rd& r, u32 dict_off, u32 dict_len, u32* k_off, u32* k_len, u32* v_off, u32* k_hash, u32& n_out) {
+    u32 lane = threadIdx.x & 31;
+    u32 pos = dict_off + 1;
+    if (dict_len == 2) { n_out = 0; return true; }
+    u32 q, s0, k;
+    if (!ck_lx_range(lx, 0, pos, q, s0, k) || q != dict_off + dict_len - 1 || k + 1 > CK_F2_MAX) return false;
+    bool good = true;
+    for (u32 base = 0; base <= k; base += 32) {
+        u32 e = base + lane;
+        bool ok = true;
+        if (e <= k) {
+            u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
+            Span key;
+            ok = r.at(p) == '"' && ck_string(r, p, key) && r.at(p) == ':';
+            u32 v = p + 1, p2 = v;
+            if (ok) { ck_skip_value(r, p2); ok = (p2 == tend); }
+            if (ok) { k_off[e] = key.off; k_len[e] = key.len; if (v_off) v_off[e] = v; k_hash[e] = ck_hash_span(r, key.off, key.len); }
+        }
+        good = __all_sync(0xffffffffu, ok) && good;
+    }
+    n_out = k + 1;
+    return good;
+}
+// all lanes call it; the record is a validated canonical envelope (STATUS == CK_OK)
+__device__ __forceinline__ void ck_f2_build_warp(ck_f2_index* ix, ck_long_index* lx, const u8* rec, u32 rlen, Rd& r, u32 tc, u32 tcl, u32 tr, u32 trl) {
+    u32 lane = threadIdx.x & 31;
+    ck_lx_build(rec, rlen, lx);
+    u32 n = 0, m = 0;
+    bool ok = ck_f2_index_dict(lx, r, tc, tcl, ix->k_off, ix->k_len, ix->v_off, ix->k_hash, n);
+    ok = ok && ck_f2_index_dict(lx, r, tr, trl, ix->r_off, ix->r_len, nullptr, ix->r_hash, m);
+    if (ok) { if (lane == 0) { ix->n_calls = n; ix->n_results = m; ix->overflow = 0; } }
+    else if (lane == 0) ck_f2_build(ix, r, tc, tr);
+    __syncwarp();
+}
+
 // pass 1: payload slots per record (pending + 1 for the handler return of a list[Call])
 __global__ void __launch_bounds__(32 * CK_F2_WARPS)
 ck_fanout2_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, const ck_agent_cfg* __restrict__ cfgp, u32 max_fanout, u32 sequential,
                         u32* __restrict__ counts) {
-    __shared__ ck_f2_index s_ix[CK_F2_WARPS];
     u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 i = blockIdx.x * CK_F2_WARPS + w;
     if (i >= n) return;
-    ck_f2_index* ix = &s_ix[w];
+    ck_long_index* lx = (ck_long_index*)ck_win_smem + w;
+    ck_f2_index* ix = (ck_f2_index*)((ck_long_index*)ck_win_smem + CK_F2_WARPS) + w;
 #define COL(k) cols[(size_t)(k) * stride + i]
     u32 status = COL(CK_COL_STATUS), nframes = COL(CK_COL_NFRAMES);
     if (status != CK_OK || nframes == 0) {
@@ -62,8 +103,7 @@ ck_fanout2_count_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, co
     }
     u32 rlen; const u8* rec = ck_rec(v, i, rlen);
     Rd r; r.init(rec, rlen);
-    if (lane == 0) ck_f2_build(ix, r, COL(CK_COL_TC_OFF), COL(CK_COL_TR_OFF));
-    __syncwarp();
+    ck_f2_build_warp(ix, lx, rec, rlen, r, COL(CK_COL_TC_OFF), COL(CK_COL_TC_LEN), COL(CK_COL_TR_OFF), COL(CK_COL_TR_LEN));
     u32 pending = 0;
     for (u32 j = lane; j < ix->n_calls; j += 32) pending += ck_f2_pending(ix, r, j) ? 1u : 0u;
     for (int o = 16; o; o >>= 1) pending += __shfl_xor_sync(0xffffffffu, pending, o);
@@ -85,19 +125,18 @@ __global__ void __launch_bounds__(32 * CK_F2_WARPS)
 ck_fanout2_plan_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, const ck_agent_cfg* __restrict__ cfgp, const u8* __restrict__ lit,
                        const u32* __restrict__ tool_name_hash, const long long* __restrict__ slot_base, unsigned long long unix_ms, unsigned long long seed,
                        const u8* __restrict__ aux, u8* __restrict__ glue, ck_out_desc* __restrict__ descs, u32* __restrict__ pay_len, ck_pub* __restrict__ pubs) {
-    __shared__ ck_f2_index s_ix[CK_F2_WARPS];
     u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 i = blockIdx.x * CK_F2_WARPS + w;
     if (i >= n) return;
-    ck_f2_index* ix = &s_ix[w];
+    ck_long_index* lx = (ck_long_index*)ck_win_smem + w;
+    ck_f2_index* ix = (ck_f2_index*)((ck_long_index*)ck_win_smem + CK_F2_WARPS) + w;
 #define COL(k) cols[(size_t)(k) * stride + i]
     u32 action = COL(CK_COL_ACTION);
     if (COL(CK_COL_STATUS) != CK_OK || (action != CK_ACT_CALL && action != CK_ACT_FANOUT)) return;
     const ck_agent_cfg& cfg = *cfgp;
     u32 rlen; const u8* rec = ck_rec(v, i, rlen);
     Rd r; r.init(rec, rlen);
-    if (lane == 0) ck_f2_build(ix, r, COL(CK_COL_TC_OFF), COL(CK_COL_TR_OFF));
-    __syncwarp();
+    ck_f2_build_warp(ix, lx, rec, rlen, r, COL(CK_COL_TC_OFF), COL(CK_COL_TC_LEN), COL(CK_COL_TR_OFF), COL(CK_COL_TR_LEN));
     u32 slot0 = (u32)slot_base[i];
     u32 frames_off = COL(CK_COL_FRAMES_OFF), frames_len = COL(CK_COL_FRAMES_LEN), nframes = COL(CK_COL_NFRAMES);
     u32 fov_off = COL(CK_COL_FOV_OFF), fov_len = COL(CK_COL_FOV_LEN), sov_off = COL(CK_COL_SOV_OFF), sov_len = COL(CK_COL_SOV_LEN);

@@ -24,7 +24,7 @@ extern __shared__ uint4 ck_win_smem[];   // nvcc's host pass parses the device c
 // Every stage after decode reads a record through ck_rec(), i.e. its canonical bytes.
 // ------------------------------------------------------------------------------------------------
 #ifndef CK_LONG_MIN
-#define CK_LONG_MIN 4096u        // records at least this long are walked one per warp (ck_walk_long.cuh)
+#define CK_LONG_MIN 16384u       // records at least this long are walked one per warp (ck_walk_long.cuh); measured: §7 of DESIGN.md
 #endif
 struct ck_canon_ctl { unsigned long long cursor; u32 count; u32 pad; };   // overlay bytes handed out, records listed; pad = long records listed
 struct ck_view {

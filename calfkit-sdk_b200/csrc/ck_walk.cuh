@@ -147,18 +147,31 @@ struct GRd {
 
 typedef GRd Rd;        // the plan / fan-out kernels read a few scattered spots of a record: plain global loads
 
-// the reader of a warp that walks ONE record in lockstep: plain global loads (every lane reads the same address: one
-// transaction, broadcast), plus the record's structural index in shared memory
+// the reader of a warp that walks ONE record: plain global loads (in lockstep every lane reads the same address: one
+// transaction, broadcast), plus the record's structural index in shared memory.  The same type serves the lockstep walk and
+// the per-lane element walks (one instantiation of the walker: the long kernel's code must fit the instruction cache); the
+// reader state says which one it is — only a lockstep walk (state 2; bit 0 is used by the match cores) may fan a list out.
 struct URd : GRd {
     static const bool kWarp = true;
+    u32 lock;
+    CK_HD void init(const u8* base, u32 len, u32 st = 0) { GRd::init(base, len); lock = st; }
+    CK_HD u32 st() const { return lock; }
+    CK_HD void set_st(u32 s) { lock = s; }
+    CK_HD void invalidate() {}
     CK_HD const ck_long_index* lx() const {
 #if defined(__CUDA_ARCH__)
-        return (const ck_long_index*)ck_win_smem + (threadIdx.x >> 5);
+        return lock ? (const ck_long_index*)ck_win_smem + (threadIdx.x >> 5) : nullptr;
 #else
         return nullptr;
 #endif
     }
-    CK_HD ck_long_index* lxw() const { return (ck_long_index*)lx(); }
+    CK_HD ck_long_index* lxw() const {
+#if defined(__CUDA_ARCH__)
+        return (ck_long_index*)ck_win_smem + (threadIdx.x >> 5);
+#else
+        return nullptr;
+#endif
+    }
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -857,7 +870,7 @@ CK_HD_NOINLINE u64 ck_message_core(const u8* g, u32 n, u32 pos, u32 st, u32 d, A
                     bool ok = true;
                     if (e <= k) {
                         u32 p = e ? lx->sep[1][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[1][s0 + e];
-                        GRd lr; lr.init(r.g, r.n);
+                        R lr; lr.init(r.g, r.n, 0);
                         kind = ck_message_part(lr, p, d + 2, cx);
                         ok = kind != 0 && p == tend;
                     }
@@ -1132,7 +1145,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
                     ToolCallSpans tc = {{0, 0}, {0, 0}, {0, 0}};
                     if (e <= k) {
                         u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
-                        GRd lr; lr.init(r.g, r.n);
+                        R lr; lr.init(r.g, r.n, 0);
                         Span key;
                         ok = ck_string(lr, p, key) && ck_match(lr, p, ":", 1);
                         v0 = p;
@@ -1203,7 +1216,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
                     bool ok = true;
                     if (e <= k) {
                         u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
-                        GRd lr; lr.init(r.g, r.n);
+                        R lr; lr.init(r.g, r.n, 0);
                         Span key;
                         ok = ck_string(lr, p, key) && ck_match(lr, p, ":", 1);
                         v0 = p;
@@ -1264,7 +1277,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
                     bool ok = true;
                     if (e <= k) {
                         u32 p = e ? lx->sep[0][s0 + e - 1] + 1 : pos, tend = e == k ? q : lx->sep[0][s0 + e];
-                        GRd lr; lr.init(r.g, r.n);
+                        R lr; lr.init(r.g, r.n, 0);
                         ok = ck_message(lr, p, 5, cx) != 0 && p == tend;
                     }
                     good = ck_all(ok) && good;

@@ -14,7 +14,7 @@
 #define CK_WALK_LONG_CUH
 
 #ifndef CK_LONG_MIN
-#define CK_LONG_MIN 4096u
+#define CK_LONG_MIN 16384u
 #endif
 #define CK_LONG_WARPS 4
 
@@ -118,7 +118,7 @@ ck_walk_long_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride) {
         u32 len; const u8* rec = ck_rec_in(v, i, len);
         ck_lx_build(rec, len, lx);
         WalkOut o; o.base = cols + i; o.stride = stride; o.active = (lane == 0);
-        URd r; r.init(rec, len);
+        URd r; r.init(rec, len, 2);                                 // state 2 (bit 0 belongs to the match cores): lockstep, lists may fan out
         AnyCtx cx; cx.kfill = 0;
         u32 stop = 0;
         u32 status = ck_walk_envelope(r, o, cx, stop) ? CK_OK : CK_NOT_CANONICAL;

@@ -1,23 +1,23 @@
 """Turns what scripts/profile_round.sh left in gpurun_out/ into the tracked summaries under profiles/ (run here, no GPU):
    python scripts/make_profiles.py r01 [n_records_of_the_ncu_runs=1048576]"""
 import csv, json, os, shutil, subprocess, sys
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 NREC = int(sys.argv[2]) if len(sys.argv) > 2 else 1048576
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
-for name in ("bench_1gpu", "bench_fanout", "bench_reply", "bench_reference"):
+for name in ("bench_1gpu", "bench_fanout", "bench_mixed", "bench_reply", "bench_reference", "bench_2gpu", "bench_4gpu", "bench_8gpu"):
     src = os.path.join(G, f"{R}_{name}.json")
     if os.path.exists(src):
         lines = [l for l in open(src).read().splitlines() if l.startswith("{")]
         if lines:
             open(os.path.join(P, f"{R}_{name}.json"), "w").write(lines[-1] + "\n")
-for name in ("launches.csv", "pytest_gpu.log"):
+for name in ("launches.csv", "pytest_gpu.log", "sass_mnemonics.txt", "exchange_parity_2gpu.log"):
     src = os.path.join(G, f"{R}_{name}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f"{R}_{name}"))
 traffic = {}
-for k, short in (("walk", "walk"), ("plan_tool", "plan"), ("emit", "emit")):
+for k, short in (("walk", "walk"), ("plan_tool2", "plan"), ("emit", "emit"), ("walk_long", "walk_long")):
     rep = os.path.join(G, f"{R}_{k}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -32,8 +32,9 @@ for k, short in (("walk", "walk"), ("plan_tool", "plan"), ("emit", "emit")):
     def metric(name):
         i = hdr.index(name); v = float(val[i]); u = unit[i].lower()
         return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
-    traffic[short] = {"dram_bytes_per_record": (metric("dram__bytes_read.sum") + metric("dram__bytes_write.sum")) / NREC,
-                      "source": f"profiles/{R}_{k}.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum) / {NREC} records"}
+    nrec = 4096 if k == "walk_long" else NREC
+    traffic[short] = {"dram_bytes_per_record": (metric("dram__bytes_read.sum") + metric("dram__bytes_write.sum")) / nrec,
+                      "source": f"profiles/{R}_{k}.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum) / {nrec} records"}
 if traffic:
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 # kernel shares of a step from the launch list (cold-cache, serialised: compare shares, not absolutes)

