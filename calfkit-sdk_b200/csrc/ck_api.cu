@@ -274,8 +274,12 @@ static int launch_decode(ck_handle* h) {
         KTimer t(h, CK_K_WALK);
         if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
         else CKL(h) ck_walk_kernel<<<(n + 127) / 128, 128, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, n, h->d_cols, n, 0);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    {
         // records of CK_LONG_MIN bytes or more were handed to a device-side list: one warp each, lists walked element-parallel
         // (exits at once when there are none)
+        KTimer t(h, CK_K_WALK_LONG);
         u32 lblocks = (n + CK_LONG_WARPS - 1) / CK_LONG_WARPS; if (lblocks > 148 * 4) lblocks = 148 * 4;
         CKL(h) ck_walk_long_kernel<<<lblocks, 32 * CK_LONG_WARPS, CK_LONG_WARPS * sizeof(ck_long_index), h->stream>>>(v, n, h->d_cols, n);
         CUDA_TRY(h, cudaGetLastError());

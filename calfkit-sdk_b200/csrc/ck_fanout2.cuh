@@ -77,10 +77,10 @@ __device__ __forceinline__ bool ck_f2_index_dict(const ck_long_index* lx, Rd& r,
 // all lanes call it; the record is a validated canonical envelope (STATUS == CK_OK)
 __device__ __forceinline__ void ck_f2_build_warp(ck_f2_index* ix, ck_long_index* lx, const u8* rec, u32 rlen, Rd& r, u32 tc, u32 tcl, u32 tr, u32 trl) {
     u32 lane = threadIdx.x & 31;
-    ck_lx_build(rec, rlen, lx);
     u32 n = 0, m = 0;
-    bool ok = ck_f2_index_dict(lx, r, tc, tcl, ix->k_off, ix->k_len, ix->v_off, ix->k_hash, n);
-    ok = ok && ck_f2_index_dict(lx, r, tr, trl, ix->r_off, ix->r_len, nullptr, ix->r_hash, m);
+    bool ok = true;
+    if (tcl > 2) { ck_lx_build(rec, rlen, lx, tc, tc + tcl, 3); ok = ck_f2_index_dict(lx, r, tc, tcl, ix->k_off, ix->k_len, ix->v_off, ix->k_hash, n); }
+    if (ok && trl > 2) { __syncwarp(); ck_lx_build(rec, rlen, lx, tr, tr + trl, 3); ok = ck_f2_index_dict(lx, r, tr, trl, ix->r_off, ix->r_len, nullptr, ix->r_hash, m); }
     if (ok) { if (lane == 0) { ix->n_calls = n; ix->n_results = m; ix->overflow = 0; } }
     else if (lane == 0) ck_f2_build(ix, r, tc, tr);
     __syncwarp();

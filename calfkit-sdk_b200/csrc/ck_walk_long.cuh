@@ -29,15 +29,18 @@ __device__ __forceinline__ u32 ck_mask16_or20(const uint4& w, u32 c) {          
     return ck_nib(__vcmpeq4(w.x | b, cc)) | (ck_nib(__vcmpeq4(w.y | b, cc)) << 4) | (ck_nib(__vcmpeq4(w.z | b, cc)) << 8) | (ck_nib(__vcmpeq4(w.w | b, cc)) << 12);
 }
 
-__device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_long_index* __restrict__ lx) {
+// [from, to): the bytes to scan (the whole record, or one container that starts at a structural character outside any
+// string); depth0: containers open before `from`
+__device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_long_index* __restrict__ lx, u32 from = 0, u32 to = 0xffffffffu, int depth0 = 0) {
     u32 lane = threadIdx.x & 31;
-    u32 m = (u32)((uintptr_t)g & 15);
-    const uint4* stream = (const uint4*)(g - m);                    // 16-byte aligned; the buffers are padded on both sides of a record
-    u32 total = m + n;
+    u32 m0 = (u32)((uintptr_t)g & 15);
+    const uint4* stream = (const uint4*)(g - m0);                   // 16-byte aligned; the buffers are padded on both sides of a record
+    if (to > n) to = n;
+    u32 m = m0 + from, total = m0 + to;                             // valid stream positions: [m, total)
     u32 n_sep[2] = {0, 0}, n_close[2] = {0, 0};
-    u32 prev_bs = 0, str_carry = 0; int depth_carry = 0;
+    u32 prev_bs = 0, str_carry = 0; int depth_carry = depth0;
     bool overflow = false;
-    for (u32 t0 = 0; t0 < total; t0 += 512) {
+    for (u32 t0 = m & ~511u; t0 < total; t0 += 512) {
         u32 p0 = t0 + 16 * lane;                                    // stream position of this lane's first byte
         uint4 w = make_uint4(0, 0, 0, 0);
         if (p0 < total) w = __ldg(stream + (p0 >> 4));
@@ -96,7 +99,7 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
                 int d = dbase + (int)__popc(O & below) - (int)__popc(C & below);
                 u32 li = d == 4 ? 0u : (d == 6 ? 1u : 2u);
                 if (li >= 2) continue;
-                u32 pos = p0 + b - m;
+                u32 pos = p0 + b - m0;
                 if ((C >> b) & 1u) lx->close_[li][off[li + 2]++] = pos; else lx->sep[li][off[li]++] = pos;
             }
         }
