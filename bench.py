@@ -432,6 +432,7 @@ def run_reply(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) ->
     batch = synth.pack(recs)
     in_bytes = int(batch.data.nbytes)
     eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096, max_out_bytes=n * 272 + (1 << 20))
+    eng.set_bucketing(True)            # four reply shapes mixed in every warp: bucket by length before the walk
     d_in = torch.from_numpy(batch.data.copy()).to(dev)
     d_off = torch.from_numpy(batch.offsets.copy()).to(dev)
     stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
@@ -551,6 +552,7 @@ def run_mixed(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) ->
     eng = BatchEngine(local_rank, max_records=n, max_in_bytes=in_bytes + 4096)
     eng.register_topics(topics, num_partitions=NUM_PARTITIONS)
     eng.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))
+    eng.set_bucketing(True)            # sizes from 128 B to 64 KB in one batch: bucket by length before the walk
     d_in = torch.from_numpy(batch.data.copy()).to(dev)
     d_off = torch.from_numpy(batch.offsets.copy()).to(dev)
     stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
@@ -582,7 +584,7 @@ def run_mixed(args, rank, world, local_rank, dev, real_stdout, all_cpus=None) ->
     value = world * n / (ms_step / 1e3)
     from calfkit.engine.lane import Arena, LanePipeline
     pipe = LanePipeline(local_rank, lambda e_: (e_.register_topics(topics, num_partitions=NUM_PARTITIONS),
-                                                e_.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT))),
+                                                e_.set_tool_node("tool.get_weather.output", ToolTemplate.from_format(TOOL_FMT)), e_.set_bucketing(True)),
                         lanes=3, max_records=n, max_in_bytes=in_bytes + 4096)
     h_in = torch.from_numpy(batch.data.copy()).pin_memory()
     h_off = torch.from_numpy(batch.offsets.copy()).pin_memory()

@@ -253,6 +253,10 @@ class BatchEngine:
         """TailCall to the agent's own subscribe topic (agent.py:171-175)."""
         self._check(self.lib.ck_tailcall_plan(self.h, unix_ms, seed))
 
+    def set_bucketing(self, on: bool = True) -> None:
+        """bucket every submitted batch by record length before the walk (topics with mixed record sizes / shapes)"""
+        self._check(self.lib.ck_set_option(self.h, 1, 1 if on else 0))
+
     # ---- aggregation gate on the device (csrc/ck_gate.cuh; reference nodes/agent.py:57-68) ---------------------------
     def gate_create(self, max_entries: int = 1 << 14, max_slots: int | None = None, arena_bytes: int = 256 << 20) -> None:
         self._check(self.lib.ck_gate_create(self.h, max_entries, max_slots if max_slots is not None else 16 * max_entries, arena_bytes))

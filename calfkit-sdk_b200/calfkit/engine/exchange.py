@@ -6,8 +6,8 @@ that a different worker process consumes (calfkit/nodes/base.py:82-87 key=correl
 
 Production path (`PeerExchange`): every rank maps its peers' receive buffers (CUDA IPC over NVSwitch) and
 `ck_exchange_send` plans, packs and transfers in one pass on the device — a warp per forwarded payload stores it straight
-into the owner's region — with no host synchronisation; torch.distributed is used for the one-off handle exchange and for
-two 4-byte barriers per step.  The tensor-level `plan_exchange` / `exchange` below is the device-agnostic statement of the
+into the owner's region — with no host synchronisation and no library collective (the two barriers of a step are flag
+words in peer memory); torch.distributed is used once, for the handle exchange.  The tensor-level `plan_exchange` / `exchange` below is the device-agnostic statement of the
 same plan (CPU tensors under the gloo tests; the kernels are pinned to it on the GPU)."""
 from __future__ import annotations
 
@@ -120,23 +120,14 @@ class PeerExchange:
         dist.all_gather(allh, mine, group=group)
         handles = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
         engine._check(engine.lib.ck_comm_connect(engine.h, handles.ctypes.data))
-        self._token = torch.zeros(1, dtype=torch.int32, device=mine.device)
-        # the barriers must be ordered with the engine's kernels: they are issued with the engine's stream current
-        self._stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=mine.device)
         dist.barrier(group=group)
         _ = C
 
-    def barrier(self) -> None:
-        """4-byte all-reduce ordered on the engine's stream: a device-side barrier, the host does not wait"""
-        with torch.cuda.stream(self._stream):
-            dist.all_reduce(self._token, group=self.group)
-
     def send(self, step: int) -> None:
-        """forward the foreign-partition payloads of the engine's current plan.  Stream-ordered, asynchronous:
-        barrier (peers have consumed last step's regions) -> ck_exchange_send -> barrier (all stores have landed)."""
-        self.barrier()
+        """forward the foreign-partition payloads of the engine's current plan.  Stream-ordered, asynchronous, no library
+        collective: plan -> flag barrier (peers have consumed last step's regions) -> P2P stores -> flag barrier (landed).
+        `step` must increase by one on every call of this exchange, on every rank."""
         self.engine._check(self.engine.lib.ck_exchange_send(self.engine.h, step))
-        self.barrier()
 
     def received(self, step: int | None = None):
         """[(source rank, meta records, payload bytes)] for every other rank; raises if a sender overflowed a region"""

@@ -42,7 +42,7 @@ struct ck_handle {
     unsigned long long region_stride = 0, region_data_cap = 0; u32* d_x_overflow = nullptr; bool comm_ready = false;
     // publish grouping (allocated on first use)
     u32 *d_g_hist = nullptr, *d_g_o1 = nullptr, *d_g_o2 = nullptr, *d_g_keys = nullptr; long long* d_g_base = nullptr; unsigned long long *d_g_tile = nullptr, *d_g_grand = nullptr;
-    bool grouped = false;
+    bool grouped = false; bool opt_bucket = false; const u32* cur_perm = nullptr;
     // Kafka record-batch framing (allocated on first use)
     long long *d_rb_batch_off = nullptr, *d_rb_rec_pos = nullptr, *d_rb_key_off = nullptr, *d_rb_corr_off = nullptr, *d_rb_rec_off = nullptr, *d_rb_frame_len = nullptr;
     u32 *d_rb_rec_base = nullptr, *d_rb_batch_bad = nullptr, *d_rb_rec_batch = nullptr, *d_rb_val_len = nullptr, *d_rb_rec_bad = nullptr, *d_rb_idx = nullptr, *d_rb_sizes = nullptr, *d_rb_partial = nullptr;
@@ -253,12 +253,54 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
 
 static ck_view view_of(ck_handle* h) {
     ck_view v; v.in = h->cur_in; v.off = h->cur_in_off; v.ovl = h->d_ovl; v.ovl_off = h->d_ovl_off; v.ovl_len = h->d_ovl_len;
-    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list; v.len = h->cur_len; v.long_list = h->d_long_list;
+    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list; v.len = h->cur_len; v.long_list = h->d_long_list; v.perm = h->cur_perm;
     return v;
 }
 
 static int run_scan(ck_handle* h, const u32* len, u32 n, long long* out_off, u32 pad,
                     unsigned long long* tile_sum = nullptr, unsigned long long* grand = nullptr);
+
+static int group_alloc(ck_handle* h) {
+    u32 nb_max = (h->max_pubs + CK_G_BLOCK - 1) / CK_G_BLOCK;
+    if (!h->d_g_hist) {
+        size_t nh = 64 * (size_t)nb_max;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_hist, sizeof(u32) * nh));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_base, sizeof(long long) * (nh + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_o1, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_o2, sizeof(u32) * ((size_t)h->max_pubs + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_keys, sizeof(u32) * CK_G_KEYS));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_tile, sizeof(unsigned long long) * (nh / CK_SCAN_TILE + 2)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_grand, sizeof(unsigned long long)));
+    }
+    return 0;
+}
+
+// stable two-pass radix sort of indices 0..n-1 by a 12-bit key -> d_g_o2 (and per-key counts in d_g_keys)
+template <class KeyFn>
+static int group_sort(ck_handle* h, KeyFn keyf, u32 n, int timer) {
+    CUDA_TRY(h, cudaMemsetAsync(h->d_g_keys, 0, sizeof(u32) * CK_G_KEYS, h->stream));
+    if (!n) return 0;
+    u32 nb = (n + CK_G_BLOCK - 1) / CK_G_BLOCK;
+    {
+        KTimer t(h, timer);
+        CKL(h) ck_group_count_kernel<0, KeyFn><<<nb, CK_G_BLOCK, 0, h->stream>>>(keyf, nullptr, n, h->d_g_hist, h->d_g_keys);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_g_hist, 64 * nb, h->d_g_base, 0, h->d_g_tile, h->d_g_grand)) return 1;
+    {
+        KTimer t(h, timer);
+        CKL(h) ck_group_scatter_kernel<0, KeyFn><<<nb, CK_G_BLOCK, 0, h->stream>>>(keyf, nullptr, n, h->d_g_base, h->d_g_o1);
+        CKL(h) ck_group_count_kernel<6, KeyFn><<<nb, CK_G_BLOCK, 0, h->stream>>>(keyf, h->d_g_o1, n, h->d_g_hist, h->d_g_keys);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (run_scan(h, h->d_g_hist, 64 * nb, h->d_g_base, 0, h->d_g_tile, h->d_g_grand)) return 1;
+    {
+        KTimer t(h, timer);
+        CKL(h) ck_group_scatter_kernel<6, KeyFn><<<nb, CK_G_BLOCK, 0, h->stream>>>(keyf, h->d_g_o1, n, h->d_g_base, h->d_g_o2);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return 0;
+}
 
 // decode = walk every submitted record; re-emit the ones that are valid but not canonical into the overlay
 // (count -> scan -> write) and walk those again in their canonical spelling
@@ -270,6 +312,14 @@ static int launch_decode(ck_handle* h) {
     ck_view v = view_of(h);
     CUDA_TRY(h, cudaMemsetAsync(h->d_ovl_off, 0xff, sizeof(long long) * (size_t)n, h->stream));      // no overlays yet
     CUDA_TRY(h, cudaMemsetAsync(h->d_canon_ctl, 0, sizeof(ck_canon_ctl), h->stream));
+    h->cur_perm = nullptr;
+    if (h->opt_bucket && n > 64) {
+        if (group_alloc(h)) return 1;
+        ck_key_len kf; kf.v = v;
+        if (group_sort(h, kf, n, CK_K_WALK)) return 1;
+        h->cur_perm = h->d_g_o2;
+        v = view_of(h);
+    }
     {
         KTimer t(h, CK_K_WALK);
         if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
@@ -549,41 +599,18 @@ extern "C" int ck_fanout_plan(ck_handle* h, uint64_t unix_ms, uint64_t seed, uin
 // ---- grouping the publish table by topic (csrc/ck_group.cuh) ---------------------------------------------------------------
 extern "C" int ck_group_publishes(ck_handle* h) {
     cudaSetDevice(h->device);
-    u32 nb_max = (h->max_pubs + CK_G_BLOCK - 1) / CK_G_BLOCK;
-    if (!h->d_g_hist) {
-        size_t nh = 64 * (size_t)nb_max;
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_hist, sizeof(u32) * nh));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_base, sizeof(long long) * (nh + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_o1, sizeof(u32) * ((size_t)h->max_pubs + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_o2, sizeof(u32) * ((size_t)h->max_pubs + 1)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_keys, sizeof(u32) * CK_G_KEYS));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_tile, sizeof(unsigned long long) * (nh / CK_SCAN_TILE + 2)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_g_grand, sizeof(unsigned long long)));
-    }
-    u32 n = h->n_pubs;
+    if (group_alloc(h)) return 1;
     h->grouped = true;
-    CUDA_TRY(h, cudaMemsetAsync(h->d_g_keys, 0, sizeof(u32) * CK_G_KEYS, h->stream));
-    if (!n) return 0;
-    u32 nb = (n + CK_G_BLOCK - 1) / CK_G_BLOCK;
-    {
-        KTimer t(h, CK_K_ROUTE);
-        CKL(h) ck_group_count_kernel<0><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, nullptr, n, h->d_g_hist, h->d_g_keys);
-        CUDA_TRY(h, cudaGetLastError());
-    }
-    if (run_scan(h, h->d_g_hist, 64 * nb, h->d_g_base, 0, h->d_g_tile, h->d_g_grand)) return 1;
-    {
-        KTimer t(h, CK_K_ROUTE);
-        CKL(h) ck_group_scatter_kernel<0><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, nullptr, n, h->d_g_base, h->d_g_o1);
-        CKL(h) ck_group_count_kernel<6><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, h->d_g_o1, n, h->d_g_hist, h->d_g_keys);
-        CUDA_TRY(h, cudaGetLastError());
-    }
-    if (run_scan(h, h->d_g_hist, 64 * nb, h->d_g_base, 0, h->d_g_tile, h->d_g_grand)) return 1;
-    {
-        KTimer t(h, CK_K_ROUTE);
-        CKL(h) ck_group_scatter_kernel<6><<<nb, CK_G_BLOCK, 0, h->stream>>>(h->d_pubs, h->d_g_o1, n, h->d_g_base, h->d_g_o2);
-        CUDA_TRY(h, cudaGetLastError());
-    }
-    return 0;
+    ck_key_pub kf; kf.pubs = h->d_pubs;
+    return group_sort(h, kf, h->n_pubs, CK_K_ROUTE);
+}
+
+// engine options.  CK_OPT_BUCKET (1): bucket every submitted batch by record length before the thread-per-record walk —
+// for topics that carry records of mixed sizes / shapes (a warp takes as long as its longest record, and lanes on
+// different schema branches run one after the other); homogeneous batches do not need it (it costs six small launches).
+extern "C" int ck_set_option(ck_handle* h, uint32_t option, uint64_t value) {
+    if (option == 1) { h->opt_bucket = value != 0; return 0; }
+    return fail(h, "ck_set_option: unknown option");
 }
 
 // order[n_publishes]: publish indices grouped by key (0 = unregistered topic, 1 + id = registered topic id, 4095 = unused
@@ -826,10 +853,10 @@ extern "C" int ck_comm_create(ck_handle* h, uint32_t rank, uint32_t world, uint3
     h->comm_rank = rank; h->comm_world = world; h->max_fwd = max_fwd;
     h->region_data_cap = (data_cap + 15) & ~15ull;
     h->region_stride = (CK_X_HDR + (unsigned long long)max_fwd * sizeof(ck_xmeta) + h->region_data_cap + 255) & ~255ull;
-    CUDA_TRY(h, cudaMalloc((void**)&h->d_recv, h->region_stride * world + CK_PAD));
-    CUDA_TRY(h, cudaMemset(h->d_recv, 0, h->region_stride * world));
-    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_overflow, sizeof(u32) * CK_X_MAXWORLD));
-    CUDA_TRY(h, cudaMemset(h->d_x_overflow, 0, sizeof(u32) * CK_X_MAXWORLD));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_recv, h->region_stride * world + CK_X_FLAGS_BYTES + CK_PAD));
+    CUDA_TRY(h, cudaMemset(h->d_recv, 0, h->region_stride * world + CK_X_FLAGS_BYTES));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_x_overflow, sizeof(u32) * (CK_X_MAXWORLD + 1)));
+    CUDA_TRY(h, cudaMemset(h->d_x_overflow, 0, sizeof(u32) * (CK_X_MAXWORLD + 1)));     // [world]: barrier timeout flag
     cudaIpcMemHandle_t ih;
     CUDA_TRY(h, cudaIpcGetMemHandle(&ih, h->d_recv));
     memcpy(ipc_handle_out, &ih, 64);
@@ -902,11 +929,16 @@ static int exchange_send_on_stream(ck_handle* h, uint64_t step) {
     // byte offsets of the (16-byte padded) payloads in destination order; scanned over all publish slots so that the
     // launch does not need the selected count on the host (unselected tail entries are zero)
     if (run_scan(h, h->d_x_len32, npubs ? npubs : 1, h->d_x_dst_off, 15, h->d_x_tile, h->d_x_grand2)) return 1;
+    unsigned long long flags_off = h->region_stride * world;
     {
         KTimer t(h, CK_K_EMIT);
-        if (npubs) CKL(h) ck_xsend_kernel<<<(npubs + 7) / 8, 256, 0, h->stream>>>(h->d_pubs, h->d_x_pub, h->d_x_src_off, h->d_x_len32, h->d_x_dst_off, h->d_x_base, nb,
+        // barrier 1: every peer has consumed what it received last time (its own stream order puts that before this point)
+        CKL(h) ck_xbarrier_kernel<<<1, 32, 0, h->stream>>>(h->peers, rank, world, flags_off, 0, step, h->d_x_overflow + CK_X_MAXWORLD);
+        if (npubs) CKL(h) ck_xsend_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_pubs, h->d_x_pub, h->d_x_src_off, h->d_x_len32, h->d_x_dst_off, h->d_x_base, nb,
             h->d_x_grand, h->d_out, h->peers, rank, world, h->region_stride, h->max_fwd, h->region_data_cap, h->d_x_overflow);
         CKL(h) ck_xhdr_kernel<<<1, 32, 0, h->stream>>>(h->d_x_dst_off, h->d_x_base, nb, h->d_x_grand, h->peers, rank, world, h->region_stride, step, h->d_x_overflow);
+        // barrier 2: everybody's stores (to everybody) have landed
+        CKL(h) ck_xbarrier_kernel<<<1, 32, 0, h->stream>>>(h->peers, rank, world, flags_off, 1, step, h->d_x_overflow + CK_X_MAXWORLD);
         CUDA_TRY(h, cudaGetLastError());
     }
     return 0;
@@ -930,6 +962,7 @@ extern "C" int ck_fetch_received(ck_handle* h, uint32_t src, uint64_t* hdr4 /* s
     CUDA_TRY(h, cudaMemcpyAsync(&hd, region, sizeof hd, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     hdr4[0] = hd.step; hdr4[1] = hd.count; hdr4[2] = hd.overflow; hdr4[3] = hd.nbytes;
+    { u32 to = 0; CUDA_TRY(h, cudaMemcpy(&to, h->d_x_overflow + CK_X_MAXWORLD, sizeof to, cudaMemcpyDeviceToHost)); if (to) return fail(h, "exchange barrier timed out: a peer did not arrive"); }
     if (hd.nbytes > data_cap) return fail(h, "ck_fetch_received: host buffer too small");
     if (host_meta && hd.count) CUDA_TRY(h, cudaMemcpyAsync(host_meta, region + CK_X_HDR, sizeof(ck_xmeta) * (size_t)hd.count, cudaMemcpyDeviceToHost, h->stream));
     if (host_data && hd.nbytes) CUDA_TRY(h, cudaMemcpyAsync(host_data, region + CK_X_HDR + (size_t)h->max_fwd * sizeof(ck_xmeta), hd.nbytes, cudaMemcpyDeviceToHost, h->stream));

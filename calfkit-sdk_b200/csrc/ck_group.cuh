@@ -24,17 +24,27 @@ __device__ __forceinline__ u32 ck_group_key(const ck_pub& p) {
     return k < CK_G_KEYS - 2 ? k : CK_G_KEYS - 2;
 }
 
+// key functors: the publish table by destination topic; the records of a batch by length (32-byte classes) — the second
+// one buckets a heterogeneous batch before the thread-per-record walk: lanes of a warp then walk records of one size class
+// (a warp takes as long as its longest record) and, since a topic's records of one size mostly share a shape, of one shape
+// (lanes on different schema branches execute one after the other)
+struct ck_key_pub { const ck_pub* pubs; __device__ __forceinline__ u32 operator()(u32 i) const { return ck_group_key(pubs[i]); } };
+struct ck_key_len {
+    ck_view v;
+    __device__ __forceinline__ u32 operator()(u32 i) const { u32 len; ck_rec_in(v, i, len); u32 k = len >> 5; return k < CK_G_KEYS - 1 ? k : CK_G_KEYS - 1; }
+};
+
 // pass over `in` (NULL = identity order): digit histogram per block -> hist[digit][block]; pass 0 also counts whole keys
-template <int SHIFT>
+template <int SHIFT, class KeyFn>
 __global__ void __launch_bounds__(CK_G_BLOCK)
-ck_group_count_kernel(const ck_pub* __restrict__ pubs, const u32* __restrict__ in, u32 n, u32* __restrict__ hist, u32* __restrict__ key_hist) {
+ck_group_count_kernel(KeyFn keyf, const u32* __restrict__ in, u32 n, u32* __restrict__ hist, u32* __restrict__ key_hist) {
     __shared__ u32 s_cnt[64];
     if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = j < n;
     u32 key = 0;
-    if (live) { key = ck_group_key(pubs[in ? in[j] : j]); atomicAdd(&s_cnt[(key >> SHIFT) & 63u], 1u); }
+    if (live) { key = keyf(in ? in[j] : j); atomicAdd(&s_cnt[(key >> SHIFT) & 63u], 1u); }
     if (SHIFT == 0) {
         u32 act = __ballot_sync(0xffffffffu, live);
         if (live) {
@@ -46,9 +56,9 @@ ck_group_count_kernel(const ck_pub* __restrict__ pubs, const u32* __restrict__ i
     if (threadIdx.x < 64) hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-template <int SHIFT>
+template <int SHIFT, class KeyFn>
 __global__ void __launch_bounds__(CK_G_BLOCK)
-ck_group_scatter_kernel(const ck_pub* __restrict__ pubs, const u32* __restrict__ in, u32 n, const long long* __restrict__ base, u32* __restrict__ out) {
+ck_group_scatter_kernel(KeyFn keyf, const u32* __restrict__ in, u32 n, const long long* __restrict__ base, u32* __restrict__ out) {
     __shared__ u32 s_w[CK_G_BLOCK / 32][64];
     u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 k = threadIdx.x; k < (CK_G_BLOCK / 32) * 64; k += CK_G_BLOCK) (&s_w[0][0])[k] = 0;
@@ -56,7 +66,7 @@ ck_group_scatter_kernel(const ck_pub* __restrict__ pubs, const u32* __restrict__
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = j < n;
     u32 idx = 0, digit = 0, rank_in_warp = 0;
-    if (live) { idx = in ? in[j] : j; digit = (ck_group_key(pubs[idx]) >> SHIFT) & 63u; }
+    if (live) { idx = in ? in[j] : j; digit = (keyf(idx) >> SHIFT) & 63u; }
     u32 act = __ballot_sync(0xffffffffu, live);
     if (live) {
         u32 same = __match_any_sync(act, digit);

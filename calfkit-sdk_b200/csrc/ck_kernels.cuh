@@ -31,6 +31,7 @@ struct ck_view {
     const u8* in; const long long* off;
     const u8* ovl; const long long* ovl_off; const u32* ovl_len;     // ovl_off[i] < 0: record i has no overlay
     ck_canon_ctl* canon_ctl; u32* canon_list;                        // records the walker left to the canonicaliser
+    const u32* perm;                                                 // NULL, or thread t of the walk takes record perm[t] (length-bucketed batch)
     u32* long_list;                                                  // records of CK_LONG_MIN bytes or more: walked one per warp (ck_walk_long.cuh)
     const u32* len;                                                  // NULL: record i = [off[i], off[i+1]); else off[i] .. + len[i]
 };                                                                   //       (values inside raw Kafka record batches are not contiguous)
@@ -100,6 +101,7 @@ template <class R>
 __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (v.perm) i = v.perm[i];                                                                       // bucketed batch: neighbours in a warp are of one size class
     u32 len; const u8* rec;
     if (mode == 0) rec = ck_rec_in(v, i, len);                                                       // the submitted spelling
     else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }                                  // re-walk of canonicalised records

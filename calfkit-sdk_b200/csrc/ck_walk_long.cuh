@@ -111,7 +111,10 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * CK_LONG_WARPS)
+#ifndef CK_LONG_MINB
+#define CK_LONG_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * CK_LONG_WARPS, CK_LONG_MINB)
 ck_walk_long_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride) {
     u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 count = v.canon_ctl->pad;                                   // records the thread-per-record kernel handed over

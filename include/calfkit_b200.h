@@ -69,6 +69,11 @@ int  ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t nparts, c
 int  ck_submit(ck_handle* h, const uint8_t* host_in, const int64_t* host_off, uint32_t n);
 int  ck_submit_device(ck_handle* h, const uint8_t* dev_in, const int64_t* dev_off, uint32_t n);
 
+/* engine options.  option 1 (bucket): value != 0 -> every submitted batch is bucketed by record length (stable radix sort of
+ * the record indices on the device) before the thread-per-record walk, so that the lanes of a warp walk records of one size
+ * class; for topics with mixed sizes / shapes (reference analogue: none — the reference handles one record at a time) */
+int  ck_set_option(ck_handle* h, uint32_t option, uint64_t value);
+
 /* group the publish table of the current plan by destination topic on the device (stable two-pass radix sort over 12-bit
  * keys: 0 = topic without a registered id, 1 + id = registered topic, 4095 = unused slot) — the per-topic split a producer
  * needs (reference: one broker.publish per topic, nodes/base.py:82-87) without any host-side scan of the table.

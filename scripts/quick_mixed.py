@@ -15,6 +15,7 @@ print(f"gen {time.time() - t0:.1f} s, {b.data.nbytes / n:.0f} B/record mean, max
 e = BatchEngine(0, max_records=n, max_in_bytes=b.data.nbytes + 4096)
 e.register_topics(["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"] + [f"agent_{i:03d}.input" for i in range(256)], num_partitions=8)
 e.set_tool_node("tool.get_weather.output", ToolTemplate.from_format("It's sunny in {location}"))
+if os.environ.get("CK_BUCKET", "1") == "1": e.set_bucketing(True)
 d_in = torch.from_numpy(b.data.copy()).cuda(); d_off = torch.from_numpy(b.offsets.copy()).cuda()
 e.profile(True)
 for it in range(4):

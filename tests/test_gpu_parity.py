@@ -617,3 +617,33 @@ def test_codec_goldens_on_device(engine):
         else:
             assert st == (2 if c["first_type"] == "json_invalid" and c["n_errors"] == 1 else 3), (c["name"], st)
     assert set(declined) <= set(DECLARED_UNSUPPORTED), declined
+
+
+def test_length_bucketing_changes_nothing_but_the_schedule(engine):
+    """CK_OPT_BUCKET: the walk takes the records in length order (a permutation built on the device); every column, payload
+    and publish must be identical to the unbucketed run — on a batch that mixes sizes, shapes, invalid and empty records."""
+    from calfkit import synth
+    from calfkit.engine import BatchEngine, ToolTemplate
+    rng = random.Random(3)
+    recs = synth.mixed_events(300, seed=51, hi=30000, n_agents=16) + synth.tool_events(500, seed=52) + \
+        synth.tool_events(100, seed=53, size=None, full_history=True) + [b"", b"{", b'{"context":{}}']
+    recs += [bytes(r[:-3]) for r in recs[:20]] + [b"{ " + r[1:] for r in recs[300:320]]
+    rng.shuffle(recs)
+    b = synth.pack(recs)
+    topics = [f"agent_{k:03d}.input" for k in range(16)] + ["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"]
+    outs = []
+    for bucket in (False, True):
+        e = BatchEngine(0, max_records=2048, max_in_bytes=32 << 20)
+        try:
+            e.register_topics(topics, num_partitions=8)
+            e.set_tool_node("tool.get_weather.output", ToolTemplate.from_format("It's sunny in {location}"))
+            e.set_bucketing(bucket)
+            e.submit(b.data, b.offsets)
+            e.tool_plan()
+            o = e.fetch()
+            outs.append((o.cols.copy(), [(p.topic, p.key, p.payload, p.partition, p.record) for p in o.publishes()]))
+        finally:
+            e.close()
+    ok_rows = outs[0][0][0] == 0
+    assert (outs[0][0][0] == outs[1][0][0]).all() and (outs[0][0][:, ok_rows] == outs[1][0][:, ok_rows]).all()
+    assert outs[0][1] == outs[1][1] and ok_rows.sum() > 900
