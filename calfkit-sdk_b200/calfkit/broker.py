@@ -61,8 +61,9 @@ class _HandlerRef:
 
 
 class MemoryBroker:
-    def __init__(self, *servers: Any, middlewares: list | None = None, **kwargs: Any):
+    def __init__(self, *servers: Any, middlewares: list | None = None, num_partitions: int = 8, **kwargs: Any):
         self.servers, self.kwargs = servers, kwargs
+        self.num_partitions = num_partitions       # partitions per topic (Kafka's default partitioner: murmur2(key) % partitions)
         self._connection: Any = None
         self.queues: dict[str, deque[Record]] = defaultdict(deque)
         self.arenas: dict[str, deque] = defaultdict(deque)            # topic -> deque[Arena]
@@ -124,6 +125,13 @@ class MemoryBroker:
         """split what a GPU lane produced (engine.lane.PublishBatch) over the topics, by index selection"""
         for tid, cnt in batch.topic_counts().items():
             self.produced += cnt
+            if tid < 0 and batch.source is None:
+                # forwarded by another rank without a registered topic id: the name stayed with the source record there.
+                # Workers of one deployment register each other's topics (Worker(route_topics=...)): loud, not silent
+                import logging
+                logging.getLogger(__name__).error("%d forwarded publishes to a topic this worker has no id for: register it via route_topics", cnt)
+                self.dropped_unsubscribed += cnt
+                continue
             if tid < 0:
                 # topics the engine has no id for (another worker's node, a client's private reply topic): the kernel left
                 # the FNV-1a of the name in `pad`, so they are grouped vectorised and the name is decoded once per group

@@ -236,23 +236,46 @@ class PublishBatch:
 _FAST_COLS = np.asarray([COL["STATUS"], COL["ACTION"], COL["CORR_OFF"], COL["CORR_LEN"]], dtype=np.uint32)
 
 
+def received_batch(meta: np.ndarray, data: np.ndarray, topic_names: dict[int, str]) -> "PublishBatch":
+    """a region another rank wrote into this rank's receive buffer, as a PublishBatch (payload i = forwarded payload i; its
+    topic id and partition travelled with it; the key — the correlation id — is inside the payload and not needed to route)"""
+    n = len(meta)
+    lens = meta["len"].astype(np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum((lens + 15) & ~15, out=off[1:])
+    pubs = np.zeros(n, dtype=PUB_DTYPE)
+    pubs["payload"] = np.arange(n, dtype=np.uint32)
+    pubs["topic_id"], pubs["partition"], pubs["record"], pubs["has_key"] = meta["topic_id"], meta["partition"], np.arange(n, dtype=np.uint32), 0
+    return PublishBatch(data, off, meta["len"].astype(np.uint32), pubs, topic_names, None, None, None, None)
+
+
 class Lane:
     """one engine + its pinned landing buffers; `submit` is asynchronous (H2D + all kernels queued on the engine's
     stream), `collect` copies the results back and hands them out as a PublishBatch that owns its buffers"""
     def __init__(self, device: int, configure: Callable[[BatchEngine], None], pool: PinnedPool, *, max_records: int,
-                 max_in_bytes: int, max_out_bytes: int | None = None):
+                 max_in_bytes: int, max_out_bytes: int | None = None, exchange: tuple[int, int] | None = None):
         self.eng = BatchEngine(device, max_records=max_records, max_in_bytes=max_in_bytes, max_out_bytes=max_out_bytes)
         configure(self.eng)
         self.pool, self.max_records, self.max_in = pool, max_records, max_in_bytes
         self.arena: Arena | None = None
         self.busy = self.collecting = False
         self.d2h_bytes = 0
+        # one process per GPU, records sharded by Kafka partition: keyed publishes whose partition another rank owns are
+        # stored straight into that rank's receive buffer (engine/exchange.py); what arrives here is produced here
+        self.px, self.step_no = None, 0
+        if exchange is not None and exchange[1] > 1:
+            from calfkit.engine.exchange import PeerExchange
+            rank, world = exchange
+            self.px = PeerExchange(self.eng, rank, world, max_fwd=max_records, data_cap=max_in_bytes + 64 * max_records)
 
     def submit(self, arena: Arena) -> None:
-        """device-template tool node: decode + plan + encode + route, all asynchronous"""
+        """device-template tool node: decode + plan + encode + route (+ forward to the owning ranks), all asynchronous"""
         self.arena, self.busy = arena, True
         self.eng.submit(arena.data, arena.offsets)
         self.eng.tool_plan()
+        if self.px is not None:
+            self.step_no += 1
+            self.px.send(self.step_no)
 
     def start_collect(self) -> None:
         """queue the D2H of this lane's results into fresh landing buffers (waits only for the lane's own kernels to know
@@ -290,6 +313,11 @@ class Lane:
         overlay = eng.overlay() if listed.value else None       # rare: some records arrived in a non-canonical spelling
         arena, self.arena, self.busy, self.collecting = self.arena, None, False, False
         self._views = self._b_out = self._b_meta = None
+        self.received = []
+        if self.px is not None:       # what the other ranks forwarded to this one during this step
+            for _src, meta, data in self.px.received(self.step_no):
+                if len(meta):
+                    self.received.append(received_batch(meta, data, eng.topic_names))
 
         def done():
             pool.give(b_out)
@@ -312,10 +340,11 @@ class LanePipeline:
     drain() flushes.  With K = 3 a lane's D2H starts a full step after its kernels were queued: both PCIe directions and
     the SMs overlap (measured: bench.py e2e)."""
     def __init__(self, device: int, configure: Callable[[BatchEngine], None], *, lanes: int = 3, max_records: int, max_in_bytes: int,
-                 max_out_bytes: int | None = None, pool: PinnedPool | None = None):
+                 max_out_bytes: int | None = None, pool: PinnedPool | None = None, exchange: tuple[int, int] | None = None):
         self.pool = pool or PinnedPool()
-        self.lanes = [Lane(device, configure, self.pool, max_records=max_records, max_in_bytes=max_in_bytes, max_out_bytes=max_out_bytes)
-                      for _ in range(lanes)]
+        self.lanes = [Lane(device, configure, self.pool, max_records=max_records, max_in_bytes=max_in_bytes, max_out_bytes=max_out_bytes,
+                           exchange=exchange) for _ in range(lanes)]
+        self.received: list[PublishBatch] = []           # batches other ranks forwarded here, collected with the last results
         self._k = 0
         self._inflight: list[Lane] = []
 
@@ -329,23 +358,39 @@ class LanePipeline:
         self._inflight.append(lane)
         ready = None
         if self._inflight[0].collecting:
-            ready = self._inflight.pop(0).finish_collect()
+            lane0 = self._inflight.pop(0)
+            ready = lane0.finish_collect()
+            self.received += lane0.received
         if len(self._inflight) >= len(self.lanes) - 1 and not self._inflight[0].collecting:
             self._inflight[0].start_collect()
         return ready
 
     def drain(self) -> Iterator[PublishBatch]:
         while self._inflight:
-            yield self._inflight.pop(0).collect()
+            lane0 = self._inflight.pop(0)
+            batch = lane0.collect()
+            self.received += lane0.received
+            yield batch
+
+    def take_received(self) -> list[PublishBatch]:
+        out, self.received = self.received, []
+        return out
 
     @property
     def pending(self) -> int:
         return len(self._inflight)
 
+    @property
+    def pending_records(self) -> int:
+        """records of the steps still in flight (lockstep ticks of an idle rank carry empty batches)"""
+        return sum(l.arena.n for l in self._inflight if l.arena is not None)
+
     def launch_count(self) -> int:
         return sum(l.eng.launch_count() for l in self.lanes)
 
     def close(self) -> None:
+        for l in self.lanes:
+            l.px = None
         for l in self.lanes:
             l.close()
         self.pool.close()

@@ -32,6 +32,11 @@ from calfkit.nodes import BaseNodeDef
 logger = logging.getLogger(__name__)
 
 
+def _EMPTY_ARENA():
+    from calfkit.engine.lane import Arena
+    return Arena(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64))
+
+
 def engine_for(node: BaseNodeDef, *, device: int = 0, max_records: int = 1 << 14, max_in_bytes: int = 64 << 20,
                extra_topics: list[str] | None = None) -> BatchEngine:
     """lazily created, per-node engine (also used by the object-level BaseNodeDef.handler)"""
@@ -53,12 +58,17 @@ class Worker:
                  group_id: str | None = None, extra_publish_kwargs: dict[str, Any] | None = None,
                  extra_subscribe_kwargs: dict[str, Any] | None = None, *, device: int | None = None,
                  batch_records: int = 1 << 14, batch_bytes: int = 64 << 20, lanes: int = 3,
-                 route_topics: list[str] | None = None):
+                 route_topics: list[str] | None = None, rank: int | None = None, world: int | None = None):
         """Reference signature (worker/worker.py:13-31) plus keyword-only engine knobs: `device` (default: LOCAL_RANK of a
         one-process-per-GPU launch, else 0), the batch bounds a poll honours (records AND bytes: a batch never exceeds what
         the engines were sized for), the number of pipelined lanes per device-template node, and `route_topics`: names of
         topics owned by OTHER workers that this worker's outputs go to (agents' input topics ...) so that the device resolves
-        them to ids too; names it does not know are still routed, grouped by hash on the host."""
+        them to ids too; names it does not know are still routed, grouped by hash on the host.
+        `rank` / `world` (default: torch.distributed's, when initialised): one worker process per GPU, records sharded by Kafka
+        partition (reference: consumer-group sharding, worker/worker.py:38,47, with every hop keyed by correlation_id,
+        nodes/base.py:86,103,117,134).  A keyed publish whose partition (murmur2(key) % partitions) is owned by another rank
+        (partition % world) is stored straight into that rank's receive buffer over NVLink and produced THERE; all ranks
+        tick in lockstep (an idle rank submits an empty batch) so that the per-step barriers of the exchange match."""
         self._client = client
         self._nodes = nodes or list()
         self._max_workers = max_workers
@@ -71,6 +81,14 @@ class Worker:
         self._batch_bytes = batch_bytes
         self._lanes = lanes
         self._route_topics = list(route_topics or [])
+        if rank is None or world is None:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank, world = dist.get_rank(), dist.get_world_size()
+            except ImportError:
+                pass
+        self._rank, self._world = (rank or 0), (world or 1)
         self._subs: list[tuple[BaseNodeDef, Any]] = []
         self._pipes: dict[int, LanePipeline] = {}
         self.stats = {"records": 0, "publishes": 0, "rejected": 0, "raises": 0, "host_fallback": 0, "steps": 0}
@@ -102,13 +120,16 @@ class Worker:
                 eng.register_topics(topics, num_partitions=getattr(self._client._connection, "num_partitions", 0))
                 node.configure_engine(eng)
             pipe = LanePipeline(self._device, configure, lanes=self._lanes, max_records=self._batch_records,
-                                max_in_bytes=self._batch_bytes)
+                                max_in_bytes=self._batch_bytes, exchange=(self._rank, self._world) if self._world > 1 else None)
             self._pipes[id(node)] = pipe
         return pipe
 
     def _produce_fast(self, node: BaseNodeDef, batch: PublishBatch) -> None:
         broker = self._client._connection
         n = batch.source.n
+        if n == 0:
+            batch.release()
+            return
         self.stats["records"] += n
         bad = batch.status != CK_OK
         nbad = int(np.count_nonzero(bad))
@@ -154,15 +175,19 @@ class Worker:
             if getattr(node, "_template", None) is not None:
                 pipe = self._pipeline(node)
                 arena = broker.poll_arena(sub.topics, self._batch_records, self._batch_bytes)
+                if arena is None and self._world > 1:
+                    arena = _EMPTY_ARENA()                     # lockstep: every rank runs the exchange on every tick
                 if arena is not None:
                     consumed += arena.n
                     done = pipe.push(arena)
                     if done is not None:
                         self._produce_fast(node, done)
-                elif pipe.pending:                             # input idle: flush what is in flight
+                elif pipe.pending:                             # input idle (single rank): flush what is in flight
                     for done in pipe.drain():
-                        consumed += 1                          # keeps run(until_idle) going until the outputs are produced
                         self._produce_fast(node, done)
+                for rb in pipe.take_received():                # forwarded here by the owners of other partitions' inputs
+                    self.stats["received"] = self.stats.get("received", 0) + rb.n_publishes
+                    broker.produce_publishes(rb)
                 continue
             records: list[Record] = broker.poll_batch(sub.topics, self._batch_records, self._batch_bytes)
             if not records:
@@ -176,6 +201,16 @@ class Worker:
             pipe.close()
         self._pipes.clear()
 
+    def _all_idle(self, n: int) -> bool:
+        """N > 1: the ranks stop together — a rank with nothing to do still has to run the exchange for the others"""
+        if self._world == 1:
+            return n == 0
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([n], dtype=torch.int64, device=torch.device("cuda", self._device))
+        dist.all_reduce(t)
+        return int(t.item()) == 0
+
     async def run(self, *, until_idle: bool = False, idle_sleep: float = 0.001, **extra_run_args: Any) -> None:
         """Run the worker as a service (reference: blocks in FastStream(...).run()); `until_idle=True`
         returns once every subscribed topic is drained — used by tests and the config-1 example."""
@@ -188,8 +223,15 @@ class Worker:
         while True:
             n = self.step()
             n += await self._client._dispatcher.drain(broker) if hasattr(self._client, "_dispatcher") else 0
-            if n == 0:
+            if self._all_idle(n + sum(p.pending_records for p in self._pipes.values())):
                 if until_idle:
+                    for node, _sub in self._subs:          # nothing in flight on any rank: flush (no exchange involved)
+                        pipe = self._pipes.get(id(node))
+                        if pipe is not None:
+                            for done in pipe.drain():
+                                self._produce_fast(node, done)
+                            for rb in pipe.take_received():
+                                broker.produce_publishes(rb)
                     return
                 await asyncio.sleep(idle_sleep)
             else:

@@ -601,7 +601,7 @@ extern "C" int ck_group_publishes(ck_handle* h) {
     cudaSetDevice(h->device);
     if (group_alloc(h)) return 1;
     h->grouped = true;
-    ck_key_pub kf; kf.pubs = h->d_pubs;
+    ck_key_pub kf; kf.pubs = h->d_pubs; kf.rank = h->comm_rank; kf.world = h->comm_ready ? h->comm_world : 1;
     return group_sort(h, kf, h->n_pubs, CK_K_ROUTE);
 }
 

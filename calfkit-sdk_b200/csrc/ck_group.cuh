@@ -28,7 +28,14 @@ __device__ __forceinline__ u32 ck_group_key(const ck_pub& p) {
 // one buckets a heterogeneous batch before the thread-per-record walk: lanes of a warp then walk records of one size class
 // (a warp takes as long as its longest record) and, since a topic's records of one size mostly share a shape, of one shape
 // (lanes on different schema branches execute one after the other)
-struct ck_key_pub { const ck_pub* pubs; __device__ __forceinline__ u32 operator()(u32 i) const { return ck_group_key(pubs[i]); } };
+struct ck_key_pub {
+    const ck_pub* pubs; u32 rank, world;        // world > 1: keyed publishes whose partition another rank owns were forwarded (ck_exchange_send): not produced here
+    __device__ __forceinline__ u32 operator()(u32 i) const {
+        ck_pub p = pubs[i];
+        if (world > 1 && p.payload != 0xffffffffu && p.has_key == 1 && p.partition >= 0 && (u32)p.partition % world != rank) return CK_G_KEYS - 1;
+        return ck_group_key(p);
+    }
+};
 struct ck_key_len {
     ck_view v;
     __device__ __forceinline__ u32 operator()(u32 i) const { u32 len; ck_rec_in(v, i, len); u32 k = len >> 5; return k < CK_G_KEYS - 1 ? k : CK_G_KEYS - 1; }
