@@ -112,6 +112,11 @@ class PeerExchange:
         import ctypes as C
         import numpy as np
         self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        # every rank addresses its region inside a PEER's buffer with its own geometry: the geometry must be the same
+        # everywhere, so the ranks agree on the largest request before anything is allocated
+        geo = torch.tensor([max_fwd, data_cap], dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(geo, op=dist.ReduceOp.MAX, group=group)
+        max_fwd, data_cap = int(geo[0].item()), int(geo[1].item())
         self.max_fwd, self.data_cap = max_fwd, data_cap
         handle = np.zeros(64, dtype=np.uint8)
         engine._check(engine.lib.ck_comm_create(engine.h, rank, world, max_fwd, data_cap, handle.ctypes.data))

@@ -151,7 +151,8 @@ int  ck_gate_reset(ck_handle* h);
 /* cross-partition forward over NVLink peer memory (records shard by Kafka partition across the GPUs of a box; reference
  * analogue: producing to a topic-partition another worker process consumes, nodes/base.py:82-87 key=correlation_id).
  *   ck_comm_create    this rank's receive buffer: one region per source rank (max_fwd payloads, data_cap bytes each);
- *                     ipc_handle_out[64] is handed to every peer (any side channel)
+ *                     ipc_handle_out[64] is handed to every peer (any side channel); max_fwd and data_cap MUST be the same
+ *                     on every rank (a rank addresses its region inside a peer's buffer with its own geometry)
  *   ck_comm_connect   handles[world][64] in rank order: maps the peers' receive buffers (CUDA IPC, same box)
  *   ck_exchange_send  plan + pack + transfer in one pass on the handle's stream, no host synchronisation: the keyed
  *                     publishes of the current plan whose partition % world != rank are written straight into the owner's
