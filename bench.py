@@ -1016,7 +1016,10 @@ def main() -> None:
     w_value = world * n / (w_ms / 1e3)
     w_launches = sum(p_.launch_count() for p_ in worker._pipes.values()) - w_l0
     w_d2h = max(l_.d2h_bytes for p_ in worker._pipes.values() for l_ in p_.lanes)
-    w_ok = (w_cnt["pubs"] == 2 * n * w_steps) and worker.stats["rejected"] == 0
+    tw = torch.tensor([w_cnt["pubs"], worker.stats["rejected"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw)                      # a forwarded publish is produced (and counted) by the rank that owns its partition
+    w_ok = int(tw[0].item()) == world * 2 * n * w_steps and int(tw[1].item()) == 0
     worker.close()
 
     def shutdown():
@@ -1107,7 +1110,7 @@ def main() -> None:
         "e2e": {"value": w_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes + 8 * (n + 1), "d2h_bytes_per_step": w_d2h,
                 "ms_per_step": w_ms, "steps": w_steps, "gpu_launches": w_launches, "all_publishes_seen_by_sinks": w_ok,
                 "api": "calfkit.Worker.run(until_idle=True): MemoryBroker.poll_arena (pinned batch) -> LanePipeline (3 lanes) -> "
-                       "MemoryBroker.produce_publishes -> per-topic sinks; no exchange step inside Worker yet (N > 1: ranks run independent shards)",
+                       "MemoryBroker.produce_publishes -> per-topic sinks; N > 1: one Worker per GPU, keyed publishes forwarded to the rank that owns their partition inside Worker.run",
                 "timing": "host wall clock around Worker.run, synchronised on both sides, max over ranks",
                 "ceiling": ceiling, "frac_of_ceiling": w_value / ceiling["events_per_s"],
                 "engine_level": {"value": e2e_value, "ms_per_step": e2e_ms, "steps": e2e_steps, "d2h_bytes_per_step": d2h_bytes[0],

@@ -42,7 +42,7 @@ EXPORTS = ["ck_create", "ck_destroy", "ck_last_error", "ck_version", "ck_registe
            "ck_device_buffers", "ck_device_buffers2", "ck_gather_spans", "ck_profile", "ck_profile_read", "ck_fetch_cols",
            "ck_host_alloc", "ck_host_free", "ck_canon_stats", "ck_fetch_output_async",
            "ck_fetch_cols_async", "ck_gate_create", "ck_gate_register", "ck_gate_arrive", "ck_gate_stats", "ck_gate_reset", "ck_submit_recordbatch",
-           "ck_fetch_rb_index", "ck_encode_recordbatch", "ck_group_publishes", "ck_fetch_groups", "ck_comm_create", "ck_comm_connect", "ck_exchange_send", "ck_recv_info", "ck_fetch_received", "ck_set_option"]
+           "ck_fetch_rb_index", "ck_encode_recordbatch", "ck_group_publishes", "ck_fetch_groups", "ck_comm_create", "ck_comm_connect", "ck_exchange_send", "ck_recv_info", "ck_fetch_received", "ck_peek_received", "ck_fetch_received_async", "ck_set_option"]
 
 _lib = None
 
@@ -95,6 +95,8 @@ def load() -> C.CDLL:
         "ck_exchange_send": (C.c_int, [vp, C.c_uint64]),
         "ck_recv_info": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
         "ck_fetch_received": (C.c_int, [vp, C.c_uint32, vp, u8p, u8p, C.c_uint64]),
+        "ck_peek_received": (C.c_int, [vp, vp]),
+        "ck_fetch_received_async": (C.c_int, [vp, C.c_uint32, C.c_uint64, C.c_uint64, u8p, u8p]),
         "ck_set_option": (C.c_int, [vp, C.c_uint32, C.c_uint64]),
         "ck_group_publishes": (C.c_int, [vp]),
         "ck_fetch_groups": (C.c_int, [vp, u32p, u32p, C.c_int]),

@@ -152,6 +152,18 @@ class PeerExchange:
             out.append((src, meta[:int(hdr[1])], data[:int(hdr[3])]))
         return out
 
+    def peek(self):
+        """[world, 4] uint64 region headers (step, count, overflow, nbytes) — one stream synchronisation"""
+        import numpy as np
+        hdr = np.zeros((self.world, 4), dtype=np.uint64)
+        self.engine._check(self.engine.lib.ck_peek_received(self.engine.h, hdr.ctypes.data))
+        return hdr
+
+    def fetch_async(self, src: int, count: int, nbytes: int, meta, data) -> None:
+        """queue the copy of region `src` (count meta records, nbytes of payloads) into page-locked arrays; complete after
+        the engine's next sync"""
+        self.engine._check(self.engine.lib.ck_fetch_received_async(self.engine.h, src, count, nbytes, meta.ctypes.data, data.ctypes.data))
+
     @staticmethod
     def payloads(meta, data) -> list[bytes]:
         """split a region's data into payloads (16-byte aligned starts)"""

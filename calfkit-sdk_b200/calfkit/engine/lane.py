@@ -236,7 +236,7 @@ class PublishBatch:
 _FAST_COLS = np.asarray([COL["STATUS"], COL["ACTION"], COL["CORR_OFF"], COL["CORR_LEN"]], dtype=np.uint32)
 
 
-def received_batch(meta: np.ndarray, data: np.ndarray, topic_names: dict[int, str]) -> "PublishBatch":
+def received_batch(meta: np.ndarray, data: np.ndarray, topic_names: dict[int, str], on_release=None) -> "PublishBatch":
     """a region another rank wrote into this rank's receive buffer, as a PublishBatch (payload i = forwarded payload i; its
     topic id and partition travelled with it; the key — the correlation id — is inside the payload and not needed to route)"""
     n = len(meta)
@@ -246,7 +246,7 @@ def received_batch(meta: np.ndarray, data: np.ndarray, topic_names: dict[int, st
     pubs = np.zeros(n, dtype=PUB_DTYPE)
     pubs["payload"] = np.arange(n, dtype=np.uint32)
     pubs["topic_id"], pubs["partition"], pubs["record"], pubs["has_key"] = meta["topic_id"], meta["partition"], np.arange(n, dtype=np.uint32), 0
-    return PublishBatch(data, off, meta["len"].astype(np.uint32), pubs, topic_names, None, None, None, None)
+    return PublishBatch(data, off, meta["len"].astype(np.uint32), pubs, topic_names, None, None, None, None, on_release=on_release)
 
 
 class Lane:
@@ -300,6 +300,26 @@ class Lane:
             eng._check(eng.lib.ck_fetch_cols_async(eng.h, ptr(_FAST_COLS), 4, ptr(rows)))
         eng._check(eng.lib.ck_fetch_groups(eng.h, ptr(order), ptr(key_counts), 0))
         self._views = (b_out.array[:nb], off, ln, pubs, rows, order, key_counts)
+        # what the other ranks forwarded to this one during this step: the regions are complete (the stream was just
+        # synchronised for the sizes, the exchange's second barrier is behind it); their copies ride along with the results
+        self._recv = []
+        if self.px is not None:
+            from calfkit.engine.exchange import _meta_dtype
+            hdr = self.px.peek()
+            for src in range(self.px.world):
+                step, count, overflow, rbytes = (int(x) for x in hdr[src])
+                if src == self.px.rank:
+                    continue
+                if overflow:
+                    raise EngineError(f"rank {src} could not fit {overflow} payloads into its region here: raise max_fwd / data_cap")
+                if step != self.step_no:
+                    raise EngineError(f"region of rank {src} holds step {step}, expected {self.step_no}")
+                if count == 0:
+                    continue
+                b_m, b_d = pool.take(16 * count), pool.take(rbytes + 64)
+                meta, data = b_m.view(_meta_dtype(), count), b_d.array[:rbytes]
+                self.px.fetch_async(src, count, rbytes, meta, data)
+                self._recv.append((meta, data, b_m, b_d))
         self.collecting = True
 
     def finish_collect(self) -> PublishBatch:
@@ -314,10 +334,9 @@ class Lane:
         arena, self.arena, self.busy, self.collecting = self.arena, None, False, False
         self._views = self._b_out = self._b_meta = None
         self.received = []
-        if self.px is not None:       # what the other ranks forwarded to this one during this step
-            for _src, meta, data in self.px.received(self.step_no):
-                if len(meta):
-                    self.received.append(received_batch(meta, data, eng.topic_names))
+        for meta, data, b_m, b_d in self._recv:
+            self.received.append(received_batch(meta, data, eng.topic_names, on_release=lambda b_m=b_m, b_d=b_d: (pool.give(b_m), pool.give(b_d))))
+        self._recv = []
 
         def done():
             pool.give(b_out)

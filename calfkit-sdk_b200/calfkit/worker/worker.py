@@ -184,6 +184,7 @@ class Worker:
                         self._produce_fast(node, done)
                 elif pipe.pending:                             # input idle (single rank): flush what is in flight
                     for done in pipe.drain():
+                        consumed += 1                          # keeps run(until_idle) going: what was just produced may feed a node
                         self._produce_fast(node, done)
                 for rb in pipe.take_received():                # forwarded here by the owners of other partitions' inputs
                     self.stats["received"] = self.stats.get("received", 0) + rb.n_publishes
@@ -225,14 +226,19 @@ class Worker:
             n += await self._client._dispatcher.drain(broker) if hasattr(self._client, "_dispatcher") else 0
             if self._all_idle(n + sum(p.pending_records for p in self._pipes.values())):
                 if until_idle:
+                    flushed = 0
                     for node, _sub in self._subs:          # nothing in flight on any rank: flush (no exchange involved)
                         pipe = self._pipes.get(id(node))
                         if pipe is not None:
                             for done in pipe.drain():
+                                flushed += done.source.n
                                 self._produce_fast(node, done)
                             for rb in pipe.take_received():
+                                flushed += rb.n_publishes
                                 broker.produce_publishes(rb)
-                    return
+                    if self._all_idle(flushed):            # nothing came out that a subscribed node still has to consume
+                        return
+                    continue
                 await asyncio.sleep(idle_sleep)
             else:
                 await asyncio.sleep(0)

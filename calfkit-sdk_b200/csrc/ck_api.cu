@@ -506,7 +506,10 @@ extern "C" int ck_set_agent_node(ck_handle* h, int32_t publish_topic_id, const u
         // registered id of the tool's topic, if any (host-side probe of the same table the device uses is
         // not needed: ids are resolved by the route kernel when this is 0xffffffff)
         tab[4 * ntools + k] = 0xffffffffu;
-        { u32 hh = 2166136261u ^ (u32)nm.size(); for (unsigned char ch : nm) hh = (hh ^ ch) * 16777619u; tab[5 * ntools + k] = hh; }   // = ck_hash_span of the name
+        { std::vector<u64> pad(nm.size() / 8 + 4, 0ull);          // 8-byte aligned, padded: the reader loads whole aligned words
+          memcpy((u8*)pad.data() + 8, nm.data(), nm.size());
+          GRd hr; hr.init((const u8*)pad.data() + 8, (u32)nm.size());
+          tab[5 * ntools + k] = ck_hash_span(hr, 0, (u32)nm.size()); }    // the device compares it with ck_hash_span of the name in the record
     }
     if (pool.size() > CK_LIT_CAP) return fail(h, "ck_set_agent_node: literal pool overflow");
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -967,6 +970,34 @@ extern "C" int ck_fetch_received(ck_handle* h, uint32_t src, uint64_t* hdr4 /* s
     if (host_meta && hd.count) CUDA_TRY(h, cudaMemcpyAsync(host_meta, region + CK_X_HDR, sizeof(ck_xmeta) * (size_t)hd.count, cudaMemcpyDeviceToHost, h->stream));
     if (host_data && hd.nbytes) CUDA_TRY(h, cudaMemcpyAsync(host_data, region + CK_X_HDR + (size_t)h->max_fwd * sizeof(ck_xmeta), hd.nbytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// the pipelined form: ck_peek_received reads every region header with one small copy (one synchronisation of the engine's
+// stream, which the caller has normally just done anyway), ck_fetch_received_async queues the copies of one region into
+// page-locked memory and returns; they are complete after the next ck_sync
+extern "C" int ck_peek_received(ck_handle* h, uint64_t* hdr4 /* [world][4]: step, count, overflow, nbytes */) {
+    cudaSetDevice(h->device);
+    if (!h->d_recv) return fail(h, "ck_peek_received: call ck_comm_create first");
+    ck_xregion_hdr hd[CK_X_MAXWORLD];
+    CUDA_TRY(h, cudaMemcpy2DAsync(hd, sizeof(ck_xregion_hdr), h->d_recv, h->region_stride, sizeof(ck_xregion_hdr), h->comm_world,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    u32 to = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&to, h->d_x_overflow + CK_X_MAXWORLD, sizeof to, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (to) return fail(h, "exchange barrier timed out: a peer did not arrive");
+    for (u32 r = 0; r < h->comm_world; r++) {
+        hdr4[4 * r] = hd[r].step; hdr4[4 * r + 1] = hd[r].count; hdr4[4 * r + 2] = hd[r].overflow; hdr4[4 * r + 3] = hd[r].nbytes;
+    }
+    return 0;
+}
+extern "C" int ck_fetch_received_async(ck_handle* h, uint32_t src, uint64_t count, uint64_t nbytes, uint8_t* host_meta, uint8_t* host_data) {
+    cudaSetDevice(h->device);
+    if (!h->d_recv || src >= h->comm_world) return fail(h, "ck_fetch_received_async: no such region");
+    if (count > h->max_fwd || nbytes > h->region_data_cap) return fail(h, "ck_fetch_received_async: count / nbytes beyond the region");
+    const u8* region = h->d_recv + (size_t)src * h->region_stride;
+    if (host_meta && count) CUDA_TRY(h, cudaMemcpyAsync(host_meta, region + CK_X_HDR, sizeof(ck_xmeta) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
+    if (host_data && nbytes) CUDA_TRY(h, cudaMemcpyAsync(host_data, region + CK_X_HDR + (size_t)h->max_fwd * sizeof(ck_xmeta), nbytes, cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
 

@@ -189,6 +189,9 @@ struct URd : GRd {
 #define CK_WIN_BYTES 160
 #endif
 #define CK_WIN_BACK 16
+#ifndef CK_WIN_L2PF
+#define CK_WIN_L2PF 0
+#endif
 #define CK_WIN_STRIDE (CK_WIN_BYTES + 16)     // per-thread slot; the pad spreads the slots over the banks
 #define CK_WIN_NONE 0x80000000u     // o = ap - wbase is then >= 2^31 for every position: always refills
 #if defined(__CUDA_ARCH__)
@@ -208,6 +211,12 @@ CK_HD_NOINLINE u32 ck_win_refill(const u8* gb, u32 ap, u32 lim) {
 #pragma unroll
     for (u32 k = 0; k < CK_WIN_BYTES; k += 16)
         if (wb + k < lim) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + k), "l"(src + k) : "memory");
+#if CK_WIN_L2PF
+    // the NEXT window's lines start their trip from HBM to L2 now: the refill that needs them (one window of parsing
+    // later) then waits for an L2 hit instead of a DRAM access
+    if (wb + CK_WIN_BYTES < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + CK_WIN_BYTES));
+    if (wb + CK_WIN_BYTES + 128u < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + CK_WIN_BYTES + 128u));
+#endif
     asm volatile("cp.async.wait_all;" ::: "memory");
 #else
     for (u32 k = 0; k < CK_WIN_BYTES; k += 16) if (wb + k < lim) for (u32 j = 0; j < 16; j++) ck_win_host[k + j] = gb[wb + k + j];
@@ -596,11 +605,40 @@ struct AnyCtx {
     u32 kfill;
 };
 
+#ifndef CK_HASH8
+#define CK_HASH8 1
+#endif
+// hash of a key span, eight bytes a step (equal spans -> equal hashes is all the duplicate checks and the key tables
+// need; every hit is confirmed by a byte compare or sends the record to the canonicaliser)
 template <class R>
 CK_HD u32 ck_hash_span(R& r, u32 off, u32 len) {
     u32 h = 2166136261u ^ len;
-    for (u32 i = 0; i < len; i++) h = (h ^ r.at(off + i)) * 16777619u;
+#if !CK_HASH8
+    for (u32 b = 0; b < len; b++) h = (h ^ r.at(off + b)) * 16777619u;
     return h;
+#endif
+    u32 i = 0;
+    for (; i + 8 <= len; i += 8) {
+        u64 w = r.load8(off + i);
+        h = (h ^ (u32)w) * 16777619u;
+        h = (h ^ (u32)(w >> 32)) * 16777619u;
+    }
+    if (i < len) {
+        u64 w = r.load8(off + i) & (~0ull >> (8 * (8 - (len - i))));
+        h = (h ^ (u32)w) * 16777619u;
+        h = (h ^ (u32)(w >> 32)) * 16777619u;
+    }
+    return h ^ (h >> 15);
+}
+
+// two spans of the same length, byte-equal?  Eight bytes a step through two readers (each keeps its own cached word)
+template <class RA, class RB>
+CK_HD bool ck_spans_equal(RA& ra, u32 a, RB& rb, u32 b, u32 len) {
+    u64 diff = 0;
+    u32 i = 0;
+    for (; i + 8 <= len; i += 8) diff |= ra.load8(a + i) ^ rb.load8(b + i);
+    if (i < len) diff |= (ra.load8(a + i) ^ rb.load8(b + i)) & (~0ull >> (8 * (8 - (len - i))));
+    return diff == 0;
 }
 
 // base_depth: nesting level of the value inside the document (root object = depth 1)
@@ -1449,15 +1487,13 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     Span tn = {0, 0}, ar = {0, 0};
     if (nframes > 0 && top_nargs == 2 && (top_kinds & 1u)) {
         u32 h = ck_hash_span(r, top_a0.off, top_a0.len);
-        GRd gr; gr.init(r.g, r.n);          // byte compares of two far-apart spans: plain global loads
+        GRd gr, gq; gr.init(r.g, r.n); gq.init(r.g, r.n);      // compares of two far-apart spans: plain global loads
         // the hash covers the length, so a hit is (almost surely) the key: verify bytes + closing quote
         for (u32 k = 0; k < tc_n; k++) {
             if (tc_kh[k] != h) continue;
             u32 ko = tc_koff[k];
             if (ko + top_a0.len >= r.n || gr.at(ko + top_a0.len) != '"') continue;
-            bool eq = true;
-            for (u32 b = 0; b < top_a0.len; b++) if (gr.at(ko + b) != gr.at(top_a0.off + b)) { eq = false; break; }
-            if (!eq) continue;
+            if (!ck_spans_equal(gr, ko, gq, top_a0.off, top_a0.len)) continue;
             if (k == 0) { call0 = first_tc0; call1 = first_tc1; tn = first_tc.tool_name; ar = first_tc.args; break; }
             u32 p2 = ko + top_a0.len + 2;
             call0 = p2;
@@ -1470,9 +1506,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
             if (tr_kh[k] != h) continue;
             u32 ko = tr_koff[k];
             if (ko + top_a0.len >= r.n || gr.at(ko + top_a0.len) != '"') continue;
-            bool eq = true;
-            for (u32 b = 0; b < top_a0.len; b++) if (gr.at(ko + b) != gr.at(top_a0.off + b)) { eq = false; break; }
-            if (!eq) continue;
+            if (!ck_spans_equal(gr, ko, gq, top_a0.off, top_a0.len)) continue;
             if (k == 0) { res0 = first_tr0; res1 = first_tr1; break; }
             u32 p2 = ko + top_a0.len + 2;
             res0 = p2;

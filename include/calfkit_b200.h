@@ -165,6 +165,11 @@ int  ck_comm_connect(ck_handle* h, const uint8_t* handles);
 int  ck_exchange_send(ck_handle* h, uint64_t step);
 int  ck_recv_info(ck_handle* h, void** dev_recv, uint64_t* region_stride, uint32_t* max_fwd, uint64_t* data_cap);
 int  ck_fetch_received(ck_handle* h, uint32_t src, uint64_t* hdr4, uint8_t* host_meta, uint8_t* host_data, uint64_t data_cap);
+/* pipelined form: ck_peek_received reads all region headers ([world][4] = step, count, overflow, nbytes) with one stream
+ * synchronisation; ck_fetch_received_async queues the copies of region `src` into page-locked memory and returns (complete
+ * after the next ck_sync).  A region stays valid until this engine's next ck_exchange_send. */
+int  ck_peek_received(ck_handle* h, uint64_t* hdr4);
+int  ck_fetch_received_async(ck_handle* h, uint32_t src, uint64_t count, uint64_t nbytes, uint8_t* host_meta, uint8_t* host_data);
 /* multi-GPU exchange planning (records shard by Kafka partition across the GPUs of a box; reference analogue:
  * producing to a topic-partition another worker process consumes, nodes/base.py:82-87 key=correlation_id).  Selects the
  * keyed publishes whose partition % world != rank, ordered by destination rank (stable), into library-owned device
