@@ -27,7 +27,7 @@ struct ck_handle {
     u8* d_in = nullptr; long long* d_in_off = nullptr;
     u8* d_out = nullptr; long long* d_out_off = nullptr;
     u8* d_aux = nullptr; long long* d_aux_off = nullptr; u8* d_glue = nullptr;
-    u8* d_ovl = nullptr; long long* d_ovl_off = nullptr; u32* d_ovl_len = nullptr; ck_canon_ctl* d_canon_ctl = nullptr; u32* d_canon_list = nullptr; u32* d_long_list = nullptr;
+    u8* d_ovl = nullptr; long long* d_ovl_off = nullptr; u32* d_ovl_len = nullptr; ck_canon_ctl* d_canon_ctl = nullptr; u32* d_canon_list = nullptr; ck_elem* d_elems = nullptr; u32 elem_cap = 0; u32* d_cand = nullptr; uint2* d_hist_skip = nullptr;
     uint64_t max_ovl = 0;
     u32* d_cols = nullptr; ck_out_desc* d_descs = nullptr; u32* d_pay_len = nullptr; ck_pub* d_pubs = nullptr;
     unsigned long long* d_tile_sum = nullptr; unsigned long long* d_grand = nullptr;
@@ -136,7 +136,12 @@ extern "C" int ck_create(int device, uint64_t max_in_bytes, uint64_t max_out_byt
     ALLOC(h->d_ovl_len, sizeof(u32) * (size_t)max_records);
     ALLOC(h->d_canon_ctl, sizeof(ck_canon_ctl));
     ALLOC(h->d_canon_list, sizeof(u32) * (size_t)max_records);
-    ALLOC(h->d_long_list, sizeof(u32) * (size_t)max_records);
+    // list elements of long records walked one per thread: a message of a history is rarely shorter than a few hundred bytes
+    // (a full list only means the remaining ones are walked inside their record's warp)
+    { unsigned long long cap = max_in_bytes / 256 + 1024; if (cap > 0x7fffffffull) cap = 0x7fffffffull; h->elem_cap = (u32)cap; }
+    ALLOC(h->d_elems, sizeof(ck_elem) * (size_t)h->elem_cap);
+    ALLOC(h->d_cand, sizeof(u32) * (size_t)max_records);
+    ALLOC(h->d_hist_skip, sizeof(uint2) * (size_t)max_records);
     ALLOC(h->d_cols, sizeof(u32) * (size_t)CK_NUM_COLS * max_records);
     ALLOC(h->d_descs, sizeof(ck_out_desc) * (size_t)h->max_payloads);
     ALLOC(h->d_pay_len, sizeof(u32) * (size_t)h->max_payloads);
@@ -163,7 +168,7 @@ extern "C" void ck_destroy(ck_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_ovl, h->d_ovl_off, h->d_ovl_len, h->d_canon_ctl, h->d_canon_list, h->d_long_list, h->d_cols, h->d_descs, h->d_pay_len,
+    void* ptrs[] = {h->d_in, h->d_in_off, h->d_out, h->d_out_off, h->d_aux, h->d_aux_off, h->d_glue, h->d_ovl, h->d_ovl_off, h->d_ovl_len, h->d_canon_ctl, h->d_canon_list, h->d_elems, h->d_cand, h->d_hist_skip, h->d_cols, h->d_descs, h->d_pay_len,
                     h->d_pubs, h->d_tile_sum, h->d_grand, h->d_lit, h->d_tool_cfg, h->d_agent_cfg, h->d_counts, h->d_slot_base, h->d_agent_tables, h->d_topic_hist, h->d_tab_hash, h->d_tab_off,
                     h->d_tab_len, h->d_tab_id, h->d_tab_names, h->d_x_hist, h->d_x_base, h->d_x_nbytes, h->d_x_src_off, h->d_x_len, h->d_x_dst_off,
                     h->d_x_len32, h->d_x_pub, h->d_x_tile, h->d_x_grand, h->d_x_grand2};
@@ -253,7 +258,7 @@ extern "C" int ck_set_tool_node(ck_handle* h, int32_t publish_topic_id, uint32_t
 
 static ck_view view_of(ck_handle* h) {
     ck_view v; v.in = h->cur_in; v.off = h->cur_in_off; v.ovl = h->d_ovl; v.ovl_off = h->d_ovl_off; v.ovl_len = h->d_ovl_len;
-    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list; v.len = h->cur_len; v.long_list = h->d_long_list; v.perm = h->cur_perm;
+    v.canon_ctl = h->d_canon_ctl; v.canon_list = h->d_canon_list; v.len = h->cur_len; v.perm = h->cur_perm; v.elems = h->d_elems; v.elem_cap = h->elem_cap; v.hist_skip = h->d_hist_skip;
     return v;
 }
 
@@ -320,6 +325,17 @@ static int launch_decode(ck_handle* h) {
         h->cur_perm = h->d_g_o2;
         v = view_of(h);
     }
+    if (mode == 2) v.hist_skip = nullptr;                    // A/B walker: no pre-scan, every list walked in place
+    if (mode != 2) {
+        // records of CK_HIST_MIN bytes or more, one warp each: structural pre-scan; message_history listed message by message
+        // for the element pass, or (long records that are long for another reason) the whole record walked by the warp.
+        // Both kernels exit at once when there are no such records.
+        KTimer t(h, CK_K_WALK_LONG);
+        CKL(h) ck_classify_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(v, n, h->d_cand);
+        u32 lblocks = (n + CK_LONG_WARPS - 1) / CK_LONG_WARPS; if (lblocks > 148 * CK_LONG_MINB) lblocks = 148 * CK_LONG_MINB;
+        CKL(h) ck_walk_long_kernel<<<lblocks, 32 * CK_LONG_WARPS, CK_LONG_WARPS * sizeof(ck_long_index), h->stream>>>(v, h->d_cols, n, h->d_cand, h->d_hist_skip);
+        CUDA_TRY(h, cudaGetLastError());
+    }
     {
         KTimer t(h, CK_K_WALK);
         if (mode == 2) CKL(h) ck_walk_global_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, h->d_cols, n, 0);
@@ -327,11 +343,10 @@ static int launch_decode(ck_handle* h) {
         CUDA_TRY(h, cudaGetLastError());
     }
     {
-        // records of CK_LONG_MIN bytes or more were handed to a device-side list: one warp each, lists walked element-parallel
-        // (exits at once when there are none)
-        KTimer t(h, CK_K_WALK_LONG);
-        u32 lblocks = (n + CK_LONG_WARPS - 1) / CK_LONG_WARPS; if (lblocks > 148 * 4) lblocks = 148 * 4;
-        CKL(h) ck_walk_long_kernel<<<lblocks, 32 * CK_LONG_WARPS, CK_LONG_WARPS * sizeof(ck_long_index), h->stream>>>(v, n, h->d_cols, n);
+        // the history messages listed by the pre-scan or deferred by the long walker, one thread each (exits at once when
+        // there are none)
+        KTimer t(h, CK_K_WALK_ELEMS);
+        CKL(h) ck_walk_elems_kernel<<<148 * CK_WALK_MINB, CK_WALK_THREADS, CK_WALK_THREADS * CK_WIN_STRIDE, h->stream>>>(v, h->d_cols, n);
         CUDA_TRY(h, cudaGetLastError());
     }
     {

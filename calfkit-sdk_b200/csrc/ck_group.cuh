@@ -38,7 +38,9 @@ struct ck_key_pub {
 };
 struct ck_key_len {
     ck_view v;
-    __device__ __forceinline__ u32 operator()(u32 i) const { u32 len; ck_rec_in(v, i, len); u32 k = len >> 5; return k < CK_G_KEYS - 1 ? k : CK_G_KEYS - 1; }
+    // longest first: the walk's blocks start in this order, so the records that take longest start first and the short ones
+    // fill in behind them (a 16 KB record alone takes a thread ~0.5 ms; started last it would be the kernel's tail)
+    __device__ __forceinline__ u32 operator()(u32 i) const { u32 len; ck_rec_in(v, i, len); u32 k = len >> 5; return CK_G_KEYS - 1 - (k < CK_G_KEYS - 1 ? k : CK_G_KEYS - 1); }
 };
 
 // pass over `in` (NULL = identity order): digit histogram per block -> hist[digit][block]; pass 0 also counts whole keys

@@ -23,16 +23,22 @@ extern __shared__ uint4 ck_win_smem[];   // nvcc's host pass parses the device c
 // the canonical re-emission of the records that arrived in a non-canonical spelling (ck_canon.cuh).
 // Every stage after decode reads a record through ck_rec(), i.e. its canonical bytes.
 // ------------------------------------------------------------------------------------------------
+#ifndef CK_HIST_MIN
+#define CK_HIST_MIN 2048u        // records at least this long get the message_history pre-scan (ck_walk_long.cuh)
+#endif
 #ifndef CK_LONG_MIN
 #define CK_LONG_MIN 16384u       // records at least this long are walked one per warp (ck_walk_long.cuh); measured: §7 of DESIGN.md
 #endif
-struct ck_canon_ctl { unsigned long long cursor; u32 count; u32 pad; };   // overlay bytes handed out, records listed; pad = long records listed
+// per-batch counters (zeroed by launch_decode): overlay bytes handed out; records listed for the canonicaliser; list elements
+// deferred to ck_walk_elems_kernel (may exceed the capacity: clamp); records listed for the warp-per-record pass / handed out
+struct ck_canon_ctl { unsigned long long cursor; u32 count; u32 elems; u32 cand; u32 cand_next; };
 struct ck_view {
     const u8* in; const long long* off;
     const u8* ovl; const long long* ovl_off; const u32* ovl_len;     // ovl_off[i] < 0: record i has no overlay
     ck_canon_ctl* canon_ctl; u32* canon_list;                        // records the walker left to the canonicaliser
     const u32* perm;                                                 // NULL, or thread t of the walk takes record perm[t] (length-bucketed batch)
-    u32* long_list;                                                  // records of CK_LONG_MIN bytes or more: walked one per warp (ck_walk_long.cuh)
+    const uint2* hist_skip;                                          // per record: (open, close) of a message_history whose messages are on the element list
+    ck_elem* elems; u32 elem_cap;                                    // deferred list elements of long records (ck_walk_elems_kernel)
     const u32* len;                                                  // NULL: record i = [off[i], off[i+1]); else off[i] .. + len[i]
 };                                                                   //       (values inside raw Kafka record batches are not contiguous)
 __device__ __forceinline__ const u8* ck_rec_in(const ck_view& v, u32 i, u32& len) {     // the submitted bytes of record i
@@ -105,12 +111,10 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
     u32 len; const u8* rec;
     if (mode == 0) rec = ck_rec_in(v, i, len);                                                       // the submitted spelling
     else { if (v.ovl_off[i] < 0) return; rec = ck_rec(v, i, len); }                                  // re-walk of canonicalised records
-    if (mode == 0 && len >= CK_LONG_MIN && v.long_list) {            // long record: a whole warp takes it (ck_walk_long_kernel)
-        u32 k = atomicAdd(&v.canon_ctl->pad, 1u);
-        v.long_list[k] = i;
-        return;
-    }
-    WalkOut o; o.base = cols + i; o.stride = stride;
+    uint2 skip = make_uint2(0u, 0u);
+    if (mode == 0 && len >= CK_HIST_MIN && v.hist_skip) skip = v.hist_skip[i];   // written by ck_hist_prescan_kernel for every such record
+    if (skip.x == 0xffffffffu) return;                               // long record, not history-dominated: a whole warp has walked it (ck_walk_long_kernel)
+    WalkOut o; o.base = cols + i; o.stride = stride; o.skip_open = skip.x; o.skip_close = skip.y;
     u32 status, stop = 0;
     if (len == 0) status = CK_EMPTY;
     else {
@@ -130,6 +134,19 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
 #ifndef CK_WALK_MINB
 #define CK_WALK_MINB 7
 #endif
+// records long enough for the history pre-scan (ck_hist_prescan_kernel), listed with one atomic per warp
+__global__ void __launch_bounds__(256)
+ck_classify_kernel(ck_view v, u32 n, u32* __restrict__ cand) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false; u32 i = 0;
+    if (j < n) { i = v.perm ? v.perm[j] : j; u32 len; ck_rec_in(v, i, len); take = len >= CK_HIST_MIN; }
+    u32 m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    u32 lane = threadIdx.x & 31, base = 0;
+    if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(&v.canon_ctl->cand, (u32)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (take) cand[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
 __global__ void __launch_bounds__(CK_WALK_THREADS, CK_WALK_MINB)
 ck_walk_kernel(ck_view v, u32 n, u32* __restrict__ cols, u32 stride, u32 mode) { ck_walk_one<WRd>(v, n, cols, stride, mode); }
 __global__ void __launch_bounds__(CK_WALK_THREADS, 8)

@@ -51,8 +51,13 @@ extern __shared__ uint4 ck_win_smem[];       // dynamic shared memory of the wal
 #define CK_LX_CLOSE 320u             // closers indexed per depth
 #define CK_LX_MIN 4u                 // lists shorter than this are walked sequentially
 #define CK_LX_KEYS 128u              // = CK_DICT_KEYS
+#define CK_DEFER_MAX 4096u           // = CK_ELEM_MAX: list elements longer than this are not handed to the one-thread-per-element pass
+#define CK_LX_OPEN 8u                // depth-4 list openers remembered per record
+struct ck_elem { u32 rec, start, end; };         // one deferred list element: bytes [start, end) of record `rec` must be exactly one message
 struct ck_long_index {
-    u32 n_sep[2], n_close[2], ok, pad[3];
+    u32 n_sep[2], n_close[2], ok, rec, defer_cap, n_open;
+    u32 open_sq[CK_LX_OPEN];                     // '[' that open a depth-4 list (message_history is one of them)
+    ck_elem* defer_list; u32* defer_ctr;         // device-wide element list of the batch (ck_walk_elems_kernel); null: walk elements in the warp
     u32 sep[2][CK_LX_SEP];           // [0]: depth 4, [1]: depth 6 — record-relative positions of commas outside strings
     u32 close_[2][CK_LX_CLOSE];      // closers that end a container of that depth
     u32 kh[2][CK_LX_KEYS], koff[2][CK_LX_KEYS];      // key hash / offset of the entries of tool_calls [0], tool_results [1]
@@ -63,7 +68,11 @@ CK_HD bool ck_all(bool p) { return __all_sync(0xffffffffu, p); }
 CK_HD u32 ck_bcast(u32 v, u32 src) { return __shfl_sync(0xffffffffu, v, src); }
 CK_HD u32 ck_or_reduce(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
 CK_HD void ck_warp_sync() { __syncwarp(); }
+CK_HD u32 ck_defer_reserve(u32* ctr, u32 n) { u32 b = 0; if ((threadIdx.x & 31u) == 0) b = atomicAdd(ctr, n); return __shfl_sync(0xffffffffu, b, 0); }
+CK_HD u32 ck_max_reduce(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
 #else
+CK_HD u32 ck_max_reduce(u32 v) { return v; }
+CK_HD u32 ck_defer_reserve(u32*, u32) { return 0xffffffffu; }
 CK_HD u32 ck_lane() { return 0; }
 CK_HD bool ck_all(bool p) { return p; }
 CK_HD u32 ck_bcast(u32 v, u32) { return v; }
@@ -1142,6 +1151,9 @@ CK_HD bool ck_tool_result_value(R& r, u32& pos, u32 d, AnyCtx& cx) {
 // a convergent warp writes 128 contiguous bytes per column); host tests = a plain array (stride 1)
 struct WalkOut {
     u32* base; size_t stride; bool active = true;       // a warp walking one record: only lane 0 stores
+    // message_history of this record, if the pre-scan pass (ck_hist_prescan_kernel) has listed its messages for
+    // ck_walk_elems_kernel: position of its '[' and of the matching ']' (0 / 0: walk the list here)
+    u32 skip_open = 0, skip_close = 0;
     CK_HD void set(u32 col, u32 v) { if (active) base[(size_t)col * stride] = v; }
 };
 
@@ -1302,15 +1314,35 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
     }
 #endif
     a = pos - 1;
-    if (!PEEK(']')) {
+    if (o.skip_close && o.skip_open == a) pos = o.skip_close;      // the messages are validated one thread each, batch-wide
+    else if (!PEEK(']')) {
         bool par = false;
         if constexpr (R::kWarp) {
             u32 q, s0, k;
-            if (ck_lx_range(r.lx(), 0, pos, q, s0, k) && k + 1 >= CK_LX_MIN) {
-                par = true;
+            if (ck_lx_range(r.lx(), 0, pos, q, s0, k)) {
                 const ck_long_index* lx = r.lx();
+                // the messages are pure validation (no columns come out of them): hand them to the batch-wide element list —
+                // one THREAD per message through the window reader, all long records' messages side by side
+                // (ck_walk_elems_kernel; a message that fails there sends its record to the canonicaliser) ...
+                bool deferred = false;
+                u32 longest = 0;
+                for (u32 e = ck_lane(); e <= k; e += 32) { u32 a0 = e ? lx->sep[0][s0 + e - 1] + 1 : pos, a1 = e == k ? q : lx->sep[0][s0 + e]; if (a1 - a0 > longest) longest = a1 - a0; }
+                if (lx->defer_list && ck_max_reduce(longest) <= CK_DEFER_MAX) {      // long messages: here, their parts lane-parallel
+                    u32 slot = ck_defer_reserve(lx->defer_ctr, k + 1);
+                    bool fits = slot <= lx->defer_cap && k + 1 <= lx->defer_cap - slot;
+                    for (u32 e = ck_lane(); e <= k; e += 32) {
+                        if (slot >= lx->defer_cap || e >= lx->defer_cap - slot) break;
+                        ck_elem el;
+                        el.rec = fits ? lx->rec : 0xffffffffu;       // a reservation that does not fit is voided
+                        el.start = e ? lx->sep[0][s0 + e - 1] + 1 : pos; el.end = e == k ? q : lx->sep[0][s0 + e];
+                        lx->defer_list[slot + e] = el;
+                    }
+                    deferred = fits;
+                }
+                // ... or, without a list (or with a full one), walk them here, one lane each (short lists: sequentially, below)
+                par = deferred || k + 1 >= CK_LX_MIN;
                 bool good = true;
-                for (u32 base = 0; base <= k; base += 32) {
+                for (u32 base = 0; par && !deferred && base <= k; base += 32) {
                     u32 e = base + ck_lane();
                     bool ok = true;
                     if (e <= k) {
@@ -1321,7 +1353,7 @@ CK_HD bool ck_walk_envelope(R& r, WalkOut& o, AnyCtx& cx, u32& stop) {
                     good = ck_all(ok) && good;
                 }
                 if (!good) FAIL;
-                pos = q;
+                if (par) pos = q;
             }
         }
         if (!par) {

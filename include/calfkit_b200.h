@@ -221,7 +221,7 @@ int  ck_device_buffers2(ck_handle* h, void** pubs, void** pay_len, void** descs)
 int  ck_profile(ck_handle* h, int enable);         /* record (asynchronous) CUDA events around every kernel */
 int  ck_profile_read(ck_handle* h, float* ms /* CK_NUM_KERNELS */, uint32_t* launches /* CK_NUM_KERNELS */, int reset);
 
-enum { CK_K_WALK = 0, CK_K_PLAN, CK_K_SCAN, CK_K_EMIT, CK_K_ROUTE, CK_K_FANOUT, CK_K_CANON, CK_K_WALK_LONG, CK_NUM_KERNELS };
+enum { CK_K_WALK = 0, CK_K_PLAN, CK_K_SCAN, CK_K_EMIT, CK_K_ROUTE, CK_K_FANOUT, CK_K_CANON, CK_K_WALK_LONG, CK_K_WALK_ELEMS, CK_NUM_KERNELS };
 
 #ifdef __cplusplus
 }

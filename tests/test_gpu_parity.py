@@ -372,6 +372,57 @@ def test_noncanonical_inputs_are_canonicalised_on_device(engine):
     assert out.overlay is not None and (out.overlay[1] >= 0).sum() >= 40
 
 
+def test_long_records_with_bad_or_respelled_history_messages(engine):
+    """Records long enough for the warp-per-record walker, whose history messages are validated one thread each from the
+    batch-wide element list (ck_walk_elems_kernel): a message in the middle that is schema-invalid, not JSON, or merely
+    spelled differently must give exactly what the sequential walk gives — the reference's error class, or the reference's
+    output after canonicalisation — and must not disturb its neighbours in the batch."""
+    import tools_def
+    from oracle import port
+    from pydantic import ValidationError
+    from calfkit import synth
+    from calfkit.engine import ToolTemplate
+    from calfkit.engine._lib import COL
+    _setup(engine, "get_weather", ToolTemplate.from_format("It's sunny in {location}"))
+    base = [r for r in synth.mixed_events(400, seed=77, lo=20000, hi=65536, n_tools=1) if len(r) >= 20000][:24]
+    assert len(base) >= 16
+    marker = b'"part_kind":"text"'
+    recs, kinds = [], []
+    for i, r in enumerate(base):
+        hits = [m for m in range(len(r)) if r.startswith(marker, m)]
+        mid = hits[len(hits) // 2]
+        kind = i % 6
+        if kind == 0:   v = r                                                            # untouched
+        elif kind == 1: v = r[:mid] + b'"part_kind":"texx"' + r[mid + len(marker):]      # unknown union tag: schema-invalid
+        elif kind == 2: v = r[:mid] + b'"part_kind": "text"' + r[mid + len(marker):]     # valid, one space: canonicalised
+        elif kind == 3: v = r[:mid] + b'"part_kind":"text"}' + r[mid + len(marker):]     # unbalanced: not JSON
+        elif kind == 4: v = r[:mid] + b'"part_kind":"text","zz":[1,{"a":"}]"}]' + r[mid + len(marker):]   # unknown key with brackets in a string: dropped by the reference
+        else:           v = r[:mid - 1] + b' ' + r[mid - 1:]                             # whitespace before a key
+        recs.append(v); kinds.append(kind)
+    b = synth.pack(recs)
+    out = engine.run_tool_batch(b.data, b.offsets)
+    st = out.cols[COL["STATUS"]]
+    node = port.ToolNode.of(tools_def.get_weather)
+    pubs = list(out.publishes())
+    k = 0
+    for i, r in enumerate(recs):
+        try:
+            port.decode(r)
+            ok = True
+        except ValidationError as e:
+            ok, cls = False, (2 if e.errors()[0]["type"] == "json_invalid" else 3)
+        if ok:
+            assert st[i] == 0, (i, kinds[i], st[i])
+            want = port.tool_node_event(node, r)
+            got = [(p.topic, p.key, p.payload) for p in pubs[k:k + len(want)]]
+            assert got == [(t, kk, pl) for (t, kk, c, pl) in want], (i, kinds[i])
+            k += len(want)
+        else:
+            assert st[i] == cls, (i, kinds[i], st[i], cls)
+    assert k == len(pubs)
+    assert {kinds[i] for i in range(len(recs)) if st[i] == 0} >= {0, 2, 4, 5} and {kinds[i] for i in range(len(recs)) if st[i] != 0} == {1, 3}
+
+
 def test_exchange_plan_kernels_match_tensor_plan(engine):
     """ck_exchange_plan (histogram -> scan -> stable scatter -> scan) against the device-agnostic tensor plan that
     the world-size-2 gloo test covers (calfkit/engine/exchange.py), on a real publish table, for every rank of
