@@ -18,15 +18,20 @@
 #endif
 #define CK_LONG_WARPS 4
 
-__device__ __forceinline__ u32 ck_nib(u32 m) { return (((m & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; }     // 0xFF/0x00 per byte -> 4 bits
+// bytes of a word equal to a character -> 4 bits.  Exact zero-byte test of x = word ^ cccc (no borrow between bytes):
+// bit 7 of a byte of ~(((x & 0x7f..) + 0x7f..) | x) is set iff the byte is 0; the multiply gathers the four flags.
+__device__ __forceinline__ u32 ck_nib_eq(u32 x) {
+    u32 t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+    return ((t >> 7) * 0x01020408u) >> 24;
+}
 __device__ __forceinline__ u32 ck_mask16(const uint4& w, u32 c) {
     u32 cc = c * 0x01010101u;
-    return ck_nib(__vcmpeq4(w.x, cc)) | (ck_nib(__vcmpeq4(w.y, cc)) << 4) | (ck_nib(__vcmpeq4(w.z, cc)) << 8) | (ck_nib(__vcmpeq4(w.w, cc)) << 12);
+    return ck_nib_eq(w.x ^ cc) | (ck_nib_eq(w.y ^ cc) << 4) | (ck_nib_eq(w.z ^ cc) << 8) | (ck_nib_eq(w.w ^ cc) << 12);
 }
 __device__ __forceinline__ u32 ck_mask16_or20(const uint4& w, u32 c) {          // bytes equal to c once bit 5 is set: '{' / '[' and '}' / ']'
     const u32 b = 0x20202020u;
     u32 cc = c * 0x01010101u;
-    return ck_nib(__vcmpeq4(w.x | b, cc)) | (ck_nib(__vcmpeq4(w.y | b, cc)) << 4) | (ck_nib(__vcmpeq4(w.z | b, cc)) << 8) | (ck_nib(__vcmpeq4(w.w | b, cc)) << 12);
+    return ck_nib_eq((w.x | b) ^ cc) | (ck_nib_eq((w.y | b) ^ cc) << 4) | (ck_nib_eq((w.z | b) ^ cc) << 8) | (ck_nib_eq((w.w | b) ^ cc) << 12);
 }
 
 // [from, to): the bytes to scan (the whole record, or one container that starts at a structural character outside any
@@ -54,8 +59,7 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
         u32 V = 0xFFFFu;
         if (p0 < m) V &= (m - p0 >= 16) ? 0u : (0xFFFFu << (m - p0));
         if (p0 + 16 > total) V &= (p0 >= total) ? 0u : (0xFFFFu >> (p0 + 16 - total));
-        u32 Q = ck_mask16(w, '"') & V, B = ck_mask16(w, '\\') & V, K = ck_mask16(w, ',') & V;
-        u32 O = ck_mask16_or20(w, '{') & V, C = ck_mask16_or20(w, '}') & V;
+        u32 Q = ck_mask16(w, '"') & V, B = ck_mask16(w, '\\') & V;
         // escaped quotes: preceded by a backslash run of length 1 or 3 (longer runs: the proposal may be wrong, the walk decides)
         u32 up = __shfl_up_sync(0xffffffffu, B >> 12, 1);
         u32 prev4 = lane ? up : prev_bs;
@@ -70,7 +74,11 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
         u32 carry = (__popc(odd & ((1u << lane) - 1u)) & 1u) ^ str_carry;   // parity before this lane's first byte
         str_carry ^= __popc(odd) & 1u;
         u32 E = ((S << 1) & 0xFFFFu) ^ (carry ? 0xFFFFu : 0u);      // bit b: byte b lies inside a string
-        O &= ~E; C &= ~E; K &= ~E;
+        // commas and brackets matter outside strings only: a lane whose 16 bytes all lie inside one (most lanes of a
+        // conversation's text) skips their masks
+        u32 K = 0, O = 0, C = 0;
+        u32 outside = ~E & V;
+        if (outside) { K = ck_mask16(w, ',') & outside; O = ck_mask16_or20(w, '{') & outside; C = ck_mask16_or20(w, '}') & outside; }
         // nesting depth before each byte
         int dbase = depth_carry;
         if (__any_sync(0xffffffffu, (O | C) != 0)) {                // (tiles inside one long string have no bracket at all)
@@ -82,7 +90,7 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
         }
         // '[' that opens a depth-4 list (rare: a handful per record) — remembered for the message_history look-up
         {
-            u32 SQ = ck_mask16(w, '[') & O;
+            u32 SQ = O ? ck_mask16(w, '[') & O : 0u;
             u32 mine = 0, firstpos = 0;
             for (u32 x = SQ; x; x &= x - 1) {
                 u32 b = __ffs(x) - 1, below = (1u << b) - 1u;
@@ -97,8 +105,9 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
                 n_open++;
             }
         }
-        // this lane's entries for the four lists
-        u32 cnt[4] = {0, 0, 0, 0};
+        // this lane's entries for the four lists (sep / close at depth 4, sep / close at depth 6); scalars, not an indexed
+        // array: a dynamically indexed local array lives in local memory
+        u32 c_s0 = 0, c_s1 = 0, c_c0 = 0, c_c1 = 0;
         u32 pend = K | C;
         {   // the depths this lane's bytes can be at: nothing to list if neither 4 nor (DEEP) 6 is among them
             int dlo = dbase - (int)__popc(C), dhi = dbase + (int)__popc(O);
@@ -107,30 +116,33 @@ __device__ __forceinline__ void ck_lx_build(const u8* __restrict__ g, u32 n, ck_
         for (u32 x = pend; x; x &= x - 1) {
             u32 b = __ffs(x) - 1, below = (1u << b) - 1u;
             int d = dbase + (int)__popc(O & below) - (int)__popc(C & below);
-            u32 li = d == 4 ? 0u : (DEEP && d == 6 ? 1u : 2u);
-            if (li < 2) cnt[li + (((C >> b) & 1u) ? 2u : 0u)]++;
+            bool cl = ((C >> b) & 1u) != 0;
+            if (d == 4) { if (cl) c_c0++; else c_s0++; }
+            else if (DEEP && d == 6) { if (cl) c_c1++; else c_s1++; }
         }
-        if (!__any_sync(0xffffffffu, (cnt[0] | cnt[1] | cnt[2] | cnt[3]) != 0)) continue;      // nothing to list in this tile
-        u32 off[4];
+        if (!__any_sync(0xffffffffu, (c_s0 | c_s1 | c_c0 | c_c1) != 0)) continue;      // nothing to list in this tile
+        u32 o_s0, o_s1 = 0, o_c0, o_c1 = 0;
+        {
+            auto scan = [&](u32 c, u32& total) { u32 sc = c;
 #pragma unroll
-        for (int l = 0; l < 4; l++) {
-            u32 c = cnt[l], s = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (u32)o) s += y; }
-            u32 tot = __shfl_sync(0xffffffffu, s, 31);
-            u32 basel = l < 2 ? n_sep[l] : n_close[l - 2];
-            off[l] = basel + s - c;
-            if (l < 2) { if (n_sep[l] + tot > CK_LX_SEP) overflow = true; n_sep[l] += tot; }
-            else { if (n_close[l - 2] + tot > CK_LX_CLOSE) overflow = true; n_close[l - 2] += tot; }
+                for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= (u32)o) sc += y; }
+                total = __shfl_sync(0xffffffffu, sc, 31); return sc - c; };
+            u32 tot;
+            o_s0 = n_sep[0] + scan(c_s0, tot); if (n_sep[0] + tot > CK_LX_SEP) overflow = true; n_sep[0] += tot;
+            o_c0 = n_close[0] + scan(c_c0, tot); if (n_close[0] + tot > CK_LX_CLOSE) overflow = true; n_close[0] += tot;
+            if (DEEP) {
+                o_s1 = n_sep[1] + scan(c_s1, tot); if (n_sep[1] + tot > CK_LX_SEP) overflow = true; n_sep[1] += tot;
+                o_c1 = n_close[1] + scan(c_c1, tot); if (n_close[1] + tot > CK_LX_CLOSE) overflow = true; n_close[1] += tot;
+            }
         }
         if (!overflow) {
             for (u32 x = pend; x; x &= x - 1) {
                 u32 b = __ffs(x) - 1, below = (1u << b) - 1u;
                 int d = dbase + (int)__popc(O & below) - (int)__popc(C & below);
-                u32 li = d == 4 ? 0u : (DEEP && d == 6 ? 1u : 2u);
-                if (li >= 2) continue;
+                bool cl = ((C >> b) & 1u) != 0;
                 u32 pos = p0 + b - m0;
-                if ((C >> b) & 1u) lx->close_[li][off[li + 2]++] = pos; else lx->sep[li][off[li]++] = pos;
+                if (d == 4) { if (cl) lx->close_[0][o_c0++] = pos; else lx->sep[0][o_s0++] = pos; }
+                else if (DEEP && d == 6) { if (cl) lx->close_[1][o_c1++] = pos; else lx->sep[1][o_s1++] = pos; }
             }
         }
     }
@@ -198,10 +210,12 @@ ck_walk_long_kernel(ck_view v, u32* __restrict__ cols, u32 stride, const u32* __
             u32 slot = ck_defer_reserve(&v.canon_ctl->elems, k + 1);
             take = slot <= v.elem_cap && k + 1 <= v.elem_cap - slot;
             for (u32 e = lane; e <= k; e += 32) {
-                if (slot >= v.elem_cap || e >= v.elem_cap - slot) break;
+                if (!take && (slot >= v.elem_cap || e >= v.elem_cap - slot)) break;
                 ck_elem el; el.rec = take ? i : 0xffffffffu;        // a reservation that does not fit is voided
                 el.start = e ? lx->sep[0][s0 + e - 1] + 1 : open + 1; el.end = e == k ? q : lx->sep[0][s0 + e];
-                v.elems[slot + e] = el;
+                // requests and responses alternate in a conversation and differ in shape and length: even messages first,
+                // then the odd ones, so that the lanes of a warp of the element pass walk alike messages
+                v.elems[slot + (take ? (e >> 1) + ((e & 1u) ? (k >> 1) + 1u : 0u) : e)] = el;
             }
             if (take) res = make_uint2(open, q);
         }

@@ -22,5 +22,13 @@ for k in walk plan_tool2 emit; do
 done
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ck_walk_long_kernel -s 2 -c 1 -f -o $O/${R}_walk_long \
     python scripts/quick_fanout.py 4096 > $O/${R}_ncu_walk_long.log 2>&1
+# the long-record decode of the mixed workload: warp pre-scan and one thread per history message
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ck_walk_long_kernel -s 2 -c 1 -f -o $O/${R}_prescan_mixed \
+    python scripts/quick_mixed.py 65536 > $O/${R}_ncu_prescan_mixed.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ck_walk_elems_kernel -s 2 -c 1 -f -o $O/${R}_walk_elems \
+    python scripts/quick_mixed.py 65536 > $O/${R}_ncu_walk_elems.log 2>&1
+# summaries are made here (ncu is on the box); the reports themselves are too large to bring back
+PROFILES_OUT=$O/profiles_$R KEEP_REP=0 python scripts/make_profiles.py $R > $O/${R}_make_profiles.log 2>&1
+rm -f $O/*.ncu-rep
 cuobjdump -sass calfkit-sdk_b200/libcalfkit_b200.so | grep -E "LDGSTS|UBLKCP|SYNCS|ATOM|RED\." | awk '{print $2}' | sort | uniq -c | sort -rn | head -20 > $O/${R}_sass_mnemonics.txt
 ls -la $O
