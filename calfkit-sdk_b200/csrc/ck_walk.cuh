@@ -464,10 +464,37 @@ CK_HD_NOINLINE u64 ck_string_core(const u8* g, u32 n, u32 pos, u32 st) {
 #endif
         u64 special = (x & CK_REP8(0x80)) | ck_haszero(x ^ CK_REP8('"')) | ck_haszero(x ^ CK_REP8('\\')) | ck_lt20(x);
         if (special == 0) { pos += 8; continue; }
-        pos += ck_ctz64(special) >> 3;
+        u32 bi = ck_ctz64(special) >> 3;
+        pos += bi;
         if (pos >= r.n) return false;
-        u8 c = r.at(pos);
+        // the special byte and what follows it in the word already loaded: multi-byte sequences and the two-character
+        // escapes that lie inside it are checked from the register (text in other scripts has one every few bytes)
+        u64 y = x >> (8 * bi);
+        u32 avail = 8 - bi;
+        u8 c = (u8)y;
         if (c == '"') return CK_RET(pos + 1);
+        if (c >= 0x80) {
+            u32 need; u32 lo = 0x80, hi = 0xBF;
+            if (c >= 0xC2 && c <= 0xDF) need = 1;
+            else if (c >= 0xE0 && c <= 0xEF) { need = 2; if (c == 0xE0) lo = 0xA0; if (c == 0xED) hi = 0x9F; }
+            else if (c >= 0xF0 && c <= 0xF4) { need = 3; if (c == 0xF0) lo = 0x90; if (c == 0xF4) hi = 0x8F; }
+            else return false;
+            if (need < avail) {
+                if (pos + need >= r.n) return false;
+                u32 c1 = (u32)(y >> 8) & 0xFFu;
+                if (c1 < lo || c1 > hi) return false;
+                if (need >= 2) { u32 c2 = (u32)(y >> 16) & 0xFFu; if (c2 < 0x80 || c2 > 0xBF) return false; }
+                if (need == 3) { u32 c3 = (u32)(y >> 24) & 0xFFu; if (c3 < 0x80 || c3 > 0xBF) return false; }
+                pos += need + 1;
+                continue;
+            }
+            if (!ck_utf8_seq(r, pos)) return false;         // the sequence crosses the word: byte by byte
+            continue;
+        }
+        if (c == '\\' && avail >= 2) {
+            u8 e = (u8)(y >> 8);
+            if (e == '"' || e == '\\' || e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f') { if (pos + 1 >= r.n) return false; pos += 2; continue; }
+        }
         if (c == '\\') {
             if (pos + 1 >= r.n) return false;
             u8 e = r.at(pos + 1);
