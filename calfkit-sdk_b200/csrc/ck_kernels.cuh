@@ -132,7 +132,7 @@ __device__ __forceinline__ void ck_walk_one(ck_view v, u32 n, u32* __restrict__ 
     }
 }
 #ifndef CK_WALK_MINB
-#define CK_WALK_MINB 7
+#define CK_WALK_MINB 8
 #endif
 // records long enough for the history pre-scan (ck_hist_prescan_kernel), listed with one atomic per warp
 __global__ void __launch_bounds__(256)

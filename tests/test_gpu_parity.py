@@ -423,6 +423,40 @@ def test_long_records_with_bad_or_respelled_history_messages(engine):
     assert {kinds[i] for i in range(len(recs)) if st[i] == 0} >= {0, 2, 4, 5} and {kinds[i] for i in range(len(recs)) if st[i] != 0} == {1, 3}
 
 
+def test_element_list_overflow_falls_back_to_the_warp_walk():
+    """More history messages in a batch than the element list holds (tiny messages, an engine sized to the bytes): the
+    reservations that do not fit are voided and those records are walked by their warp instead — same outputs."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import tools_def
+    from oracle import port
+    from calfkit import synth
+    from calfkit.engine import BatchEngine, ToolTemplate
+    base = synth.tool_events(96, seed=13)
+    marker = b'"message_history":['
+    recs = []
+    for i, r in enumerate(base):
+        turns = ",".join(synth.user_request("q%d" % k) for k in range(120 + i % 5))
+        p = r.index(marker) + len(marker)
+        recs.append(r[:p] + turns.encode() + b"," + r[p:])
+    b = synth.pack(recs)
+    n_msgs = sum(120 + i % 5 for i in range(len(recs)))
+    e = BatchEngine(0, max_records=128, max_in_bytes=int(b.data.nbytes) + 4096)
+    assert n_msgs > (int(b.data.nbytes) + 4096) // 256 + 1024          # more messages than list entries (ck_api.cu: elem_cap)
+    try:
+        e.register_topics(["tool.get_weather.input", "tool.get_weather.output", "weather_agent.input"], num_partitions=8)
+        e.set_tool_node("tool.get_weather.output", ToolTemplate.from_format("It's sunny in {location}"))
+        out = e.run_tool_batch(b.data, b.offsets)
+        assert (out.cols[0] == 0).all()
+        node = port.ToolNode.of(tools_def.get_weather)
+        got = [(p.topic, p.key, p.payload) for p in out.publishes()]
+        want = [(t, k, pl) for r in recs for (t, k, _c, pl) in port.tool_node_event(node, r)]
+        assert got == want
+    finally:
+        e.close()
+
+
 def test_exchange_plan_kernels_match_tensor_plan(engine):
     """ck_exchange_plan (histogram -> scan -> stable scatter -> scan) against the device-agnostic tensor plan that
     the world-size-2 gloo test covers (calfkit/engine/exchange.py), on a real publish table, for every rank of
