@@ -36,6 +36,10 @@ def lib():
         _lib.ck_host_walk_global.restype = ctypes.c_int
         _lib.ck_host_walk_trust.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_walk_trust.restype = ctypes.c_int
+        _lib.ck_host_walk_skip.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+        _lib.ck_host_walk_skip.restype = ctypes.c_int
+        _lib.ck_host_elem.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+        _lib.ck_host_elem.restype = ctypes.c_int
         _lib.ck_host_num_cols.restype = ctypes.c_int
         _lib.ck_host_vm_walk.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p]
         _lib.ck_host_vm_walk.restype = ctypes.c_int
@@ -50,6 +54,19 @@ def walk(payload: bytes):
     cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
     ok = L.ck_host_walk(payload, len(payload), cols.ctypes.data)
     return bool(ok), cols
+
+
+def walk_skip(payload: bytes, open_: int, close: int):
+    """the record walk with message_history = [open_, close] handed to the element pass: -> (accepted, cols)"""
+    L = lib()
+    cols = np.zeros(L.ck_host_num_cols(), dtype=np.uint32)
+    ok = L.ck_host_walk_skip(payload, len(payload), cols.ctypes.data, open_, close)
+    return bool(ok), cols
+
+
+def elem_ok(payload: bytes, start: int, end: int) -> bool:
+    """what ck_walk_elems_kernel decides for one listed message"""
+    return bool(lib().ck_host_elem(payload, len(payload), start, end))
 
 
 def walk_global(payload: bytes):
