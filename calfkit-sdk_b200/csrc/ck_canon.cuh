@@ -304,12 +304,18 @@ CK_HD int cj_emit_number(const CIn& in, u32 a, u32 b, COut& o, bool as_float) {
     if (nd == 0) { if (neg) o.put('-'); CPUTS(o, "0.0"); return CE_OK; }      // +-0.0
     if (e10 > 290 || e10 < -290) return CE_UNSUP;                             // near overflow / subnormal: not decided here
     if (nd > 15) {
-        // 16-17 digits: only if they are exactly what repr() of the nearest double prints (csrc/ck_float.cuh, exact
-        // integer arithmetic); anything else would need a shortest-digits printer
-        if (nd > 17) return CE_UNSUP;
+        // 16-19 digits: kept if they are exactly what repr() of the nearest double prints, else replaced by that spelling
+        // (csrc/ck_float.cuh: exact integer arithmetic, a search over the 15/16/17-digit decimals next to the literal)
+        if (nd > 19) return CE_UNSUP;
         u64 m = 0;
         for (u32 k = 0; k < nd; k++) m = m * 10 + (u64)(D[k] - '0');
-        if (!ckf_is_repr(m, e10 - (int)nd)) return CE_UNSUP;
+        if (!(nd <= 17 && ckf_is_repr(m, e10 - (int)nd))) {
+            u64 ms; int ks;
+            if (!ckf_shortest(m, e10 - (int)nd, ms, ks)) return CE_UNSUP;
+            u32 n2 = 0; { u64 t = ms; while (t) { n2++; t /= 10; } }
+            { u64 t = ms; for (u32 k = n2; k-- > 0;) { D[k] = (u8)('0' + t % 10); t /= 10; } }
+            nd = n2; e10 = ks + (int)n2;
+        }
     }
     if (neg) o.put('-');
     // value = D[0].D[1..] * 10^(e10-1)

@@ -234,4 +234,61 @@ CKF_HD bool ckf_is_repr(uint64_t m, int k) {
 #undef CKF_INSIDE
 }
 
+// Shortest round-trip spelling of the double a long literal denotes (what pydantic-core / repr() print for it), for
+// literals of 16..19 significant digits that are NOT already that spelling: m * 10^k is the literal (m without trailing
+// zeros), the result is ms * 10^ks (ms without trailing zeros).  Search instead of digit generation, every step decided
+// with the exact comparisons above:
+//   level n = 15, 16, 17 digits: the n-digit decimals next to the literal (its truncation t and t + 1) are the only
+//   candidates for "some n-digit decimal rounds to d" — the literal lies inside d's rounding interval, so any n-digit point
+//   inside it has one of the two between itself and the literal;
+//   n = 15: at most one such decimal exists (two 15-digit decimals never share a double) and it is the answer;
+//   n = 16, 17: the answer is the grid point nearest to d (found by stepping over midpoints), confirmed by ckf_is_repr —
+//   which also arbitrates ties and the narrow interval above a power of two — with its two neighbours as fallbacks.
+// false = undecided (the caller reports CK_UNSUPPORTED): never a wrong spelling.
+CKF_HD bool ckf_shortest(uint64_t m, int k, uint64_t& ms, int& ks) {
+    uint64_t f; int e;
+    if (!ckf_nearest_double(m, k, f, e)) return false;
+    bool pow2 = (f == (1ull << 52));
+    uint64_t lo_g = pow2 ? 4 * f - 1 : 2 * f - 1; int lo_t = pow2 ? e - 2 : e - 1;
+    uint64_t hi_g = 2 * f + 1; int hi_t = e - 1;
+    bool incl = (f & 1) == 0;
+#define CKF_INSIDE2(res, c, kk) do { int a_ = ckf_cmp_dec_bin((c), (kk), lo_g, lo_t), b_ = ckf_cmp_dec_bin((c), (kk), hi_g, hi_t); \
+        (res) = (a_ == 2 || b_ == 2) ? 2 : (((a_ > 0 || (a_ == 0 && incl)) && (b_ < 0 || (b_ == 0 && incl))) ? 1 : 0); } while (0)
+    uint32_t nd = 0; { uint64_t t = m; while (t) { nd++; t /= 10; } }
+    if (nd < 16 || nd > 19) return false;
+    for (uint32_t n = 15; n <= 17 && n <= nd; n++) {
+        uint32_t p = nd - n;
+        uint64_t pw = 1; for (uint32_t i = 0; i < p; i++) pw *= 10;
+        uint64_t t = m / pw; int kn = k + (int)p;
+        int in0, in1 = 0;
+        CKF_INSIDE2(in0, t, kn);
+        if (p > 0) CKF_INSIDE2(in1, t + 1, kn);
+        if (in0 == 2 || in1 == 2) return false;
+        if (!in0 && !in1) continue;
+        uint64_t c = in0 ? t : t + 1;
+        if (n > 15) {
+            // nearest grid point to d: smallest c whose upper midpoint is not below d, then not above its lower midpoint
+            for (int it = 0; it < 24; it++) { int g = ckf_cmp_dec_bin(2 * c + 1, kn, f, e + 1); if (g == 2) return false; if (g < 0) c++; else break; }
+            for (int it = 0; it < 24; it++) { int g = ckf_cmp_dec_bin(2 * c - 1, kn, f, e + 1); if (g == 2) return false; if (g > 0) c--; else break; }
+            uint64_t pick = 0; bool found = false;
+            for (int dlt = 0; dlt < 3 && !found; dlt++) {
+                uint64_t cc = dlt == 0 ? c : (dlt == 1 ? c - 1 : c + 1);
+                if (cc % 10 == 0) continue;                       // a shorter decimal: level n - 1 would have found it
+                uint32_t cd = 0; { uint64_t tt = cc; while (tt) { cd++; tt /= 10; } }
+                if (cd != n) continue;
+                int ins; CKF_INSIDE2(ins, cc, kn);                // it must denote d, not a neighbouring double
+                if (ins == 2) return false;
+                if (ins == 1 && ckf_is_repr(cc, kn)) { pick = cc; found = true; }
+            }
+            if (!found) return false;
+            c = pick;
+        }
+        while (c % 10 == 0) { c /= 10; kn++; }
+        ms = c; ks = kn;
+        return true;
+    }
+    return false;
+#undef CKF_INSIDE2
+}
+
 #endif

@@ -122,3 +122,36 @@ def test_datetime_spellings():
         s = f"{rng.randrange(1, 9999):04d}-{rng.randrange(0, 14):02d}-{rng.randrange(0, 33):02d}{sep}{rng.randrange(0, 25):02d}:{rng.randrange(0, 61):02d}:{rng.randrange(0, 61):02d}{frac}{zone}"
         _check(r[:i] + s.encode() + r[j:], stats)
     assert stats.get(0, 0) > 500
+
+
+def test_long_float_literals_are_respelled_as_the_reference_does():
+    """float literals with 16-19 significant digits that are not the shortest round-trip spelling of their double (a value
+    printed with %.17g or copied from a decimal source) come back as exactly what the reference dumps — csrc/ck_float.cuh
+    finds that spelling by an exact search, no binary floating point involved; the re-emitted record is a fixed point"""
+    import struct
+    from calfkit import synth
+    rng = random.Random(17)
+    base = json.loads(synth.tool_events(1, seed=61)[0])
+    lits = ["123456789.123456789", "0.1000000000000000055", "5.6843418860808015e-14", "0.30000000000000004", "1.0000000000000002",
+            "123456789012345680.0", "9007199254740993.0", "2.2250738585072014e-280", "0.3000000000000000166", "4.35", "4.3499999999999996447",
+            "1234567890123456789e-5", "72057594037927936.0", "9.999999999999999e22", "1.00000000000000011102230246251565404"]
+    for _ in range(300):
+        d = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
+        if d != d or abs(d) == float("inf") or abs(d) < 1e-280 or abs(d) > 1e280:
+            continue
+        lits.append(("%." + str(rng.choice([16, 17, 18])) + "e") % d)
+    decided = 0
+    for k in range(0, len(lits), 8):
+        chunk = lits[k:k + 8]
+        txt = json.dumps(base).replace('"metadata": null', '"metadata": {"f": [' + ", ".join(chunk) + ']}', 1)
+        assert '"f": [' in txt
+        st, out = canon(txt.encode())
+        tst, tout = _truth(txt.encode())
+        assert tst == 0
+        if st == 4:
+            assert any(len(c.split("e")[0].replace(".", "").replace("-", "").strip("0")) > 19 for c in chunk), chunk   # only > 19 digits may be declined
+            continue
+        assert st == 0 and out == tout, (chunk, out[out.find(b'"f"'):][:300], tout[tout.find(b'"f"'):][:300])
+        assert walk_trust(out)[0]
+        decided += 1
+    assert decided >= 35

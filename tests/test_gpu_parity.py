@@ -549,7 +549,8 @@ def test_reply_outputs_match_reference_goldens_and_oracle(engine):
 
 def test_long_floats_on_device(engine):
     """16-17 digit floats (computed values such as 0.30000000000000004): accepted in place when they are the
-    shortest round-trip spelling (csrc/ck_float.cuh), in canonical and in re-spelled records; outputs byte-exact."""
+    shortest round-trip spelling (csrc/ck_float.cuh), in canonical and in re-spelled records; literals of 16-19 digits that
+    are NOT that spelling are replaced by it (exact search, ckf_shortest); outputs byte-exact."""
     import tools_def
     from oracle import port
     from calfkit import synth
@@ -562,6 +563,9 @@ def test_long_floats_on_device(engine):
     for k, r in enumerate(base):
         vals = [repr(rng.choice([rng.random(), 0.1 + 0.2, rng.uniform(-1e6, 1e6), rng.random() * 1e-7, rng.random() * 1e18]))
                 for _ in range(rng.randrange(1, 6))]
+        if k % 5 == 0:      # literals longer than the shortest spelling (%.17e / %.18e): the device finds the reference's spelling
+            vals += [("%." + str(rng.choice([16, 17, 18])) + "e") % rng.choice([rng.random(), rng.uniform(-1e9, 1e9), rng.random() * 1e-12])
+                     for _ in range(2)] + ["123456789.123456789", "0.1000000000000000055"]
         i = r.index(b'"provided_deps":{') + len(b'"provided_deps":{')
         j = r.index(b"}", i)
         sep = b" , " if k % 3 == 0 else b","                       # every third record is re-spelled (canonicaliser path)
@@ -667,7 +671,7 @@ def _murmur2(data: bytes) -> int:
     return h
 
 
-DECLARED_UNSUPPORTED = {"any_numbers": "re-spelling floats needs a shortest-digits printer", "datetime_number": "unix-number datetimes",
+DECLARED_UNSUPPORTED = {"any_numbers": "floats at the overflow / subnormal edge (1e400 -> null, 5e-324, DBL_MAX); long literals in the normal range are re-spelled", "datetime_number": "unix-number datetimes",
                         "frame_missing_frame_id": "default_factory field: the reference invents a fresh id",
                         "datetime_bad": "rejected by the reference; the device cannot class the datetime spelling",
                         "usage_int_bad": "rejected by the reference; lax int rules beyond the plain spellings"}
