@@ -11,7 +11,7 @@
 //   CK_SCHEMA_INVALID  well-formed JSON that violates the Envelope schema (missing / *_type /
 //                      union_tag_* / literal_error ...)
 //   CK_UNSUPPORTED     constructs whose result cannot be decided / reproduced on the device yet
-//                      (lax coercions "5" -> 5, >15-digit floats, exotic datetimes, default_factory fields
+//                      (floats at the overflow / subnormal edge, fractional unix timestamps, exotic datetimes, default_factory fields
 //                      that are absent, multi-modal content ...) — reported per record, never guessed.
 // Soundness contract (fuzzed against pydantic through tests/hostsim): OK implies identical bytes,
 // JSON_INVALID / SCHEMA_INVALID imply pydantic raises with that class.
@@ -465,11 +465,66 @@ CK_HD bool cj_two(const u8* s, u32 k, u32& v) {
     return true;
 }
 // datetime string -> canonical spelling; only layouts whose result is certain are accepted
+// unix timestamp given as a plain integer (a JSON number, or a string holding one; an all-zero fraction is allowed): seconds,
+// or milliseconds beyond the reference's watershed of 2e10 (speedate), always UTC.  Other numeric spellings (fractions,
+// exponents: the reference goes through binary floating point there) stay undecided.
+CK_HD int cj_emit_unix_datetime(const CIn& in, u32 a, u32 b, COut& o) {
+    u32 p = a;
+    bool neg = false;
+    if (p < b && in.p[p] == '-') { neg = true; p++; }
+    u32 d0 = p;
+    long long v = 0;
+    while (p < b && cj_isdigit(in.p[p])) { if (p - d0 >= 15) return CE_UNSUP; v = v * 10 + (in.p[p] - '0'); p++; }
+    if (p == d0 || (in.p[d0] == '0' && p - d0 > 1)) return CE_UNSUP;
+    if (p < b) {                                               // ".000": still the integer
+        if (in.p[p] != '.' || p + 1 >= b) return CE_UNSUP;
+        for (u32 q = p + 1; q < b; q++) if (in.p[q] != '0') return CE_UNSUP;
+    }
+    if (neg) v = -v;
+    long long secs = v, micros = 0;
+    if (v > 20000000000ll || v < -20000000000ll) {
+        secs = v / 1000; long long ms = v % 1000;
+        if (ms < 0) { ms += 1000; secs -= 1; }
+        micros = ms * 1000;
+    }
+    long long days = secs / 86400, rem = secs % 86400;
+    if (rem < 0) { rem += 86400; days -= 1; }
+    // civil date from days since 1970-01-01 (proleptic Gregorian)
+    long long z = days + 719468;
+    long long era = (z >= 0 ? z : z - 146096) / 146097;
+    long long doe = z - era * 146097;
+    long long yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    long long y = yoe + era * 400;
+    long long doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    long long mp = (5 * doy + 2) / 153;
+    long long d = doy - (153 * mp + 2) / 5 + 1;
+    long long mth = mp < 10 ? mp + 3 : mp - 9;
+    if (mth <= 2) y += 1;
+    if (y < 1 || y > 9999) return CE_UNSUP;
+    u32 hh = (u32)(rem / 3600), mi = (u32)((rem % 3600) / 60), ss = (u32)(rem % 60);
+    o.put('"');
+    o.put((u8)('0' + (y / 1000) % 10)); o.put((u8)('0' + (y / 100) % 10)); o.put((u8)('0' + (y / 10) % 10)); o.put((u8)('0' + y % 10));
+    o.put('-'); o.put((u8)('0' + mth / 10)); o.put((u8)('0' + mth % 10));
+    o.put('-'); o.put((u8)('0' + d / 10)); o.put((u8)('0' + d % 10));
+    o.put('T'); o.put((u8)('0' + hh / 10)); o.put((u8)('0' + hh % 10));
+    o.put(':'); o.put((u8)('0' + mi / 10)); o.put((u8)('0' + mi % 10));
+    o.put(':'); o.put((u8)('0' + ss / 10)); o.put((u8)('0' + ss % 10));
+    if (micros) { o.put('.'); long long dv = 100000; for (int k = 0; k < 6; k++) { o.put((u8)('0' + (micros / dv) % 10)); dv /= 10; } }
+    o.put('Z'); o.put('"');
+    return CE_OK;
+}
+
 CK_HD int cj_emit_datetime(const CIn& in, u32 pos, COut& o) {
-    if (in.p[pos] != '"') return CE_UNSUP;                    // numbers (unix timestamps) etc.
+    if (in.p[pos] == '-' || cj_isdigit(in.p[pos])) return cj_emit_unix_datetime(in, pos, cj_scalar_end(in, pos), o);
+    if (in.p[pos] != '"') return CE_UNSUP;
     u32 e = cj_skip_value(in, pos);
     u32 a = pos + 1, b = e - 1;
     for (u32 i = a; i < b; i++) if (in.p[i] == '\\' || in.p[i] >= 0x80) return CE_UNSUP;
+    {   // a string holding a plain integer is taken as the number it spells
+        u32 q = a; if (q < b && in.p[q] == '-') q++;
+        u32 q0 = q; while (q < b && cj_isdigit(in.p[q])) q++;
+        if (q == b && q > q0) return cj_emit_unix_datetime(in, a, b, o);
+    }
     if (b - a < 19) return CE_UNSUP;
     const u8* s = in.p + a;
 #define two(k, v) cj_two(s, (k), (v))
@@ -477,16 +532,19 @@ CK_HD int cj_emit_datetime(const CIn& in, u32 pos, COut& o) {
     if (!two(0, y1) || !two(2, y2) || s[4] != '-' || !two(5, mo) || s[7] != '-' || !two(8, d) || (s[10] != 'T' && s[10] != 't' && s[10] != ' ' && s[10] != '_') ||
         !two(11, h) || s[13] != ':' || !two(14, mi) || s[16] != ':' || !two(17, sec)) return CE_UNSUP;
     u32 y = y1 * 100 + y2;
-    if (y < 1 || mo < 1 || mo > 12 || d < 1 || h > 23 || mi > 59 || sec > 59) return CE_UNSUP;
+    // the layout is RFC 3339's: a field out of its range is a parsing error in the reference (datetime_from_date_parsing), not
+    // another spelling
+    if (y < 1 || mo < 1 || mo > 12 || d < 1 || h > 23 || mi > 59 || sec > 59) return CE_SCHEMA;
     u32 dim = (mo == 2) ? (((y % 4 == 0 && y % 100 != 0) || y % 400 == 0) ? 29 : 28) : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31);
-    if (d > dim) return CE_UNSUP;
+    if (d > dim) return CE_SCHEMA;
     u32 k = 19, len = b - a;
     u8 frac[6] = {'0', '0', '0', '0', '0', '0'}; bool has_frac = false;
     if (k < len && (s[k] == '.' || s[k] == ',')) {
         k++;
         u32 nf = 0;
         while (k < len && cj_isdigit(s[k])) { if (nf < 6) frac[nf] = s[k]; nf++; k++; }
-        if (nf == 0 || nf > 9) return CE_UNSUP;
+        if (nf == 0) return CE_SCHEMA;                        // "12:00:00.Z": a parsing error in the reference
+        if (nf > 9) return CE_UNSUP;
         for (u32 j = 0; j < 6; j++) if (frac[j] != '0') has_frac = true;
     }
     // zone
@@ -495,7 +553,8 @@ CK_HD int cj_emit_datetime(const CIn& in, u32 pos, COut& o) {
     else if ((s[k] == 'Z' || s[k] == 'z') && k + 1 == len) zone = 1;
     else if ((s[k] == '+' || s[k] == '-') && ((k + 6 == len && s[k + 3] == ':') || k + 5 == len)) {      // +HH:MM or +HHMM
         sign = s[k];
-        if (!two(k + 1, oh) || !two(k + (k + 6 == len ? 4 : 3), om) || oh > 23 || om > 59) return CE_UNSUP;
+        if (!two(k + 1, oh) || !two(k + (k + 6 == len ? 4 : 3), om)) return CE_UNSUP;
+        if (oh > 23 || om > 59) return CE_SCHEMA;             // offset out of range: a parsing error in the reference
         zone = (oh == 0 && om == 0) ? 1 : 2;
     } else return CE_UNSUP;
 #undef two
@@ -675,7 +734,17 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
             // lax mode: a float literal with an all-zero fraction (7.0, 12.000) is the integer; other float spellings undecided
             u32 j = i;
             if (in.p[j] != '.' || j + 1 >= e || i - pos > 15) return CE_UNSUP;
-            for (j = i + 1; j < e; j++) if (in.p[j] != '0') return CE_UNSUP;
+            for (j = i + 1; j < e; j++) if (in.p[j] != '0') {
+                // a non-zero fraction digit: with <= 15 significant digits in all (and no exponent) the double the reference
+                // parses keeps its fractional part (distinct decimals of <= 15 digits are distinct doubles) -> int_from_float
+                bool plain = true; u32 sig = 0; bool nz = false;
+                for (u32 q = pos; q < e; q++) {
+                    u8 c2 = in.p[q];
+                    if (c2 == 'e' || c2 == 'E') plain = false;
+                    if (cj_isdigit(c2)) { if (c2 != '0') nz = true; if (nz) sig++; }
+                }
+                return (plain && sig <= 15) ? CE_SCHEMA : CE_UNSUP;
+            }
             if (in.p[pos] == '-' && i == pos + 2 && in.p[pos + 1] == '0') { o.put('0'); return CE_OK; }      // -0.0 -> 0
             return cj_emit_number(in, pos, i, o, false);
         }

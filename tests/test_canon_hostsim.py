@@ -122,6 +122,27 @@ def test_datetime_spellings():
         s = f"{rng.randrange(1, 9999):04d}-{rng.randrange(0, 14):02d}-{rng.randrange(0, 33):02d}{sep}{rng.randrange(0, 25):02d}:{rng.randrange(0, 61):02d}:{rng.randrange(0, 61):02d}{frac}{zone}"
         _check(r[:i] + s.encode() + r[j:], stats)
     assert stats.get(0, 0) > 500
+    assert stats.get(3, 0) > 500        # out-of-range fields in the RFC 3339 layout are the reference's parsing errors, not "unsupported"
+
+
+def test_unix_timestamps_and_numeric_strings():
+    """datetime fields given as unix numbers (seconds; milliseconds beyond the 2e10 watershed), as JSON numbers or as strings
+    holding a plain integer: UTC, exactly as the reference dumps them; fractions / exponents stay declared-unsupported"""
+    from calfkit import synth
+    r = synth.tool_events(1, seed=3)[0]
+    i = r.index(b'"timestamp":"') + len(b'"timestamp":')
+    j = r.index(b'"', i + 1) + 1
+    rng = random.Random(9)
+    stats: dict = {}
+    specials = [0, -1, 1, 86399, 86400, -86400, 951782400, 951868800, 1767225600, 20000000000, 20000000001, -20000000000, -20000000001,
+                253402300799, 253402300800, -62135596800, -62135596801, 1767225600123, -1767225600123, 99999999999999, 4102444800, 68169600]
+    for k in range(3000):
+        v = rng.choice(specials) if k % 4 == 0 else rng.choice([rng.randrange(-3 * 10**10, 3 * 10**10), rng.randrange(-10**14, 10**14),
+                                                              rng.randrange(0, 2 * 10**9), rng.randrange(-10**16, 10**16)])
+        form = rng.randrange(6)
+        lit = [str(v), str(v), '"' + str(v) + '"', str(v) + ".0", str(v) + ".5", "%de0" % v][form]
+        _check(r[:i] + lit.encode() + r[j:], stats)
+    assert stats.get(0, 0) > 1200 and stats.get(4, 0) > 300
 
 
 def test_long_float_literals_are_respelled_as_the_reference_does():
@@ -155,3 +176,25 @@ def test_long_float_literals_are_respelled_as_the_reference_does():
         assert walk_trust(out)[0]
         decided += 1
     assert decided >= 35
+
+
+def test_int_fields_given_as_other_number_spellings():
+    """usage counters given as floats / strings: 7.0 is 7, 1.5 is the reference's int_from_float error (decided for <= 15
+    significant digits without an exponent), the rest is declared unsupported — never a different integer"""
+    from calfkit import synth
+    r = synth.tool_events(1, seed=5, size=None, full_history=True)[0]
+    k0 = r.index(b'"input_tokens":') + len(b'"input_tokens":')
+    k1 = k0
+    while r[k1:k1 + 1].isdigit():
+        k1 += 1
+    rng = random.Random(21)
+    stats: dict = {}
+    for _ in range(3000):
+        ip = str(rng.choice([0, 1, 7, 51, 12345, 10**14, 10**15 + 3, rng.randrange(0, 10**rng.randrange(1, 17))]))
+        fr = rng.choice(["", ".0", ".000", ".5", ".25", ".000001", ".10", "." + str(rng.randrange(1, 10**rng.randrange(1, 12))), ".0e0", "e2", ".5e1"])
+        sign = rng.choice(["", "", "-"])
+        lit = sign + ip + fr
+        if rng.random() < 0.15:
+            lit = '"' + lit + '"'
+        _check(r[:k0] + lit.encode() + r[k1:], stats)
+    assert stats.get(0, 0) > 500 and stats.get(3, 0) > 500

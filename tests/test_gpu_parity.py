@@ -671,10 +671,8 @@ def _murmur2(data: bytes) -> int:
     return h
 
 
-DECLARED_UNSUPPORTED = {"any_numbers": "floats at the overflow / subnormal edge (1e400 -> null, 5e-324, DBL_MAX); long literals in the normal range are re-spelled", "datetime_number": "unix-number datetimes",
-                        "frame_missing_frame_id": "default_factory field: the reference invents a fresh id",
-                        "datetime_bad": "rejected by the reference; the device cannot class the datetime spelling",
-                        "usage_int_bad": "rejected by the reference; lax int rules beyond the plain spellings"}
+DECLARED_UNSUPPORTED = {"any_numbers": "floats at the overflow / subnormal edge (1e400 -> null, 5e-324, DBL_MAX); long literals in the normal range are re-spelled",
+                        "frame_missing_frame_id": "default_factory field: the reference invents a fresh id"}
 
 
 def test_codec_goldens_on_device(engine):
