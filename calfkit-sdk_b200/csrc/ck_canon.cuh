@@ -11,7 +11,7 @@
 //   CK_SCHEMA_INVALID  well-formed JSON that violates the Envelope schema (missing / *_type /
 //                      union_tag_* / literal_error ...)
 //   CK_UNSUPPORTED     constructs whose result cannot be decided / reproduced on the device yet
-//                      (floats at the overflow / subnormal edge, fractional unix timestamps, exotic datetimes, default_factory fields
+//                      (floats of more than 19 digits, fractional unix timestamps, exotic datetimes, default_factory fields
 //                      that are absent, multi-modal content ...) — reported per record, never guessed.
 // Soundness contract (fuzzed against pydantic through tests/hostsim): OK implies identical bytes,
 // JSON_INVALID / SCHEMA_INVALID imply pydantic raises with that class.
@@ -302,13 +302,21 @@ CK_HD int cj_emit_number(const CIn& in, u32 a, u32 b, COut& o, bool as_float) {
     while (nd > 0 && D[nd - 1] == '0') nd--;                                  // trailing zeros are not significant
     if (overflow_digits) return CE_UNSUP;
     if (nd == 0) { if (neg) o.put('-'); CPUTS(o, "0.0"); return CE_OK; }      // +-0.0
-    if (e10 > 290 || e10 < -290) return CE_UNSUP;                             // near overflow / subnormal: not decided here
-    if (nd > 15) {
-        // 16-19 digits: kept if they are exactly what repr() of the nearest double prints, else replaced by that spelling
-        // (csrc/ck_float.cuh: exact integer arithmetic, a search over the 15/16/17-digit decimals next to the literal)
+    // value = 0.D * 10^e10.  Beyond every double: infinity, which the reference dumps as null; below half of the smallest
+    // subnormal: zero
+    if (e10 >= 311) { CPUTS(o, "null"); return CE_OK; }
+    if (e10 <= -326) { if (neg) o.put('-'); CPUTS(o, "0.0"); return CE_OK; }
+    bool extreme = (e10 > 290 || e10 < -290);                                 // the <= 15 digit argument does not hold out here
+    if (nd > 15 || extreme) {
+        // kept if the digits are exactly what repr() of the nearest double prints, else replaced by that spelling
+        // (csrc/ck_float.cuh: exact integer arithmetic, a search over the decimals next to the literal)
         if (nd > 19) return CE_UNSUP;
         u64 m = 0;
         for (u32 k = 0; k < nd; k++) m = m * 10 + (u64)(D[k] - '0');
+        { u64 f_; int e_; int cls = ckf_nearest_double_ex(m, e10 - (int)nd, f_, e_);
+          if (cls == CKF_INF) { CPUTS(o, "null"); return CE_OK; }
+          if (cls == CKF_ZERO) { if (neg) o.put('-'); CPUTS(o, "0.0"); return CE_OK; }
+          if (cls != CKF_FINITE) return CE_UNSUP; }
         if (!(nd <= 17 && ckf_is_repr(m, e10 - (int)nd))) {
             u64 ms; int ks;
             if (!ckf_shortest(m, e10 - (int)nd, ms, ks)) return CE_UNSUP;

@@ -1,5 +1,7 @@
-// Exact test "is this decimal literal what Python's repr() prints for the double it parses to?" for literals
-// with 16 or 17 significant digits (up to 15 the DBL_DIG argument in ck_walk.cuh needs no arithmetic).
+// Exact decimal <-> double decisions for the canonicaliser, no binary floating point:
+//   ckf_nearest_double_ex   the double a decimal literal denotes (normal, subnormal, infinity, zero)
+//   ckf_is_repr             "is this literal what Python's repr() prints for the double it parses to?"
+//   ckf_shortest            the literal repr() would print instead
 //
 // pydantic-core re-emits a float as the shortest digit string that round-trips (ryu; identical to repr(float)),
 // so a float literal in a record is a fixed point of dump(validate(.)) iff, with v = m * 10^k its exact value and
@@ -7,9 +9,10 @@
 //   (B) neither neighbour of v on the 10^(k+1) grid (one digit fewer) rounds to d      -> no shorter spelling exists
 //   (C) v is the point of the 10^k grid nearest to d                                   -> it is the one repr picks
 // (v rounds to d by construction).  Everything is decided with exact integer arithmetic on small bignums
-// (<= 1280 bits: |decimal exponent| <= 300), no floating point, no tables: these literals are rare (computed
-// values such as 0.30000000000000004), the common short ones never get here.  Undecidable-by-design cases
-// (a tie whose even candidate may not round-trip, arithmetic beyond 1344 bits) answer "no": never a wrong yes.
+// (<= 1344 bits: |decimal exponent| <= 345), no floating point, no tables: these literals are rare (computed
+// values such as 0.30000000000000004, values at the edges of the range), the common short ones never get here (up to 15
+// digits in the normal range the DBL_DIG argument in ck_walk.cuh needs no arithmetic).  Undecidable-by-design cases
+// (arithmetic beyond 1344 bits) answer "no": never a wrong yes.
 //
 // __host__ __device__ like the walker, so tests/hostsim can check it against repr(float(s)) on the CPU.
 #ifndef CK_FLOAT_CUH
@@ -114,15 +117,17 @@ CKF_IN int ckf_cmp_dec_bin(uint64_t m, int k, uint64_t g, int t) {
                           g, k < 0 ? (uint32_t)(-k) : 0u, t > 0 ? (uint32_t)t : 0u);
 }
 
-// d = f * 2^e nearest to m * 10^k (53-bit f, ties to even).  false: out of the range handled here / tie.
-CKF_HD bool ckf_nearest_double(uint64_t m, int k, uint64_t& f, int& e) {
-    if (m == 0 || k > 300 || k < -330) return false;
+// d = f * 2^e nearest to m * 10^k (ties to even): 53-bit f for a normal double, f < 2^52 with e == -1074 for a subnormal.
+// Returns CKF_FINITE, CKF_INF (rounds to infinity), CKF_ZERO (rounds to zero) or CKF_UNDECIDED (outside what the bignums hold).
+enum { CKF_FINITE = 0, CKF_UNDECIDED = 1, CKF_INF = 2, CKF_ZERO = 3 };
+CKF_HD int ckf_nearest_double_ex(uint64_t m, int k, uint64_t& f, int& e) {
+    if (m == 0 || k > 310 || k < -345) return CKF_UNDECIDED;
     // work on the rational N / D with N = m * 10^max(k,0), D = 10^max(-k,0); scale N by 2^s so that the integer
     // quotient has 55..56 bits, then round to 53
     CkBig N, D;
     ckb_set(N, m); ckb_mul_pow10(N, k > 0 ? (uint32_t)k : 0u);
     ckb_set(D, 1); ckb_mul_pow10(D, k < 0 ? (uint32_t)(-k) : 0u);
-    if (N.ovf || D.ovf) return false;
+    if (N.ovf || D.ovf) return CKF_UNDECIDED;
     int nb = (int)ckb_bits(N), db = (int)ckb_bits(D);
     int s = 56 - (nb - db);                       // quotient of (N << s) / D has 56 or 57 bits
     int e2;                                       // v = (N * 2^s / D) * 2^-s
@@ -138,7 +143,7 @@ CKF_HD bool ckf_nearest_double(uint64_t m, int k, uint64_t& f, int& e) {
         if (s > 0) ckb_shl(Ns, (uint32_t)s);
         CkBig Ds = D;
         if (s < 0) ckb_shl(Ds, (uint32_t)(-s));
-        if (Ns.ovf || Ds.ovf) return false;
+        if (Ns.ovf || Ds.ovf) return CKF_UNDECIDED;
         uint32_t dbits = ckb_bits(Ds);
         uint32_t drop = dbits > 60 ? dbits - 60 : 0;          // leading 60 bits of the divisor
         uint64_t dtop = ckb_extract64(Ds, drop);
@@ -162,7 +167,7 @@ CKF_HD bool ckf_nearest_double(uint64_t m, int k, uint64_t& f, int& e) {
             P.n = nn; P.ovf = Plo.ovf || Phi.ovf;
             if (c) { if (P.n < CKF_WORDS) P.w[P.n++] = (uint32_t)c; else P.ovf = true; }
             while (P.n && P.w[P.n - 1] == 0) P.n--;
-            if (P.ovf) return false;
+            if (P.ovf) return CKF_UNDECIDED;
             int c1 = ckb_cmp(P, Ns);
             if (c1 > 0) { q--; continue; }                     // q too large
             // P <= Ns: is Ns - P < Ds ?  <=>  P + Ds > Ns
@@ -172,20 +177,23 @@ CKF_HD bool ckf_nearest_double(uint64_t m, int k, uint64_t& f, int& e) {
                 S.w[i] = (uint32_t)t; cc = t >> 32;
             }
             S.n = n2;
-            if (cc) { if (S.n < CKF_WORDS) S.w[S.n++] = (uint32_t)cc; else return false; }
+            if (cc) { if (S.n < CKF_WORDS) S.w[S.n++] = (uint32_t)cc; else return CKF_UNDECIDED; }
             if (ckb_cmp(S, Ns) <= 0) { q++; continue; }        // q too small
             rem = (c1 != 0);
             goto have_q;
         }
-        return false;
+        return CKF_UNDECIDED;
 have_q:
         e2 = -s;
     }
-    // q has 56..57 bits (value = (q + rem_fraction) * 2^e2): round to 53 bits, ties to even
+    // q has 56..57 bits (value = (q + rem_fraction) * 2^e2): round to 53 bits — or to the subnormal grid 2^-1074 when
+    // that is coarser — ties to even
     int qb = 0; { uint64_t t = q; while (t) { qb++; t >>= 1; } }
-    if (qb < 54) return false;
+    if (qb < 54) return CKF_UNDECIDED;
     int drop2 = qb - 53;
-    uint64_t keep = q >> drop2, low = q & ((1ull << drop2) - 1), half = 1ull << (drop2 - 1);
+    if (e2 + drop2 < -1074) drop2 = -1074 - e2;              // subnormal: fewer than 53 bits survive
+    if (drop2 > qb) return CKF_ZERO;                          // v < 2^qb * 2^e2 <= half of the grid step
+    uint64_t keep = q >> drop2, low = q & ((1ull << drop2) - 1), half = 1ull << (drop2 - 1);      // 3 <= drop2 <= 57
     bool up;
     if (low > half) up = true;
     else if (low < half) up = false;
@@ -193,12 +201,15 @@ have_q:
     else up = (keep & 1) != 0;                   // exact tie: to even
     f = keep + (up ? 1 : 0);
     e = e2 + drop2;
+    if (f == 0) return CKF_ZERO;
     if (f == (1ull << 53)) { f >>= 1; e += 1; }
-    // normal range only (subnormals / overflow are not decided here)
-    int exp2 = e + 52;                            // value = 1.xxx * 2^exp2
-    if (exp2 < -1021 || exp2 > 1022) return false;
-    return true;
+    int fb = 0; { uint64_t t = f; while (t) { fb++; t >>= 1; } }
+    int exp2 = e + fb - 1;                        // value = 1.xxx * 2^exp2
+    if (exp2 > 1023) return CKF_INF;
+    if (exp2 < -1074) return CKF_ZERO;
+    return CKF_FINITE;
 }
+CKF_HD bool ckf_nearest_double(uint64_t m, int k, uint64_t& f, int& e) { return ckf_nearest_double_ex(m, k, f, e) == CKF_FINITE; }
 
 // m: the literal's significant digits as an integer (no trailing zeros, 16 or 17 digits), k: decimal exponent of
 // its last digit.  true only if the literal is exactly repr() of the double it denotes.
@@ -207,7 +218,7 @@ CKF_HD bool ckf_is_repr(uint64_t m, int k) {
     if (!ckf_nearest_double(m, k, f, e)) return false;
     // rounding interval of d = f*2^e:  ( (2f-1)*2^(e-1) , (2f+1)*2^(e-1) ), endpoints included iff f even;
     // below a power of two the lower half-gap is half as wide: (4f-1)*2^(e-2)
-    bool pow2 = (f == (1ull << 52));
+    bool pow2 = (f == (1ull << 52)) && e > -1074;       // (below the smallest normal the spacing does not halve)
     uint64_t lo_g = pow2 ? 4 * f - 1 : 2 * f - 1; int lo_t = pow2 ? e - 2 : e - 1;
     uint64_t hi_g = 2 * f + 1; int hi_t = e - 1;
     bool incl = (f & 1) == 0;
@@ -234,57 +245,54 @@ CKF_HD bool ckf_is_repr(uint64_t m, int k) {
 #undef CKF_INSIDE
 }
 
-// Shortest round-trip spelling of the double a long literal denotes (what pydantic-core / repr() print for it), for
-// literals of 16..19 significant digits that are NOT already that spelling: m * 10^k is the literal (m without trailing
-// zeros), the result is ms * 10^ks (ms without trailing zeros).  Search instead of digit generation, every step decided
-// with the exact comparisons above:
-//   level n = 15, 16, 17 digits: the n-digit decimals next to the literal (its truncation t and t + 1) are the only
-//   candidates for "some n-digit decimal rounds to d" — the literal lies inside d's rounding interval, so any n-digit point
-//   inside it has one of the two between itself and the literal;
-//   n = 15: at most one such decimal exists (two 15-digit decimals never share a double) and it is the answer;
-//   n = 16, 17: the answer is the grid point nearest to d (found by stepping over midpoints), confirmed by ckf_is_repr —
-//   which also arbitrates ties and the narrow interval above a power of two — with its two neighbours as fallbacks.
+// Shortest round-trip spelling of the double a literal denotes (what pydantic-core / repr() print for it), for literals that
+// are NOT already that spelling: m * 10^k is the literal (m without trailing zeros, <= 19 digits), the result is ms * 10^ks
+// (ms without trailing zeros).  Search instead of digit generation, every step decided with the exact comparisons above:
+//   level n = 1 .. 17 digits: the n-digit decimals next to the literal (its truncation t and t + 1) are the only candidates
+//   for "some n-digit decimal rounds to d" — the literal lies inside d's rounding interval, so any n-digit point inside it
+//   has one of the two between itself and the literal; at the first level that has one, the answer is the grid point nearest
+//   to d (found by stepping over midpoints) that rounds to d, confirmed by ckf_is_repr — which also arbitrates ties and the
+//   narrow interval above a power of two — with its two neighbours as fallbacks.
 // false = undecided (the caller reports CK_UNSUPPORTED): never a wrong spelling.
 CKF_HD bool ckf_shortest(uint64_t m, int k, uint64_t& ms, int& ks) {
     uint64_t f; int e;
     if (!ckf_nearest_double(m, k, f, e)) return false;
-    bool pow2 = (f == (1ull << 52));
+    bool pow2 = (f == (1ull << 52)) && e > -1074;
     uint64_t lo_g = pow2 ? 4 * f - 1 : 2 * f - 1; int lo_t = pow2 ? e - 2 : e - 1;
     uint64_t hi_g = 2 * f + 1; int hi_t = e - 1;
     bool incl = (f & 1) == 0;
 #define CKF_INSIDE2(res, c, kk) do { int a_ = ckf_cmp_dec_bin((c), (kk), lo_g, lo_t), b_ = ckf_cmp_dec_bin((c), (kk), hi_g, hi_t); \
         (res) = (a_ == 2 || b_ == 2) ? 2 : (((a_ > 0 || (a_ == 0 && incl)) && (b_ < 0 || (b_ == 0 && incl))) ? 1 : 0); } while (0)
     uint32_t nd = 0; { uint64_t t = m; while (t) { nd++; t /= 10; } }
-    if (nd < 16 || nd > 19) return false;
-    for (uint32_t n = 15; n <= 17 && n <= nd; n++) {
+    if (nd < 1 || nd > 19) return false;
+    // a normal double needs at least 15 digits only if the literal has them: start where an answer can first exist
+    for (uint32_t n = 1; n <= 17 && n <= nd; n++) {
         uint32_t p = nd - n;
         uint64_t pw = 1; for (uint32_t i = 0; i < p; i++) pw *= 10;
         uint64_t t = m / pw; int kn = k + (int)p;
-        int in0, in1 = 0;
-        CKF_INSIDE2(in0, t, kn);
+        int in0 = 0, in1 = 0;
+        if (t) CKF_INSIDE2(in0, t, kn);
         if (p > 0) CKF_INSIDE2(in1, t + 1, kn);
         if (in0 == 2 || in1 == 2) return false;
         if (!in0 && !in1) continue;
         uint64_t c = in0 ? t : t + 1;
-        if (n > 15) {
-            // nearest grid point to d: smallest c whose upper midpoint is not below d, then not above its lower midpoint
-            for (int it = 0; it < 24; it++) { int g = ckf_cmp_dec_bin(2 * c + 1, kn, f, e + 1); if (g == 2) return false; if (g < 0) c++; else break; }
-            for (int it = 0; it < 24; it++) { int g = ckf_cmp_dec_bin(2 * c - 1, kn, f, e + 1); if (g == 2) return false; if (g > 0) c--; else break; }
-            uint64_t pick = 0; bool found = false;
-            for (int dlt = 0; dlt < 3 && !found; dlt++) {
-                uint64_t cc = dlt == 0 ? c : (dlt == 1 ? c - 1 : c + 1);
-                if (cc % 10 == 0) continue;                       // a shorter decimal: level n - 1 would have found it
-                uint32_t cd = 0; { uint64_t tt = cc; while (tt) { cd++; tt /= 10; } }
-                if (cd != n) continue;
-                int ins; CKF_INSIDE2(ins, cc, kn);                // it must denote d, not a neighbouring double
-                if (ins == 2) return false;
-                if (ins == 1 && ckf_is_repr(cc, kn)) { pick = cc; found = true; }
-            }
-            if (!found) return false;
-            c = pick;
+        // nearest grid point to d: smallest c whose upper midpoint is not below d, then not above its lower midpoint
+        for (int it = 0; it < 24; it++) { int g = ckf_cmp_dec_bin(2 * c + 1, kn, f, e + 1); if (g == 2) return false; if (g < 0) c++; else break; }
+        for (int it = 0; it < 24 && c > 1; it++) { int g = ckf_cmp_dec_bin(2 * c - 1, kn, f, e + 1); if (g == 2) return false; if (g > 0) c--; else break; }
+        uint64_t pick = 0; int pick_k = kn; bool found = false;
+        for (int dlt = 0; dlt < 3 && !found; dlt++) {
+            uint64_t cc = dlt == 0 ? c : (dlt == 1 ? c - 1 : c + 1);
+            if (cc == 0) continue;
+            int kc = kn;
+            while (cc % 10 == 0) { cc /= 10; kc++; }          // a carry (9 -> 10): the same value with fewer digits
+            uint32_t cd = 0; { uint64_t tt = cc; while (tt) { cd++; tt /= 10; } }
+            if (cd > n) continue;
+            int ins; CKF_INSIDE2(ins, cc, kc);                // it must denote d, not a neighbouring double
+            if (ins == 2) return false;
+            if (ins == 1 && ckf_is_repr(cc, kc)) { pick = cc; pick_k = kc; found = true; }
         }
-        while (c % 10 == 0) { c /= 10; kn++; }
-        ms = c; ks = kn;
+        if (!found) return false;
+        ms = pick; ks = pick_k;
         return true;
     }
     return false;

@@ -582,7 +582,8 @@ CK_HD_NOINLINE u64 ck_number_core(const u8* g, u32 n, u32 pos, u32 st, bool allo
         if (d0 < '1' || d0 > '9') return false;
         u32 x = 0, xl = 0;
         while (p < r.n) { u8 d = r.at(p); if (d < '0' || d > '9') break; x = x * 10 + (u32)(d - '0'); p++; if (++xl > 3) return false; }
-        if (x > 290 || (sg == '-' ? x < 6 : x < 16)) return false;
+        // (second walk, over the canonicaliser's own output: it has decided the extremes exactly, e-324 .. e+308)
+        if (x > (R::kTrustFloats ? (sg == '-' ? 324u : 308u) : 290u) || (sg == '-' ? x < 6 : x < 16)) return false;
         return CK_RET(p);
     }
     if (p < r.n && r.at(p) == 'E') return false;

@@ -155,7 +155,11 @@ def test_long_float_literals_are_respelled_as_the_reference_does():
     base = json.loads(synth.tool_events(1, seed=61)[0])
     lits = ["123456789.123456789", "0.1000000000000000055", "5.6843418860808015e-14", "0.30000000000000004", "1.0000000000000002",
             "123456789012345680.0", "9007199254740993.0", "2.2250738585072014e-280", "0.3000000000000000166", "4.35", "4.3499999999999996447",
-            "1234567890123456789e-5", "72057594037927936.0", "9.999999999999999e22", "1.00000000000000011102230246251565404"]
+            "1234567890123456789e-5", "72057594037927936.0", "9.999999999999999e22", "1.00000000000000011102230246251565404",
+            # the edges: overflow is null, below half the smallest subnormal is zero, subnormals have their own shortest spelling
+            "1e400", "-1e400", "1.7976931348623157e308", "1.7976931348623158e308", "1.797693134862315807e308", "1.797693134862315808e308",
+            "5e-324", "4.9406564584124654e-324", "3e-324", "2.4703282292062327e-324", "2.4703282292062328e-324", "1e-400", "-1e-400",
+            "2.2250738585072014e-308", "2.225073858507201e-308", "2.2250738585072011e-308", "1e-323", "9.8813129168249309e-324", "123e-320"]
     for _ in range(300):
         d = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
         if d != d or abs(d) == float("inf") or abs(d) < 1e-280 or abs(d) > 1e280:

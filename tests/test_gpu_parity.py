@@ -671,8 +671,7 @@ def _murmur2(data: bytes) -> int:
     return h
 
 
-DECLARED_UNSUPPORTED = {"any_numbers": "floats at the overflow / subnormal edge (1e400 -> null, 5e-324, DBL_MAX); long literals in the normal range are re-spelled",
-                        "frame_missing_frame_id": "default_factory field: the reference invents a fresh id"}
+DECLARED_UNSUPPORTED = {"frame_missing_frame_id": "default_factory field: the reference invents a fresh id"}
 
 
 def test_codec_goldens_on_device(engine):
