@@ -731,7 +731,17 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
             if (in.p[b] == '-') b++;
             u32 d0 = b;
             while (cj_isdigit(in.p[b])) b++;
-            if (in.p[b] != '"' || b == d0 || b - d0 > 18 || (in.p[d0] == '0' && b - d0 > 1) || (in.p[a] == '-' && in.p[d0] == '0')) return CE_UNSUP;
+            if (in.p[b] != '"' || b == d0 || b - d0 > 18 || (in.p[d0] == '0' && b - d0 > 1) || (in.p[a] == '-' && in.p[d0] == '0')) {
+                // a string with a character no integer spelling contains ("x", "abc"): int_parsing in the reference; anything made
+                // of digits, signs, separators, exponent letters or blanks only stays undecided
+                for (u32 q = a; in.p[q] != '"'; q++) {
+                    u8 cc = in.p[q];
+                    if (cc == '\\' || cc >= 0x80 || cc < 0x20) return CE_UNSUP;
+                    bool maybe = cj_isdigit(cc) || cc == '+' || cc == '-' || cc == '_' || cc == '.' || cc == ' ' || cc == 'e' || cc == 'E';
+                    if (!maybe) return CE_SCHEMA;
+                }
+                return CE_UNSUP;
+            }
             o.copy(in, a, b);
             return CE_OK;
         }
@@ -842,13 +852,24 @@ CK_HDR int cj_emit_value(CJ& c, u32 pos, u32 type, u32 arg) {
             o.put(':');
             u32 key0 = q;
             q = cj_skip_value(in, q); q = cj_skip_ws(in, q); q++; q = cj_skip_ws(in, q);
-            {   // dict assignment: the value of the LAST member with this key (a 32-bit hash hit is verified on the decoded bytes)
-                u32 scan = cj_skip_ws(in, cj_skip_value(in, q)), lastv = 0;
+            {   // dict assignment: the value of the LAST member with this key (a 32-bit hash hit is verified on the decoded bytes).
+                // The reference validates every member before the assignment: a shadowed value that is not a valid instance
+                // still fails the record (found by the mutation fuzz), so the shadowed ones are emitted into nothing first.
+                u32 scan = cj_skip_ws(in, cj_skip_value(in, q)), lastv = 0, prevv = q;
                 while (in.p[scan] == ',') {
                     scan = cj_skip_ws(in, scan + 1);
                     u32 k2 = scan;
                     scan = cj_skip_ws(in, cj_skip_value(in, scan)); scan++; scan = cj_skip_ws(in, scan);
-                    if (cj_str_hash(in, k2) == h) { if (!cj_keys_equal(in, key0, k2)) return CE_UNSUP; lastv = scan; }
+                    if (cj_str_hash(in, k2) == h) {
+                        if (!cj_keys_equal(in, key0, k2)) return CE_UNSUP;
+                        if (type != T_DICT_TRV) {                                 // (tool_results values fall back to Any: always valid)
+                            u32 save = o.len, sd = c.depth, sh = c.hsp; bool sovf = o.ovf;
+                            int r0 = type == T_DICT_INT ? cj_emit_value(c, prevv, T_INT, 0) : cj_emit_value(c, prevv, T_MODEL, M_TOOLCALL);
+                            o.len = save; o.ovf = sovf; c.depth = sd; c.hsp = sh;
+                            if (r0) return r0;
+                        }
+                        lastv = scan; prevv = scan;
+                    }
                     scan = cj_skip_ws(in, cj_skip_value(in, scan));
                 }
                 cont = q;

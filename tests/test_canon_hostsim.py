@@ -202,3 +202,23 @@ def test_int_fields_given_as_other_number_spellings():
             lit = '"' + lit + '"'
         _check(r[:k0] + lit.encode() + r[k1:], stats)
     assert stats.get(0, 0) > 500 and stats.get(3, 0) > 500
+
+
+def test_shadowed_duplicate_dict_values_are_still_validated():
+    """dict[str, Model]: the reference validates every member before the assignment, so a duplicate key whose EARLIER value is
+    not a valid instance fails the record although the later value replaces it (found by scripts/fuzz_canon.py); for model
+    fields the last one simply wins"""
+    from calfkit import synth
+    r = synth.tool_events(1, seed=5, size=None, full_history=True)[0].decode()
+    k = r.index('"tool_calls":{') + len('"tool_calls":{')
+    key = r[k:r.index('":{', k) + 1]
+    end = r.index('},"tool_results"', k)
+    stats: dict = {}
+    for v in (r[:k] + key + ':{"art_kind":"tool-call"},' + r[k:],                 # invalid value shadowed by the valid one
+              r[:end] + "," + key + ':{"art_kind":"tool-call"}' + r[end:],         # valid value shadowed by the invalid one
+              r[:k] + key + ":" + r[k + len(key) + 1:end] + "," + r[k:],            # the same valid value twice
+              r.replace('"details":{}', '"details":{"a":"x","a":1}', 1),            # dict[str, int] with an invalid shadowed value
+              r.replace('"details":{}', '"details":{"a":1,"a":2}', 1),
+              r.replace('"input_tokens":51', '"input_tokens":"x","input_tokens":51', 1)):   # model field: last wins, no error
+        _check(v.encode(), stats)
+    assert stats == {3: 3, 0: 3}
