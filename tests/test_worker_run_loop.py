@@ -71,7 +71,11 @@ def rig(monkeypatch):
     a = TemplateNode("A", "t.a", "t.b")
     b = TemplateNode("B", "t.b", "t.c")
     pipes = {}
-    monkeypatch.setattr(Worker, "_pipeline", lambda self, node: pipes.setdefault(node.node_id, FakePipe(node)))
+    def _pipeline(self, node):                          # registered where the Worker keeps its pipelines (the final flush looks there)
+        if id(node) not in self._pipes:
+            self._pipes[id(node)] = pipes[node.node_id] = FakePipe(node)
+        return self._pipes[id(node)]
+    monkeypatch.setattr(Worker, "_pipeline", _pipeline)
     return client, client._connection, a, b, pipes
 
 
